@@ -1,0 +1,99 @@
+"""ctypes binding of the C-ABI library (include/echoglad_b200.h).
+
+There is no CPU fallback: if `libechoglad_b200.so` is missing or does not export a declared symbol the
+import raises.  Build it with `python -m echoglad_b200.build` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libechoglad_b200.so")
+
+EG_MAX_LEVELS = 16
+
+
+class GraphSpec(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "frame_size", "num_aux_graphs", "use_main_graph_only", "use_coordinate_graph",
+        "use_connection_nodes", "main_diagonal", "aux_diagonal")]
+
+
+class GraphInfo(C.Structure):
+    _fields_ = [("num_nodes", C.c_int32), ("num_edges", C.c_int32), ("num_pixel_nodes", C.c_int32),
+                ("first_pixel_node", C.c_int32), ("num_coord_nodes", C.c_int32), ("num_levels", C.c_int32),
+                ("level_size", C.c_int32 * EG_MAX_LEVELS), ("level_offset", C.c_int32 * EG_MAX_LEVELS),
+                ("max_degree", C.c_int32), ("crop_offset", C.c_int32)]
+
+
+_P = C.c_void_p
+_I = C.c_int
+_L = C.c_int64
+_F = C.c_float
+_U64 = C.c_uint64
+_SZ = C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol the header declares
+SIGNATURES = {
+    "eg_version": (C.c_char_p, []),
+    "eg_last_error": (C.c_char_p, []),
+    "eg_workspace_bytes": (_SZ, []),
+    "eg_graph_create": (_I, [C.POINTER(GraphSpec), _I, C.POINTER(_P)]),
+    "eg_graph_destroy": (None, [_P]),
+    "eg_graph_get_info": (_I, [_P, C.POINTER(GraphInfo)]),
+    "eg_graph_spec_info": (_I, [C.POINTER(GraphSpec), C.POINTER(GraphInfo)]),
+    "eg_graph_csr": (_I, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "eg_graph_export_edge_index": (_I, [_P, _I, _P, _P]),
+    "eg_graph_host_edge_index": (_I, [C.POINTER(GraphSpec), _I, _P]),
+    "eg_graph_host_node_type": (_I, [C.POINTER(GraphSpec), _I, _P]),
+    "eg_graph_check_edge_index": (_I, [_P, _I, _P, _L, _P, _P]),
+    "eg_pack_nodes": (_I, [_P, _I, C.POINTER(_P), _P, _P, _P, _P]),
+    "eg_pack_nodes_grad": (_I, [_P, _I, _P, C.POINTER(_P), _P, _P, _P]),
+    "eg_gcn_aggregate": (_I, [_P, _I, _I, _P, _P, _P]),
+    "eg_gcn_conv_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "eg_gcn_conv_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "eg_bn_act_fwd": (_I, [_L, _I, _P, _P, _P, _P, _P, _F, _F, _U64, _I, _P, _P, _P]),
+    "eg_bn_act_bwd": (_I, [_L, _I, _P, _P, _P, _P, _P, _P, _F, _F, _U64, _I, _I, _P, _P, _P, _P, _SZ, _P]),
+    "eg_dropout_mask": (_I, [_L, _I, _F, _U64, _P, _P]),
+    "eg_col_stats": (_I, [_L, _I, _P, _P, _P, _P, _SZ, _P]),
+    "eg_linear128": (_I, [_L, _P, _P, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "eg_linear128_wgrad": (_I, [_L, _P, _P, _P, _P, _P, _SZ, _P]),
+    "eg_clf_mid_fwd": (_I, [_L, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "eg_clf_mid_bwd": (_I, [_L, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "eg_clf_out_fwd": (_I, [_L, _P, _P, _P, _I, _P, _P]),
+    "eg_clf_out_bwd": (_I, [_L, _P, _P, _P, _P, _I, _P, _P, _P, _P, _SZ, _P]),
+    "eg_bce_multilevel": (_I, [_L, _P, _P, _P, _F, _F, _P, _P, _P, _SZ, _P]),
+    "eg_expected_landmark_mse": (_I, [_I, _I, _I, C.POINTER(C.c_int32), _P, _P, _P, _F, _P, _P, _P, _SZ, _P]),
+    "eg_node_labels": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int32), _P, _P, _P]),
+}
+
+
+class EchogladError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is mandatory (no CPU fallback). "
+            "Build it with `python -m echoglad_b200.build`.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise ImportError(f"{LIB_PATH} does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+WORKSPACE_BYTES = int(lib.eg_workspace_bytes())
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib.eg_last_error().decode(errors="replace")
+        raise EchogladError(f"{what or 'echoglad_b200'} failed (code {rc}): {msg}")

@@ -1,0 +1,312 @@
+// Classifier tail: the four independent heads of node_classifiers (src/core/models.py:363-377) evaluated
+// together as block-diagonal transforms.  Layer 0 of the four heads is one stacked [128 -> 4x32]
+// tensor-core GEMM (eg_linear128); this file holds layer 4 (4 x [32 -> 16]) and layer 8 (4 x [16 -> 1]).
+// The BN/ReLU/Dropout between them is eg_bn_act_* with cols = 128 / 64.
+#include "common.cuh"
+
+using namespace eg;
+
+namespace {
+
+constexpr int kMidThreads = 128;  // warp k <-> head k, lane <-> row of the 32-row tile
+constexpr int TR = 32;
+constexpr int LDA = 132;          // A1 tile stride
+constexpr int LDO = 68;           // Z2 tile stride
+
+// Z2[r][16k+j] = b2[k][j] + sum_i A1[r][32k+i] * W2[k][j][i]
+__global__ void __launch_bounds__(kMidThreads)
+clf_mid_fwd_kernel(long long rows, const float* __restrict__ A1, const float* __restrict__ W2,
+                   const float* __restrict__ b2, float* __restrict__ Z2, double* __restrict__ parts) {
+  __shared__ __align__(16) float As[TR * LDA];
+  __shared__ __align__(16) float Ws[4 * 16 * 32];
+  __shared__ __align__(16) float Os[TR * LDO];
+  __shared__ float bs[64];
+  const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
+  for (int i = tid; i < 2048; i += kMidThreads) Ws[i] = __ldg(W2 + i);
+  if (tid < 64) bs[tid] = __ldg(b2 + tid);
+  double run_sum = 0.0, run_sq = 0.0;  // thread c < 64 owns column c
+  const long long ntiles = (rows + TR - 1) / TR;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * TR;
+    const int nvalid = (int)min((long long)TR, rows - row0);
+    __syncthreads();  // previous tile fully consumed (also orders the Ws/bs fill)
+    for (int i = tid; i < TR * 32; i += kMidThreads) {
+      int r = i >> 5, c4 = i & 31;
+      float4 v = r < nvalid ? ldg4(A1 + (row0 + r) * 128 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(As + r * LDA + c4 * 4) = v;
+    }
+    __syncthreads();
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = bs[k * 16 + j];
+#pragma unroll
+    for (int i4 = 0; i4 < 8; ++i4) {
+      const float4 a = *reinterpret_cast<const float4*>(As + lane * LDA + k * 32 + i4 * 4);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(Ws + (k * 16 + j) * 32 + i4 * 4);
+        acc[j] = fmaf(a.x, w.x, acc[j]);
+        acc[j] = fmaf(a.y, w.y, acc[j]);
+        acc[j] = fmaf(a.z, w.z, acc[j]);
+        acc[j] = fmaf(a.w, w.w, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(Os + lane * LDO + k * 16 + q * 4) =
+          make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    __syncthreads();
+    for (int i = tid; i < TR * 16; i += kMidThreads) {
+      int r = i >> 4, c4 = i & 15;
+      if (r < nvalid) st4(Z2 + (row0 + r) * 64 + c4 * 4, *reinterpret_cast<const float4*>(Os + r * LDO + c4 * 4));
+    }
+    if (parts && tid < 64) {
+      float s = 0.f, q = 0.f;
+      for (int r = 0; r < nvalid; ++r) {
+        float v = Os[r * LDO + tid];
+        s += v;
+        q = fmaf(v, v, q);
+      }
+      run_sum += (double)s;
+      run_sq += (double)q;
+    }
+  }
+  if (parts && tid < 64) {
+    parts[(size_t)blockIdx.x * 128 + tid] = run_sum;
+    parts[(size_t)blockIdx.x * 128 + 64 + tid] = run_sq;
+  }
+}
+
+// dA1[r][32k+i] = sum_j dZ2[r][16k+j] W2[k][j][i];  per-block partials of dW2[k][j][i], db2[k][j].
+constexpr int kMidPart = 2048 + 64;
+__global__ void __launch_bounds__(kMidThreads)
+clf_mid_bwd_kernel(long long rows, const float* __restrict__ A1, const float* __restrict__ W2,
+                   const float* __restrict__ dZ2, float* __restrict__ dA1, float* __restrict__ parts) {
+  __shared__ __align__(16) float As[TR * LDA];   // A1 tile, then reused for the dA1 tile
+  __shared__ __align__(16) float Ws[4 * 16 * 32];
+  __shared__ __align__(16) float Gs[TR * LDO];   // dZ2 tile
+  const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
+  for (int i = tid; i < 2048; i += kMidThreads) Ws[i] = __ldg(W2 + i);
+  float wacc[16];  // dW2[k][j][lane]
+#pragma unroll
+  for (int j = 0; j < 16; ++j) wacc[j] = 0.f;
+  float bacc = 0.f;  // db2[k][lane] for lane < 16
+  const long long ntiles = (rows + TR - 1) / TR;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * TR;
+    const int nvalid = (int)min((long long)TR, rows - row0);
+    __syncthreads();
+    for (int i = tid; i < TR * 32; i += kMidThreads) {
+      int r = i >> 5, c4 = i & 31;
+      float4 v = r < nvalid ? ldg4(A1 + (row0 + r) * 128 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(As + r * LDA + c4 * 4) = v;
+    }
+    for (int i = tid; i < TR * 16; i += kMidThreads) {
+      int r = i >> 4, c4 = i & 15;
+      float4 v = r < nvalid ? ldg4(dZ2 + (row0 + r) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(Gs + r * LDO + c4 * 4) = v;
+    }
+    __syncthreads();
+    // weight / bias gradient: lane <-> input feature i
+#pragma unroll 4
+    for (int r = 0; r < TR; ++r) {
+      const float a = As[r * LDA + k * 32 + lane];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 gz = *reinterpret_cast<const float4*>(Gs + r * LDO + k * 16 + q * 4);
+        wacc[4 * q] = fmaf(gz.x, a, wacc[4 * q]);
+        wacc[4 * q + 1] = fmaf(gz.y, a, wacc[4 * q + 1]);
+        wacc[4 * q + 2] = fmaf(gz.z, a, wacc[4 * q + 2]);
+        wacc[4 * q + 3] = fmaf(gz.w, a, wacc[4 * q + 3]);
+      }
+      if (lane < 16) bacc += Gs[r * LDO + k * 16 + lane];
+    }
+    // input gradient: lane <-> row
+    float dz[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 gz = *reinterpret_cast<const float4*>(Gs + lane * LDO + k * 16 + q * 4);
+      dz[4 * q] = gz.x; dz[4 * q + 1] = gz.y; dz[4 * q + 2] = gz.z; dz[4 * q + 3] = gz.w;
+    }
+    __syncthreads();  // everyone is done reading the A1 tile -> reuse As for dA1
+#pragma unroll
+    for (int i4 = 0; i4 < 8; ++i4) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(Ws + (k * 16 + j) * 32 + i4 * 4);
+        o.x = fmaf(dz[j], w.x, o.x);
+        o.y = fmaf(dz[j], w.y, o.y);
+        o.z = fmaf(dz[j], w.z, o.z);
+        o.w = fmaf(dz[j], w.w, o.w);
+      }
+      *reinterpret_cast<float4*>(As + lane * LDA + k * 32 + i4 * 4) = o;
+    }
+    __syncthreads();
+    for (int i = tid; i < TR * 32; i += kMidThreads) {
+      int r = i >> 5, c4 = i & 31;
+      if (r < nvalid) st4(dA1 + (row0 + r) * 128 + c4 * 4, *reinterpret_cast<const float4*>(As + r * LDA + c4 * 4));
+    }
+  }
+  float* P = parts + (size_t)blockIdx.x * kMidPart;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) P[(k * 16 + j) * 32 + lane] = wacc[j];
+  if (lane < 16) P[2048 + k * 16 + lane] = bacc;
+}
+
+__global__ void parts_reduce_kernel(int nparts, int width, const float* __restrict__ parts, int n_a,
+                                    float* __restrict__ out_a, float* __restrict__ out_b) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= width) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += (double)parts[(size_t)p * width + i];
+  if (i < n_a) out_a[i] = (float)s; else if (out_b) out_b[i - n_a] = (float)s;
+}
+
+// logits[r][k] = b3[k] + sum_j A2[r][16k+j] W3[k][j]      (16 lanes per row, one float4 each)
+__global__ void __launch_bounds__(256)
+clf_out_fwd_kernel(long long rows, const float* __restrict__ A2, const float* __restrict__ W3,
+                   const float* __restrict__ b3, int sigmoid, float* __restrict__ out) {
+  const int q = threadIdx.x & 15, half = (threadIdx.x >> 4) & 1;
+  const float4 w = ldg4(W3 + q * 4);
+  const float4 b = ldg4(b3);
+  const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r0 = warp_id * 2; r0 < rows; r0 += nwarps * 2) {  // warp-uniform trip count
+    const long long r = r0 + half;
+    const bool valid = r < rows;
+    const float4 a = valid ? ldg4(A2 + r * 64 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float p = a.x * w.x;
+    p = fmaf(a.y, w.y, p);
+    p = fmaf(a.z, w.z, p);
+    p = fmaf(a.w, w.w, p);
+    p += __shfl_xor_sync(0xffffffffu, p, 1);
+    p += __shfl_xor_sync(0xffffffffu, p, 2);
+    const int base = half * 16;  // first lane of this half warp
+    float l0 = __shfl_sync(0xffffffffu, p, base + 0), l1 = __shfl_sync(0xffffffffu, p, base + 4);
+    float l2 = __shfl_sync(0xffffffffu, p, base + 8), l3 = __shfl_sync(0xffffffffu, p, base + 12);
+    if (q == 0 && valid) {
+      float4 o = make_float4(l0 + b.x, l1 + b.y, l2 + b.z, l3 + b.w);
+      if (sigmoid) {
+        o.x = 1.f / (1.f + expf(-o.x)); o.y = 1.f / (1.f + expf(-o.y));
+        o.z = 1.f / (1.f + expf(-o.z)); o.w = 1.f / (1.f + expf(-o.w));
+      }
+      st4(out + r * 4, o);
+    }
+  }
+}
+
+// dA2[r][16k+j] = dz[r][k] W3[k][j]; partial sums of dW3[k][j] = sum_r dz A2, db3[k] = sum_r dz.
+// Block = 16 column groups x 16 row lanes.
+constexpr int kOutPart = 64 + 4;
+__global__ void __launch_bounds__(256)
+clf_out_bwd_kernel(long long rows, const float* __restrict__ A2, const float* __restrict__ W3,
+                   const float* __restrict__ out, const float* __restrict__ dout, int sigmoid,
+                   float* __restrict__ dA2, float* __restrict__ parts) {
+  __shared__ float red[256 * 5];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int k = tx >> 2;
+  const float4 w = ldg4(W3 + tx * 4);
+  float4 sw = make_float4(0.f, 0.f, 0.f, 0.f);
+  float sb = 0.f;
+  for (long long r = (long long)blockIdx.x * 16 + ty; r < rows; r += (long long)gridDim.x * 16) {
+    float dz = __ldg(dout + r * 4 + k);
+    if (sigmoid) {
+      float s = __ldg(out + r * 4 + k);
+      dz *= s * (1.f - s);
+    }
+    const float4 a = ldg4(A2 + r * 64 + tx * 4);
+    st4(dA2 + r * 64 + tx * 4, make_float4(dz * w.x, dz * w.y, dz * w.z, dz * w.w));
+    sw.x = fmaf(dz, a.x, sw.x); sw.y = fmaf(dz, a.y, sw.y);
+    sw.z = fmaf(dz, a.z, sw.z); sw.w = fmaf(dz, a.w, sw.w);
+    sb += dz;
+  }
+  float* my = red + threadIdx.x * 5;
+  my[0] = sw.x; my[1] = sw.y; my[2] = sw.z; my[3] = sw.w; my[4] = sb;
+  __syncthreads();
+  if (threadIdx.x < 64) {  // column c = threadIdx.x
+    const int gx = threadIdx.x >> 2, kk = threadIdx.x & 3;
+    float s = 0.f;
+    for (int y = 0; y < 16; ++y) s += red[(y * 16 + gx) * 5 + kk];
+    parts[(size_t)blockIdx.x * kOutPart + threadIdx.x] = s;
+  } else if (threadIdx.x < 68) {
+    const int kk = threadIdx.x - 64;
+    float s = 0.f;
+    for (int y = 0; y < 16; ++y) s += red[(y * 16 + kk * 4) * 5 + 4];
+    parts[(size_t)blockIdx.x * kOutPart + threadIdx.x] = s;
+  }
+}
+
+}  // namespace
+
+namespace eg {
+int launch_stats_finalize(int nparts, int cols, int stride, long long rows, const double* parts, float* mean,
+                          float* var, cudaStream_t s);
+}
+
+extern "C" {
+
+int eg_clf_mid_fwd(int64_t rows, const float* A1, const float* W2, const float* b2, float* Z2, float* mean,
+                   float* var, void* ws, size_t ws_bytes, void* stream) {
+  EG_CHECK_ARG(rows >= 1 && A1 && W2 && b2 && Z2, "eg_clf_mid_fwd: NULL argument");
+  const bool stats = mean && var;
+  if (stats && (!ws || ws_bytes < kWorkspaceBytes)) {
+    set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
+    return EG_ERR_WORKSPACE;
+  }
+  long long ntiles = (rows + TR - 1) / TR;
+  int grid = (int)(ntiles < kMaxParts ? ntiles : kMaxParts);
+  double* parts = stats ? reinterpret_cast<double*>(ws) : nullptr;
+  clf_mid_fwd_kernel<<<grid, kMidThreads, 0, as_stream(stream)>>>(rows, A1, W2, b2, Z2, parts);
+  EG_LAUNCH_CHECK();
+  if (stats) return launch_stats_finalize(grid, 64, 64, rows, parts, mean, var, as_stream(stream));
+  return EG_OK;
+}
+
+int eg_clf_mid_bwd(int64_t rows, const float* A1, const float* W2, const float* dZ2, float* dA1, float* dW2,
+                   float* db2, void* ws, size_t ws_bytes, void* stream) {
+  EG_CHECK_ARG(rows >= 1 && A1 && W2 && dZ2 && dA1 && dW2 && db2, "eg_clf_mid_bwd: NULL argument");
+  if (!ws || ws_bytes < kWorkspaceBytes) {
+    set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
+    return EG_ERR_WORKSPACE;
+  }
+  long long ntiles = (rows + TR - 1) / TR;
+  int grid = (int)(ntiles < kMaxParts ? ntiles : kMaxParts);
+  float* parts = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);
+  clf_mid_bwd_kernel<<<grid, kMidThreads, 0, as_stream(stream)>>>(rows, A1, W2, dZ2, dA1, parts);
+  EG_LAUNCH_CHECK();
+  parts_reduce_kernel<<<(kMidPart + 255) / 256, 256, 0, as_stream(stream)>>>(grid, kMidPart, parts, 2048, dW2, db2);
+  EG_LAUNCH_CHECK();
+  return EG_OK;
+}
+
+int eg_clf_out_fwd(int64_t rows, const float* A2, const float* W3, const float* b3, int sigmoid, float* out,
+                   void* stream) {
+  EG_CHECK_ARG(rows >= 1 && A2 && W3 && b3 && out, "eg_clf_out_fwd: NULL argument");
+  long long blocks = (rows * 16 + 255) / 256;
+  long long cap = (long long)kNumSMs * 16;
+  int grid = (int)(blocks < cap ? blocks : cap);
+  clf_out_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(rows, A2, W3, b3, sigmoid, out);
+  EG_LAUNCH_CHECK();
+  return EG_OK;
+}
+
+int eg_clf_out_bwd(int64_t rows, const float* A2, const float* W3, const float* out, const float* dout,
+                   int sigmoid, float* dA2, float* dW3, float* db3, void* ws, size_t ws_bytes, void* stream) {
+  EG_CHECK_ARG(rows >= 1 && A2 && W3 && dout && dA2 && dW3 && db3, "eg_clf_out_bwd: NULL argument");
+  EG_CHECK_ARG(!sigmoid || out, "eg_clf_out_bwd: sigmoid head needs the forward output");
+  if (!ws || ws_bytes < kWorkspaceBytes) {
+    set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
+    return EG_ERR_WORKSPACE;
+  }
+  long long blocks = (rows + 15) / 16;
+  int grid = (int)(blocks < kMaxParts ? blocks : kMaxParts);
+  float* parts = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);
+  clf_out_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(rows, A2, W3, out, dout, sigmoid, dA2, parts);
+  EG_LAUNCH_CHECK();
+  parts_reduce_kernel<<<1, 128, 0, as_stream(stream)>>>(grid, kOutPart, parts, 64, dW3, db3);
+  EG_LAUNCH_CHECK();
+  return EG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// Shared helpers for the echoglad_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/echoglad_b200.h"
+
+namespace eg {
+
+void set_error(const char* fmt, ...);
+
+#define EG_CHECK_ARG(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      eg::set_error(__VA_ARGS__);               \
+      return EG_ERR_INVALID;                    \
+    }                                           \
+  } while (0)
+
+#define EG_CUDA(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      eg::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return EG_ERR_CUDA;                                                                   \
+    }                                                                                       \
+  } while (0)
+
+#define EG_LAUNCH_CHECK() EG_CUDA(cudaGetLastError())
+
+constexpr int kNumSMs = 148;            // B200
+constexpr int kMaxParts = 4 * kNumSMs;  // upper bound on per-CTA partial slots of any reduction
+// workspace: [kMaxParts][2][128] doubles for column statistics + [kNumSMs][128*128] floats for the
+// weight-gradient partials + slack
+constexpr size_t kStatsBytes = (size_t)kMaxParts * 2 * 128 * sizeof(double);
+constexpr size_t kWgradBytes = (size_t)kNumSMs * 128 * 128 * sizeof(float);
+constexpr size_t kWorkspaceBytes = kStatsBytes + kWgradBytes + 65536;
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- counter-based dropout RNG: one 64-bit mix per group of 4 consecutive elements -----------------
+// keep(element e) <=> 16-bit lane of mix(seed, e/4) >= p * 65536.  Stateless, so backward recomputes it.
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
+  float t = p * 65536.0f;
+  return t <= 0.f ? 0u : (t >= 65536.f ? 65536u : (uint32_t)t);
+}
+// returns 4 keep-flags (bit i = element 4*group+i kept)
+__host__ __device__ __forceinline__ uint32_t drop_keep4(uint64_t seed, uint64_t group, uint32_t thr) {
+  uint64_t r = mix64(seed ^ (group * 0x9e3779b97f4a7c15ULL));
+  uint32_t k = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) k |= (((uint32_t)(r >> (16 * i)) & 0xffffu) >= thr ? 1u : 0u) << i;
+  return k;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// streaming (evict-first) 128-bit store for outputs that are not re-read by this kernel
+__device__ __forceinline__ void st4_stream(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
+}  // namespace eg

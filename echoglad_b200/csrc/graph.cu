@@ -1,0 +1,310 @@
+// Static hierarchical graph: closed-form CSR built once on the device, plus the exports that prove
+// bit-exactness against the reference's networkx/PyG edge_index (src/core/datasets.py:375-521, :258).
+#include <cub/device/device_scan.cuh>
+
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "topology.cuh"
+
+namespace eg {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace eg
+
+struct eg_graph {
+  eg_graph_spec spec;
+  eg::Topo topo;
+  eg_graph_info info;
+  int device;
+  int nnz;
+  int32_t* rowptr;  // [N+1]
+  int32_t* col;     // [nnz]   sources, ascending, self loop last
+  float* w;         // [nnz]   dis[src]*dis[dst]
+  float* dis;       // [N]
+};
+
+using namespace eg;
+
+namespace {
+
+__global__ void degree_kernel(Topo t, int32_t* __restrict__ deg1, float* __restrict__ dis) {
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= t.N) return;
+  int d = degree_of(t, u) + 1;  // + GCN self loop (PyG add_remaining_self_loops)
+  deg1[u] = d;
+  // PyG: deg.pow(-0.5) in fp32; evaluate in double and round once (deg is a small integer)
+  dis[u] = (float)(1.0 / sqrt((double)d));
+}
+
+__global__ void fill_kernel(Topo t, const int32_t* __restrict__ rowptr, const float* __restrict__ dis,
+                            int32_t* __restrict__ col, float* __restrict__ w) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= t.N) return;
+  int e = rowptr[v];
+  const float dv = dis[v];
+  for_each_neighbor(t, v, true, [&](int u) {
+    col[e] = u;
+    w[e] = dis[u] * dv;  // gcn_norm: deg_inv_sqrt[row] * 1 * deg_inv_sqrt[col]
+    ++e;
+  });
+  col[e] = v;
+  w[e] = dv * dv;
+}
+
+__global__ void export_kernel(Topo t, const int32_t* __restrict__ rowptr, int E, int batch,
+                              int64_t* __restrict__ out) {
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)batch * t.N) return;
+  int b = (int)(gid / t.N), v = (int)(gid % t.N);
+  long long cols = (long long)batch * E;
+  long long e = (long long)b * E + (rowptr[v] - v);
+  long long base = (long long)b * t.N;
+  for_each_neighbor(t, v, false, [&](int u) {
+    out[e] = base + v;
+    out[cols + e] = base + u;
+    ++e;
+  });
+}
+
+__global__ void check_kernel(Topo t, const int32_t* __restrict__ rowptr, int E, int batch,
+                             const int64_t* __restrict__ ei, int32_t* __restrict__ mismatch) {
+  long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)batch * t.N) return;
+  int b = (int)(gid / t.N), v = (int)(gid % t.N);
+  long long cols = (long long)batch * E;
+  long long e = (long long)b * E + (rowptr[v] - v);
+  long long base = (long long)b * t.N;
+  int bad = 0;
+  for_each_neighbor(t, v, false, [&](int u) {
+    bad += (ei[e] != base + v) + (ei[cols + e] != base + u);
+    ++e;
+  });
+  if (bad) atomicAdd(mismatch, bad);
+}
+
+__global__ void set_int_kernel(int32_t* p, int32_t v) { *p = v; }
+
+void fill_info(const Topo& t, eg_graph_info* info, int num_edges, int max_degree) {
+  memset(info, 0, sizeof(*info));
+  info->num_nodes = t.N;
+  info->num_edges = num_edges;
+  info->num_pixel_nodes = t.N0;
+  info->first_pixel_node = t.nconn;
+  info->num_coord_nodes = t.ncoord;
+  info->num_levels = t.nlev;
+  for (int l = 0; l < t.nlev; ++l) {
+    info->level_size[l] = t.lsize[l];
+    info->level_offset[l] = t.loff[l];
+  }
+  info->max_degree = max_degree;
+  info->crop_offset = t.crop;
+}
+
+int init_topo(const eg_graph_spec* spec, Topo& t) {
+  if (!spec) {
+    set_error("spec is NULL");
+    return EG_ERR_INVALID;
+  }
+  int rc = topo_init(t, *spec);
+  if (rc == -2) {
+    set_error("unsupported spec: 2^num_aux_graphs (%d) < frame_size/2 (%d); the reference builds a "
+              "malformed centre crop for it (src/core/datasets.py:502)", 1 << spec->num_aux_graphs,
+              spec->frame_size / 2);
+    return EG_ERR_UNSUPPORTED;
+  }
+  if (rc != 0) {
+    set_error("invalid graph spec (frame_size=%d, num_aux_graphs=%d)", spec->frame_size, spec->num_aux_graphs);
+    return EG_ERR_INVALID;
+  }
+  return EG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* eg_version(void) { return "echoglad_b200 0.1 (sm_100a)"; }
+const char* eg_last_error(void) { return eg::g_err; }
+size_t eg_workspace_bytes(void) { return eg::kWorkspaceBytes; }
+
+int eg_graph_spec_info(const eg_graph_spec* spec, eg_graph_info* info) {
+  Topo t;
+  int rc = init_topo(spec, t);
+  if (rc) return rc;
+  EG_CHECK_ARG(info, "info is NULL");
+  long long e = 0;
+  int maxd = 0;
+  for (int u = 0; u < t.N; ++u) {
+    int d = degree_of(t, u);
+    e += d;
+    if (d + 1 > maxd) maxd = d + 1;
+  }
+  fill_info(t, info, (int)e, maxd);
+  return EG_OK;
+}
+
+int eg_graph_host_edge_index(const eg_graph_spec* spec, int batch, int64_t* out) {
+  Topo t;
+  int rc = init_topo(spec, t);
+  if (rc) return rc;
+  EG_CHECK_ARG(out && batch >= 1, "bad arguments");
+  long long E = 0;
+  for (int u = 0; u < t.N; ++u) E += degree_of(t, u);
+  long long cols = E * batch, e = 0;
+  for (int b = 0; b < batch; ++b) {
+    long long base = (long long)b * t.N;
+    for (int v = 0; v < t.N; ++v)
+      for_each_neighbor(t, v, false, [&](int u) {
+        out[e] = base + v;
+        out[cols + e] = base + u;
+        ++e;
+      });
+  }
+  return EG_OK;
+}
+
+int eg_graph_host_node_type(const eg_graph_spec* spec, int batch, double* out) {
+  Topo t;
+  int rc = init_topo(spec, t);
+  if (rc) return rc;
+  EG_CHECK_ARG(out && batch >= 1, "bad arguments");
+  for (int b = 0; b < batch; ++b)
+    for (int v = 0; v < t.N; ++v)
+      out[(size_t)b * t.N + v] = v < t.nconn ? 2.0 : (v >= t.N - t.ncoord ? 1.0 : 0.0);
+  return EG_OK;
+}
+
+int eg_graph_create(const eg_graph_spec* spec, int device, eg_graph** out) {
+  Topo t;
+  int rc = init_topo(spec, t);
+  if (rc) return rc;
+  EG_CHECK_ARG(out, "out is NULL");
+  int prev = 0;
+  EG_CUDA(cudaGetDevice(&prev));
+  EG_CUDA(cudaSetDevice(device));
+  eg_graph* g = new eg_graph();
+  g->spec = *spec;
+  g->topo = t;
+  g->device = device;
+  int32_t* deg = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  auto fail = [&](int code) {
+    cudaFree(deg);
+    cudaFree(tmp);
+    eg_graph_destroy(g);
+    cudaSetDevice(prev);
+    return code;
+  };
+#define EG_TRY(call)                                                                         \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      set_error("%s failed: %s", #call, cudaGetErrorString(_e));                             \
+      return fail(EG_ERR_CUDA);                                                              \
+    }                                                                                        \
+  } while (0)
+  EG_TRY(cudaMalloc(&g->rowptr, sizeof(int32_t) * (t.N + 1)));
+  EG_TRY(cudaMalloc(&g->dis, sizeof(float) * t.N));
+  EG_TRY(cudaMalloc(&deg, sizeof(int32_t) * (t.N + 1)));
+  EG_TRY(cudaMemset(deg, 0, sizeof(int32_t) * (t.N + 1)));
+  const int threads = 128, blocks = (t.N + threads - 1) / threads;
+  degree_kernel<<<blocks, threads>>>(t, deg, g->dis);
+  EG_TRY(cudaGetLastError());
+  EG_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, deg, g->rowptr, t.N + 1));
+  EG_TRY(cudaMalloc(&tmp, tmp_bytes));
+  EG_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, deg, g->rowptr, t.N + 1));
+  int32_t nnz = 0;
+  EG_TRY(cudaMemcpy(&nnz, g->rowptr + t.N, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  g->nnz = nnz;
+  EG_TRY(cudaMalloc(&g->col, sizeof(int32_t) * nnz));
+  EG_TRY(cudaMalloc(&g->w, sizeof(float) * nnz));
+  fill_kernel<<<blocks, threads>>>(t, g->rowptr, g->dis, g->col, g->w);
+  EG_TRY(cudaGetLastError());
+  std::vector<int32_t> hdeg(t.N);
+  EG_TRY(cudaMemcpy(hdeg.data(), deg, sizeof(int32_t) * t.N, cudaMemcpyDeviceToHost));
+  int maxd = 0;
+  for (int d : hdeg) maxd = d > maxd ? d : maxd;
+  fill_info(t, &g->info, nnz - t.N, maxd);
+  EG_TRY(cudaDeviceSynchronize());
+#undef EG_TRY
+  cudaFree(deg);
+  cudaFree(tmp);
+  cudaSetDevice(prev);
+  *out = g;
+  return EG_OK;
+}
+
+void eg_graph_destroy(eg_graph* g) {
+  if (!g) return;
+  cudaFree(g->rowptr);
+  cudaFree(g->col);
+  cudaFree(g->w);
+  cudaFree(g->dis);
+  delete g;
+}
+
+int eg_graph_get_info(const eg_graph* g, eg_graph_info* info) {
+  EG_CHECK_ARG(g && info, "NULL argument");
+  *info = g->info;
+  return EG_OK;
+}
+
+int eg_graph_csr(const eg_graph* g, const int32_t** rowptr, const int32_t** col, const float** w,
+                 const float** dis) {
+  EG_CHECK_ARG(g, "graph is NULL");
+  if (rowptr) *rowptr = g->rowptr;
+  if (col) *col = g->col;
+  if (w) *w = g->w;
+  if (dis) *dis = g->dis;
+  return EG_OK;
+}
+
+int eg_graph_export_edge_index(const eg_graph* g, int batch, int64_t* out, void* stream) {
+  EG_CHECK_ARG(g && out && batch >= 1, "bad arguments");
+  long long total = (long long)batch * g->topo.N;
+  const int threads = 128;
+  export_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, as_stream(stream)>>>(
+      g->topo, g->rowptr, g->info.num_edges, batch, out);
+  EG_LAUNCH_CHECK();
+  return EG_OK;
+}
+
+int eg_graph_check_edge_index(const eg_graph* g, int batch, const int64_t* edge_index, int64_t num_cols,
+                              int32_t* mismatch, void* stream) {
+  EG_CHECK_ARG(g && edge_index && mismatch && batch >= 1, "bad arguments");
+  cudaStream_t s = as_stream(stream);
+  if (num_cols != (int64_t)batch * g->info.num_edges) {
+    set_int_kernel<<<1, 1, 0, s>>>(mismatch, -1);
+    EG_LAUNCH_CHECK();
+    return EG_OK;
+  }
+  set_int_kernel<<<1, 1, 0, s>>>(mismatch, 0);
+  long long total = (long long)batch * g->topo.N;
+  const int threads = 128;
+  check_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
+      g->topo, g->rowptr, g->info.num_edges, batch, edge_index, mismatch);
+  EG_LAUNCH_CHECK();
+  return EG_OK;
+}
+
+}  // extern "C"
+
+// accessors for the other translation units
+namespace eg {
+const Topo& graph_topo(const eg_graph* g) { return g->topo; }
+const eg_graph_info& graph_info(const eg_graph* g) { return g->info; }
+const int32_t* graph_rowptr(const eg_graph* g) { return g->rowptr; }
+const int32_t* graph_col(const eg_graph* g) { return g->col; }
+const float* graph_w(const eg_graph* g) { return g->w; }
+const float* graph_dis(const eg_graph* g) { return g->dis; }
+int graph_nnz(const eg_graph* g) { return g->nnz; }
+}  // namespace eg

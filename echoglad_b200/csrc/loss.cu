@@ -1,0 +1,342 @@
+// Multi-level losses, forward + gradient in fused passes, no host round trips.
+//  * eg_bce_multilevel        replaces WeightedBCEWithLogitsLoss.compute (src/core/criterion.py:13-27,30-34)
+//    which builds its weight tensor on the host through numpy (2 D2H + 1 H2D per step).
+//  * eg_expected_landmark_mse replaces ExpectedLandmarkMSE.compute (src/core/criterion.py:93-151), ~15 small
+//    kernels per level in the reference.
+//  * eg_node_labels           replaces create_node_labels (src/core/datasets.py:523-549).
+#include "common.cuh"
+
+using namespace eg;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];  // fixed order
+  return t;
+}
+
+// ---- BCE ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bce_elem(float x, float y, float v, float ones_weight, float& loss, float& grad) {
+  const float w = (ones_weight > 1.f && y == 1.f) ? ones_weight : 1.f;
+  const float e = expf(-fabsf(x));
+  const float l = fmaxf(x, 0.f) - x * y + log1pf(e);
+  const float sig = x >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+  loss = v * w * l;
+  grad = v * w * (sig - y);
+}
+
+__global__ void __launch_bounds__(kThreads)
+bce_kernel(long long n4, long long n, const float* __restrict__ x, const float* __restrict__ y,
+           const float* __restrict__ valid, float ones_weight, float* __restrict__ grad,
+           double* __restrict__ parts) {
+  __shared__ double sh[8];
+  double num = 0.0, den = 0.0;
+  float fnum = 0.f, fden = 0.f;
+  int cnt = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float xv[4], yv[4], vv[4], gv[4];
+    if (i * 4 + 3 < n) {
+      float4 a = ldg4(x + i * 4), b = ldg4(y + i * 4), c = ldg4(valid + i * 4);
+      xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w;
+      yv[0] = b.x; yv[1] = b.y; yv[2] = b.z; yv[3] = b.w;
+      vv[0] = c.x; vv[1] = c.y; vv[2] = c.z; vv[3] = c.w;
+    } else {
+      for (int k = 0; k < 4; ++k) {
+        bool ok = i * 4 + k < n;
+        xv[k] = ok ? x[i * 4 + k] : 0.f;
+        yv[k] = ok ? y[i * 4 + k] : 0.f;
+        vv[k] = ok ? valid[i * 4 + k] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float l;
+      bce_elem(xv[k], yv[k], vv[k], ones_weight, l, gv[k]);
+      fnum += l;
+      fden += vv[k];
+    }
+    if (grad) {
+      if (i * 4 + 3 < n) st4(grad + i * 4, make_float4(gv[0], gv[1], gv[2], gv[3]));
+      else for (int k = 0; k < 4; ++k) if (i * 4 + k < n) grad[i * 4 + k] = gv[k];
+    }
+    if (++cnt == 16) { num += fnum; den += fden; fnum = fden = 0.f; cnt = 0; }
+  }
+  num += fnum; den += fden;
+  num = block_sum(num, sh);
+  den = block_sum(den, sh);
+  if (threadIdx.x == 0) {
+    parts[(size_t)blockIdx.x * 2] = num;
+    parts[(size_t)blockIdx.x * 2 + 1] = den;
+  }
+}
+
+__global__ void bce_finalize_kernel(int nparts, const double* __restrict__ parts, float loss_weight,
+                                    float* __restrict__ loss_out, float* __restrict__ scale_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double num = 0.0, den = 0.0;
+  for (int p = 0; p < nparts; ++p) { num += parts[2 * p]; den += parts[2 * p + 1]; }
+  *loss_out = (float)((double)loss_weight * num / den);
+  *scale_out = (float)((double)loss_weight / den);
+}
+
+__global__ void __launch_bounds__(kThreads)
+scale_kernel(long long n, float* __restrict__ g, const float* __restrict__ scale) {
+  const float s = __ldg(scale);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) g[i] *= s;
+}
+
+// ---- expected-landmark MSE (channels == 4: one float4 per node) ------------------------------------------
+struct SegStat {  // per (frame, level)
+  float e_h[4], e_w[4], gt_h[4], gt_w[4], v[4], xmax[4], sumexp[4], c_h[4], c_w[4];
+};
+
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float t = sh[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = fmaxf(t, sh[w]);
+  return t;
+}
+__device__ __forceinline__ int block_min(int v, int* sh) {
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  int t = sh[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = min(t, sh[w]);
+  return t;
+}
+
+struct Levels {
+  int n;
+  int size[EG_MAX_LEVELS];
+  int start[EG_MAX_LEVELS];
+  int total;
+};
+
+// grid = batch * levels; block handles one level of one frame, all 4 channels.
+__global__ void __launch_bounds__(kThreads)
+elmse_stats_kernel(Levels lv, const float* __restrict__ x, const float* __restrict__ y,
+                   const float* __restrict__ valid, SegStat* __restrict__ seg) {
+  __shared__ double shd[8];
+  __shared__ float shf[8];
+  __shared__ int shi[8];
+  const int b = blockIdx.x / lv.n, l = blockIdx.x % lv.n;
+  const int g = lv.size[l], n = g * g;
+  const long long base = ((long long)b * lv.total + lv.start[l]) * 4;
+  float xm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  float ym[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  float vs[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float4 a = ldg4(x + base + (long long)i * 4), c = ldg4(y + base + (long long)i * 4);
+    float4 d = ldg4(valid + base + (long long)i * 4);
+    xm[0] = fmaxf(xm[0], a.x); xm[1] = fmaxf(xm[1], a.y); xm[2] = fmaxf(xm[2], a.z); xm[3] = fmaxf(xm[3], a.w);
+    ym[0] = fmaxf(ym[0], c.x); ym[1] = fmaxf(ym[1], c.y); ym[2] = fmaxf(ym[2], c.z); ym[3] = fmaxf(ym[3], c.w);
+    vs[0] += d.x; vs[1] += d.y; vs[2] += d.z; vs[3] += d.w;
+  }
+  double vsum[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    xm[k] = block_max(xm[k], shf);
+    ym[k] = block_max(ym[k], shf);
+    vsum[k] = block_sum((double)vs[k], shd);
+  }
+  float se[4] = {0.f, 0.f, 0.f, 0.f}, sh_[4] = {0.f, 0.f, 0.f, 0.f}, sw_[4] = {0.f, 0.f, 0.f, 0.f};
+  int mh[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX}, mw[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float4 a = ldg4(x + base + (long long)i * 4), c = ldg4(y + base + (long long)i * 4);
+    const int h = i / g, w = i - h * g;
+    float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float e = expf(av[k] - xm[k]);
+      se[k] += e;
+      sh_[k] = fmaf(e, (float)h, sh_[k]);
+      sw_[k] = fmaf(e, (float)w, sw_[k]);
+      if (cv[k] == ym[k]) { mh[k] = min(mh[k], h); mw[k] = min(mw[k], w); }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double s = block_sum((double)se[k], shd);
+    double eh = block_sum((double)sh_[k], shd);
+    double ew = block_sum((double)sw_[k], shd);
+    int gh = block_min(mh[k], shi), gw = block_min(mw[k], shi);
+    if (threadIdx.x == 0) {
+      SegStat& o = seg[blockIdx.x];
+      o.e_h[k] = (float)(eh / s);
+      o.e_w[k] = (float)(ew / s);
+      o.gt_h[k] = (float)gh;
+      o.gt_w[k] = (float)gw;
+      o.v[k] = (float)(vsum[k] / (double)n);
+      o.xmax[k] = xm[k];
+      o.sumexp[k] = (float)s;
+    }
+  }
+}
+
+// one block: loss and the per-segment gradient coefficients
+__global__ void elmse_finalize_kernel(Levels lv, int batch, float loss_weight, SegStat* __restrict__ seg,
+                                      float* __restrict__ loss_out) {
+  __shared__ double sh[8];
+  double total = 0.0;
+  for (int idx = threadIdx.x; idx < lv.n * 4; idx += blockDim.x) {
+    const int l = idx / 4, k = idx % 4;
+    const double g = (double)lv.size[l];
+    double nv = 0.0;
+    for (int b = 0; b < batch; ++b) nv += (double)seg[b * lv.n + l].v[k];
+    if (nv == 0.0) nv = 1.0;
+    double acc = 0.0;
+    for (int b = 0; b < batch; ++b) {
+      SegStat& s = seg[b * lv.n + l];
+      const double dh = (double)s.e_h[k] / g - (double)s.gt_h[k] / g;
+      const double dw = (double)s.e_w[k] / g - (double)s.gt_w[k] / g;
+      acc += (dh * dh + dw * dw) * (double)s.v[k];
+      s.c_h[k] = (float)((double)loss_weight * 2.0 * dh / g * (double)s.v[k] / nv);
+      s.c_w[k] = (float)((double)loss_weight * 2.0 * dw / g * (double)s.v[k] / nv);
+    }
+    total += acc / nv;
+  }
+  total = block_sum(total, sh);
+  if (threadIdx.x == 0) *loss_out = (float)((double)loss_weight * total);
+}
+
+__global__ void __launch_bounds__(kThreads)
+elmse_grad_kernel(Levels lv, const float* __restrict__ x, const SegStat* __restrict__ seg,
+                  float* __restrict__ grad) {
+  const int b = blockIdx.x / lv.n, l = blockIdx.x % lv.n;
+  const int g = lv.size[l], n = g * g;
+  const long long base = ((long long)b * lv.total + lv.start[l]) * 4;
+  const SegStat s = seg[blockIdx.x];
+  float inv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) inv[k] = 1.0f / s.sumexp[k];
+  for (int i = threadIdx.x + blockIdx.y * blockDim.x; i < n; i += blockDim.x * gridDim.y) {
+    float4 a = ldg4(x + base + (long long)i * 4);
+    const int h = i / g, w = i - h * g;
+    float av[4] = {a.x, a.y, a.z, a.w}, o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float p = expf(av[k] - s.xmax[k]) * inv[k];
+      o[k] = p * (((float)h - s.e_h[k]) * s.c_h[k] + ((float)w - s.e_w[k]) * s.c_w[k]);
+    }
+    st4(grad + base + (long long)i * 4, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+__global__ void labels_kernel(int batch, int channels, int frame, Levels lv, const int32_t* __restrict__ coords,
+                              float* __restrict__ y) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * channels * lv.n) return;
+  const int l = idx % lv.n, c = (idx / lv.n) % channels, b = idx / (lv.n * channels);
+  const int g = lv.size[l];
+  int h = coords[(b * channels + c) * 2], w = coords[(b * channels + c) * 2 + 1];
+  if (h >= frame || w >= frame || h < -frame || w < -frame) return;  // reference raises IndexError here
+  // np.digitize(h, linspace(0, frame, g+1)) - 1 == floor(h*g/frame) for 0 <= h < frame; a negative
+  // coordinate lands in bin -1, which numpy indexing wraps to the last row/column (datasets.py:532-537)
+  int bh = (l == lv.n - 1) ? h : (h < 0 ? -1 : (int)(((long long)h * g) / frame));
+  int bw = (l == lv.n - 1) ? w : (w < 0 ? -1 : (int)(((long long)w * g) / frame));
+  if (bh < 0) bh += g;
+  if (bw < 0) bw += g;
+  y[((long long)b * lv.total + lv.start[l] + (long long)bh * g + bw) * channels + c] = 1.0f;
+}
+
+int make_levels(int num_levels, const int32_t* level_size, Levels& lv) {
+  if (num_levels < 1 || num_levels > EG_MAX_LEVELS || !level_size) return -1;
+  lv.n = num_levels;
+  int off = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    if (level_size[l] < 1) return -1;
+    lv.size[l] = level_size[l];
+    lv.start[l] = off;
+    off += level_size[l] * level_size[l];
+  }
+  lv.total = off;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eg_bce_multilevel(int64_t n, const float* logits, const float* y, const float* valid, float ones_weight,
+                      float loss_weight, float* loss_out, float* dlogits, void* ws, size_t ws_bytes,
+                      void* stream) {
+  EG_CHECK_ARG(n >= 1 && logits && y && valid && loss_out, "eg_bce_multilevel: NULL argument");
+  if (!ws || ws_bytes < kWorkspaceBytes) {
+    set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
+    return EG_ERR_WORKSPACE;
+  }
+  cudaStream_t s = as_stream(stream);
+  const long long n4 = (n + 3) / 4;
+  long long blocks = (n4 + kThreads - 1) / kThreads;
+  int grid = (int)(blocks < kMaxParts ? blocks : kMaxParts);
+  double* parts = reinterpret_cast<double*>(ws);
+  float* scale = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);
+  bce_kernel<<<grid, kThreads, 0, s>>>(n4, n, logits, y, valid, ones_weight, dlogits, parts);
+  EG_LAUNCH_CHECK();
+  bce_finalize_kernel<<<1, 32, 0, s>>>(grid, parts, loss_weight, loss_out, scale);
+  EG_LAUNCH_CHECK();
+  if (dlogits) {
+    scale_kernel<<<grid, kThreads, 0, s>>>(n, dlogits, scale);
+    EG_LAUNCH_CHECK();
+  }
+  return EG_OK;
+}
+
+int eg_expected_landmark_mse(int batch, int channels, int num_levels, const int32_t* level_size,
+                             const float* logits, const float* y, const float* valid, float loss_weight,
+                             float* loss_out, float* dlogits, void* ws, size_t ws_bytes, void* stream) {
+  EG_CHECK_ARG(batch >= 1 && logits && y && valid && loss_out, "eg_expected_landmark_mse: bad argument");
+  EG_CHECK_ARG(channels == 4, "eg_expected_landmark_mse: num_output_channels must be 4 (engine.py:92), got %d",
+               channels);
+  Levels lv;
+  EG_CHECK_ARG(make_levels(num_levels, level_size, lv) == 0, "eg_expected_landmark_mse: bad level list");
+  const size_t need = sizeof(SegStat) * (size_t)batch * num_levels;
+  if (!ws || ws_bytes < need || ws_bytes < kWorkspaceBytes) {
+    set_error("workspace too small: need %zu bytes", need > kWorkspaceBytes ? need : kWorkspaceBytes);
+    return EG_ERR_WORKSPACE;
+  }
+  cudaStream_t s = as_stream(stream);
+  SegStat* seg = reinterpret_cast<SegStat*>(ws);
+  elmse_stats_kernel<<<batch * num_levels, kThreads, 0, s>>>(lv, logits, y, valid, seg);
+  EG_LAUNCH_CHECK();
+  elmse_finalize_kernel<<<1, 64, 0, s>>>(lv, batch, loss_weight, seg, loss_out);
+  EG_LAUNCH_CHECK();
+  if (dlogits) {
+    dim3 grid(batch * num_levels, 8);
+    elmse_grad_kernel<<<grid, kThreads, 0, s>>>(lv, logits, seg, dlogits);
+    EG_LAUNCH_CHECK();
+  }
+  return EG_OK;
+}
+
+int eg_node_labels(int batch, int channels, int frame_size, int num_levels, const int32_t* level_size,
+                   const int32_t* coords, float* y, void* stream) {
+  EG_CHECK_ARG(batch >= 1 && channels >= 1 && coords && y, "eg_node_labels: bad argument");
+  Levels lv;
+  EG_CHECK_ARG(make_levels(num_levels, level_size, lv) == 0, "eg_node_labels: bad level list");
+  EG_CHECK_ARG(lv.size[num_levels - 1] == frame_size, "eg_node_labels: last level must be the pixel grid");
+  cudaStream_t s = as_stream(stream);
+  EG_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)batch * lv.total * channels, s));
+  const int total = batch * channels * num_levels;
+  labels_kernel<<<(total + 127) / 128, 128, 0, s>>>(batch, channels, frame_size, lv, coords, y);
+  EG_LAUNCH_CHECK();
+  return EG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+"""Data-parallel plumbing: one process per GPU, frames sharded across ranks, ONE flat fp32 gradient
+bucket all-reduced over NCCL (NVLink 5 / NVSwitch) per step.
+
+Replaces the reference's single-process `torch_geometric.nn.DataParallel` / `nn.DataParallel`
+(src/engine.py:105-110), which re-broadcasts all parameters and gathers logits to GPU 0 every step.
+The batched graph is block-diagonal, so frames are independent through the whole GNN path; BatchNorm
+statistics and loss normalisers stay per rank, exactly as they are per replica in the reference.
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None) -> tuple:
+    """(rank, local_rank, world_size); initialises torch.distributed when WORLD_SIZE > 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+def shard_range(num_frames: int, rank: int, world: int) -> range:
+    """Frames [r*B/G, (r+1)*B/G) of a global batch; the global batch must divide evenly so that per-rank
+    loss normalisers (sum(valid), num_valid) average to the global loss."""
+    if num_frames % world != 0:
+        raise ValueError(f"global batch {num_frames} does not divide over {world} ranks")
+    per = num_frames // world
+    return range(rank * per, (rank + 1) * per)
+
+
+class FlatGradBucket:
+    """All gradients of `params` live as views into one contiguous fp32 buffer, so the data-parallel
+    reduction is a single all-reduce with no flatten/unflatten copies."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * 4
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None) -> None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(dist.get_world_size(group))

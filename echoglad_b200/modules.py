@@ -1,0 +1,329 @@
+"""Drop-in `nn.Module`s for the reference's landmark models, with IDENTICAL constructor kwargs, forward
+signature and `state_dict` layout, whose GNN stack / classifiers run on the sm_100a
+kernels.  The CNN embedder and the UNet pyramid stay in PyTorch (north star: "CNN embedder left in
+PyTorch"); they are written here only so the replacement is self-contained.
+
+Reference classes replaced:
+  UNETHierarchicalPatchModel  src/core/models.py:639-756   (MODELS['unet_hierarchical_patch'])
+  HierarchicalPatchModel      src/core/models.py:262-553   (MODELS['hierarchicalpatch'])
+  CNN (embedder)              src/core/models.py:161-260   (MODELS['cnn'])  — plain PyTorch, out of scope
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as TF
+
+from . import ops
+from ._lib import EchogladError
+from .graph import DeviceGraph, HierGraphSpec
+
+F = 128
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parameter containers (names chosen so that state_dict keys equal the reference's)
+# ---------------------------------------------------------------------------------------------------------
+
+class _GCNConvParams(nn.Module):
+    """Holds PyG GCNConv's parameters: `lin.weight` [out,in] (glorot, no bias) and `bias` (zeros)."""
+
+    def __init__(self, fin: int, fout: int):
+        super().__init__()
+        self.lin = nn.Linear(fin, fout, bias=False)
+        self.bias = nn.Parameter(torch.zeros(fout))
+        a = math.sqrt(6.0 / (fin + fout))
+        nn.init.uniform_(self.lin.weight, -a, a)
+
+
+class _GNNBlock(nn.Module):
+    """`Sequential('x, edge_index', [GCNConv, BatchNorm1d, Dropout, ReLU|Identity])` of the reference
+    (src/core/models.py:329-335): children `module_0` (conv params) and `module_1` (BatchNorm1d buffers)."""
+
+    def __init__(self, fin: int, fout: int, dropout_p: float, relu: bool):
+        super().__init__()
+        self.module_0 = _GCNConvParams(fin, fout)
+        self.module_1 = nn.BatchNorm1d(fout)
+        self.dropout_p = float(dropout_p)
+        self.relu = relu
+
+
+def _update_running(bn: nn.BatchNorm1d, mean: torch.Tensor, var: torch.Tensor, n: int, sl=slice(None)) -> None:
+    """torch BatchNorm train-mode bookkeeping: momentum update with the UNBIASED variance."""
+    with torch.no_grad():
+        m = bn.momentum if bn.momentum is not None else 0.1
+        unbiased = var[sl] * (n / max(n - 1, 1))
+        bn.running_mean.mul_(1 - m).add_(mean[sl], alpha=m)
+        bn.running_var.mul_(1 - m).add_(unbiased, alpha=m)
+        bn.num_batches_tracked += 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# landmark model
+# ---------------------------------------------------------------------------------------------------------
+
+class HierarchicalPatchModel(nn.Module):
+    """Base landmark model: average-pooled pyramid of the embedder output as node features."""
+
+    def __init__(self,
+                 frame_size: int = 32,
+                 gnn_dropout_p: float = 0.0,
+                 classifier_dropout_p: float = 0.0,
+                 node_embedding_dim: int = 128,
+                 node_hidden_dim: int = 64,
+                 num_output_channels: int = 4,
+                 num_gnn_layers: int = 3,
+                 num_aux_graphs: int = 4,
+                 gnn_jk_mode: str = 'last',
+                 classifier_hidden_dim: int = 16,
+                 residual: bool = True,
+                 use_coordinate_graph: bool = False,
+                 output_activation: str = 'sigmoid',
+                 use_connection_nodes=False,
+                 use_main_graph_only=False,
+                 main_graph_type: str = 'grid',
+                 aux_graph_type: str = 'grid'):
+        super().__init__()
+        assert gnn_jk_mode in ['last', 'max', 'cat'], "Only last, max or cat jumping knowledge mode is supported."
+        if output_activation not in ('sigmoid', 'logit'):
+            raise TypeError(f"invalid output_activation:{output_activation}")  # reference raises a TypeError too
+        if node_embedding_dim != F or node_hidden_dim != F:
+            raise NotImplementedError(
+                f"echoglad_b200 tensor-core paths are built for node_embedding_dim == node_hidden_dim == {F} "
+                f"(configs/default.yml:14-15); got {node_embedding_dim}/{node_hidden_dim}")
+        if num_output_channels != 4 or classifier_hidden_dim != 32:
+            raise NotImplementedError(
+                "echoglad_b200 classifier kernels are built for num_output_channels == 4 (src/engine.py:92) and "
+                f"classifier_hidden_dim == 32 (configs/default.yml:16); got {num_output_channels}/{classifier_hidden_dim}")
+        if use_coordinate_graph and not use_main_graph_only:
+            raise NotImplementedError("use_coordinate_graph=True is not built yet (SURVEY.md §8(f) row 3)")
+        if gnn_jk_mode == 'cat':
+            raise NotImplementedError("gnn_jk_mode='cat' feeds (L+1)*128 features into Linear(128, .) and fails in "
+                                      "the reference as well (src/core/models.py:364,479-482)")
+
+        self.gnn_layers = nn.ModuleList(
+            _GNNBlock(node_embedding_dim if i == 0 else node_hidden_dim, node_hidden_dim, gnn_dropout_p,
+                      relu=(i != num_gnn_layers - 1)) for i in range(num_gnn_layers))
+        self.node_coordinate_mlp = nn.ModuleList()
+        self.output_activation = output_activation
+        last = nn.Sigmoid() if output_activation == 'sigmoid' else nn.Identity()
+        h = classifier_hidden_dim
+        # never called as modules: they only hold the parameters under the reference's key names
+        self.node_classifiers = nn.ModuleList(
+            nn.Sequential(nn.Linear(node_hidden_dim, h), nn.BatchNorm1d(h), nn.ReLU(inplace=True),
+                          nn.Dropout(p=classifier_dropout_p), nn.Linear(h, h // 2), nn.BatchNorm1d(h // 2),
+                          nn.ReLU(inplace=True), nn.Dropout(p=classifier_dropout_p), nn.Linear(h // 2, 1), last)
+            for _ in range(num_output_channels))
+        self.jk = None  # 'max' is evaluated inline; kept for attribute parity with the reference
+
+        self.frame_size = frame_size
+        self.residual = residual
+        self.num_gnn_layers = num_gnn_layers
+        self.node_embedding_dim = node_embedding_dim
+        self.num_aux_graphs = num_aux_graphs
+        self.use_coordinate_graph = use_coordinate_graph
+        self.use_connection_nodes = use_connection_nodes
+        self.use_main_graph_only = use_main_graph_only
+        self.gnn_jk_mode = gnn_jk_mode
+        self.classifier_dropout_p = float(classifier_dropout_p)
+        self.graph_spec = HierGraphSpec(frame_size=frame_size, num_aux_graphs=num_aux_graphs,
+                                        use_main_graph_only=bool(use_main_graph_only),
+                                        use_coordinate_graph=bool(use_coordinate_graph),
+                                        use_connection_nodes=bool(use_connection_nodes),
+                                        main_graph_type=main_graph_type, aux_graph_type=aux_graph_type)
+        self._step = 0
+        self.dropout_seed = 0x5EED
+
+    # -- node features ---------------------------------------------------------------------------------------
+    def pyramid(self, x: torch.Tensor) -> List[torch.Tensor]:
+        """[B,128,S,S] embedder output -> list of level maps [B,128,s_l,s_l] (src/core/models.py:512-524)."""
+        maps = [] if self.use_main_graph_only else [TF.adaptive_avg_pool2d(x, 2 ** k)
+                                                    for k in range(1, self.num_aux_graphs + 1)]
+        return maps + [x]
+
+    def connection_rows(self, maps: List[torch.Tensor]) -> torch.Tensor:
+        """[B, naux+1, 128]: the frame mean repeated (base variant, src/core/models.py:531-534)."""
+        return maps[-1].mean(dim=(2, 3)).unsqueeze(1).repeat(1, self.num_aux_graphs + 1, 1)
+
+    def create_node_pixels(self, x: torch.Tensor, graph: DeviceGraph) -> torch.Tensor:
+        maps = self.pyramid(x)
+        head = self.connection_rows(maps) if graph.meta.first_pixel_node else None
+        return ops.PackNodes.apply(graph, head, None, *maps)
+
+    # -- forward ---------------------------------------------------------------------------------------------
+    def forward(self, data_batch=None, x: torch.Tensor = None, node_coords: torch.Tensor = None,
+                edge_index: torch.Tensor = None, node_type=None, batch_idx: torch.Tensor = None):
+        if data_batch is not None:
+            x, edge_index = data_batch.x, data_batch.edge_index
+        if x is None or not x.is_cuda:
+            raise EchogladError("the landmark module needs CUDA inputs: echoglad_b200 has no CPU fallback")
+        batch = x.shape[0]
+        graph = DeviceGraph.get(self.graph_spec, x.device)
+        graph.validate_edge_index_once(edge_index, batch)
+
+        feats = self.create_node_pixels(x.float(), graph)
+        h = self.gnn_stack(feats, graph, batch)
+        if graph.meta.num_pixel_nodes != graph.meta.num_nodes:  # drop connection / coordinate rows
+            a = graph.meta.first_pixel_node
+            h = h.view(batch, graph.meta.num_nodes, F)[:, a:a + graph.meta.num_pixel_nodes].reshape(-1, F)
+        out = self.classify(h)
+        self._step += 1
+        return out.squeeze(1), None
+
+    def _seed(self, salt: int) -> int:
+        return (self.dropout_seed * 0x9E3779B1 + self._step * 1000003 + salt * 7919) & 0x7FFFFFFFFFFFFFFF
+
+    def gnn_stack(self, feats: torch.Tensor, graph: DeviceGraph, batch: int) -> torch.Tensor:
+        hidden = [feats]
+        rows = feats.shape[0]
+        for i, blk in enumerate(self.gnn_layers):
+            bn = blk.module_1
+            use_batch_stats = self.training or not bn.track_running_stats
+            y, mean, var = ops.GCNLayer.apply(
+                graph, batch, hidden[i], blk.module_0.lin.weight, blk.module_0.bias, bn.weight, bn.bias,
+                bn.running_mean, bn.running_var, use_batch_stats, bn.eps,
+                blk.dropout_p if self.training else 0.0, self._seed(i), blk.relu, bool(self.residual))
+            if self.training and bn.track_running_stats:
+                _update_running(bn, mean, var, rows)
+            hidden.append(y)
+        if self.gnn_jk_mode == 'max':
+            out = hidden[0]
+            for t in hidden[1:]:
+                out = torch.maximum(out, t)
+            return out
+        return hidden[-1]
+
+    def classify(self, h: torch.Tensor) -> torch.Tensor:
+        clf = self.node_classifiers
+        cat = torch.cat
+        w1 = cat([c[0].weight for c in clf]); b1 = cat([c[0].bias for c in clf])
+        g1 = cat([c[1].weight for c in clf]); be1 = cat([c[1].bias for c in clf])
+        w2 = torch.stack([c[4].weight for c in clf]); b2 = torch.stack([c[4].bias for c in clf])
+        g2 = cat([c[5].weight for c in clf]); be2 = cat([c[5].bias for c in clf])
+        w3 = cat([c[8].weight for c in clf]); b3 = cat([c[8].bias for c in clf])
+        with torch.no_grad():
+            m1 = cat([c[1].running_mean for c in clf]); v1 = cat([c[1].running_var for c in clf])
+            m2 = cat([c[5].running_mean for c in clf]); v2 = cat([c[5].running_var for c in clf])
+        out, bm1, bv1, bm2, bv2 = ops.ClassifierHeads.apply(
+            h, w1, b1, g1, be1, m1, v1, w2, b2, g2, be2, m2, v2, w3, b3, self.training, BN_EPS,
+            self.classifier_dropout_p if self.training else 0.0, self._seed(101),
+            self.output_activation == 'sigmoid')
+        if self.training:
+            rows = h.shape[0]
+            for k, c in enumerate(clf):
+                _update_running(c[1], bm1, bv1, rows, slice(32 * k, 32 * k + 32))
+                _update_running(c[5], bm2, bv2, rows, slice(16 * k, 16 * k + 16))
+        return out
+
+
+class _DownConv(nn.Module):
+    """conv3x3-ReLU-BN twice, then AdaptiveMaxPool to `out_size` (reference DownConv, models.py:841-856)."""
+
+    def __init__(self, cin: int, cout: int, out_size: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.BN1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.BN2 = nn.BatchNorm2d(cout)
+        self.out_size = out_size
+
+    def forward(self, x):
+        x = self.BN1(TF.relu(self.conv1(x)))
+        x = self.BN2(TF.relu(self.conv2(x)))
+        return TF.adaptive_max_pool2d(x, self.out_size)
+
+
+class _UpConv(nn.Module):
+    """nearest upsample, conv-ReLU-BN, concat skip, conv-ReLU-BN (reference UpConv, models.py:859-876)."""
+
+    def __init__(self, cin: int, cout: int, out_size: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.BN1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.BN2 = nn.BatchNorm2d(cout)
+        self.out_size = out_size
+
+    def forward(self, x, skip):
+        x = TF.interpolate(x, size=self.out_size)
+        x = self.BN1(TF.relu(self.conv1(x)))
+        return self.BN2(TF.relu(self.conv2(torch.cat([x, skip], dim=1))))
+
+
+class UNETHierarchicalPatchModel(HierarchicalPatchModel):
+    """default.yml landmark model: node features come from the decoder maps of a 7-level UNet."""
+
+    def __init__(self, encoder_embedding_widths: list = None, encoder_embedding_dims=None, **kwargs):
+        super().__init__(**kwargs)
+        if encoder_embedding_widths is None:
+            encoder_embedding_widths = [128, 64, 32, 16, 8, 4, 2]
+        # reference quirk kept: any truthy value is overwritten by the default list (models.py:652-653)
+        if encoder_embedding_dims:
+            encoder_embedding_dims = [8, 16, 32, 64, 128, 256, 512]
+        if self.num_aux_graphs > len(encoder_embedding_widths):
+            raise TypeError(f"num_aux_graphs:{self.num_aux_graphs} is larger than total number of usable "
+                            f"intermediate layers:{len(encoder_embedding_widths)}")
+        dims = list(encoder_embedding_dims)
+        self.down_convs = nn.ModuleList(_DownConv(f // 2, f, encoder_embedding_widths[i])
+                                        for i, f in enumerate(dims))
+        up_sizes = list(reversed(encoder_embedding_widths))[1:] + [self.frame_size]
+        self.up_convs = nn.ModuleList(_UpConv(f, f // 2, up_sizes[i]) for i, f in enumerate(reversed(dims)))
+        feats_in = list(reversed(dims)) + [dims[0] // 2]
+        self.linears = nn.ModuleList(nn.Conv2d(c, self.node_embedding_dim, kernel_size=1) for c in feats_in)
+
+    def pyramid(self, x: torch.Tensor) -> List[torch.Tensor]:
+        skips = []
+        for down in self.down_convs:
+            skips.append(x)
+            x = down(x)
+        feats = [x]
+        for up in self.up_convs:
+            x = up(x, skips.pop())
+            feats.append(x)
+        naux = 0 if self.use_main_graph_only else self.num_aux_graphs
+        used = list(range(naux)) + [len(feats) - 1]
+        return [TF.relu(self.linears[i](feats[i])) for i in used]
+
+    def connection_rows(self, maps: List[torch.Tensor]) -> torch.Tensor:
+        """One connection node per used level = its spatial mean (src/core/models.py:735-752)."""
+        return torch.stack([m.mean(dim=(2, 3)) for m in maps], dim=1)
+
+
+class CNN(nn.Module):
+    """The default.yml embedder (`cnn`, one residual block 1 -> 4 channels).  Plain PyTorch: out of the
+    hot-path scope, present so that engine-level runs are self-contained.  Same state_dict keys as the
+    reference (`conv.{i}.0.{one_by_one_cnn,conv,bn}.*`, src/core/models.py:71-260)."""
+
+    class _Block(nn.Module):
+        def __init__(self, cin, cout, k, pool, p):
+            super().__init__()
+            self.one_by_one_cnn = nn.Conv2d(cin, cout, 1) if cin != cout else None
+            self.conv = nn.Conv2d(cin, cout, k, padding=(k - 1) // 2)
+            self.bn = nn.BatchNorm2d(cout)
+            self.pool = nn.MaxPool2d(pool)
+            self.dropout = nn.Dropout2d(p)
+
+        def forward(self, x):
+            res = x if self.one_by_one_cnn is None else self.one_by_one_cnn(x)
+            return self.dropout(TF.relu(self.pool(self.bn(self.conv(x)) + res)))
+
+    def __init__(self, out_channels: list, kernel_sizes: list = None, pool_sizes: list = None,
+                 fc_output_dim: list = None, cnn_dropout_p: float = 0.0):
+        super().__init__()
+        n = len(out_channels)
+        kernel_sizes = kernel_sizes or [3] * n
+        pool_sizes = pool_sizes or [1] * n
+        if fc_output_dim is not None:
+            raise NotImplementedError("fc_output_dim is unused by default.yml")
+        chans = [1] + list(out_channels)
+        self.conv = nn.Sequential(*[nn.Sequential(CNN._Block(chans[i], chans[i + 1], kernel_sizes[i],
+                                                             pool_sizes[i], cnn_dropout_p)) for i in range(n)])
+        self.output_fc = None
+
+    def forward(self, x):
+        return self.conv(x)

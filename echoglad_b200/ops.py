@@ -1,0 +1,348 @@
+"""torch.autograd wrappers over the C ABI (ctypes; raw device pointers; torch's current stream).
+
+PyTorch is plumbing here — device memory, streams, autograd bookkeeping — every FLOP and byte of the
+GNN path runs in the hand-written sm_100a kernels of libechoglad_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from ._lib import WORKSPACE_BYTES, EchogladError, check, lib
+from .graph import DeviceGraph
+
+F = 128
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise EchogladError(f"{name} must be a CUDA tensor: echoglad_b200 has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise EchogladError(f"{name} must be float32 (got {t.dtype})")
+    return t.contiguous()
+
+
+def _ws(device) -> torch.Tensor:
+    return torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# plain (non-autograd) calls, used by tests / bench and by the Functions below
+# ---------------------------------------------------------------------------------------------------------
+
+def gcn_aggregate(graph: DeviceGraph, batch: int, x: torch.Tensor) -> torch.Tensor:
+    x = _f32(x, "x")
+    out = torch.empty_like(x)
+    check(lib.eg_gcn_aggregate(graph.handle, batch, x.shape[1], x.data_ptr(), out.data_ptr(), _stream(x)),
+          "eg_gcn_aggregate")
+    return out
+
+
+def linear128(a: torch.Tensor, w: torch.Tensor, trans_w: bool, bias=None, addend=None, stats: bool = False):
+    a, w = _f32(a, "a"), _f32(w, "w")
+    out = torch.empty_like(a)
+    mean = var = None
+    ws = None
+    if stats:
+        mean = torch.empty(F, device=a.device)
+        var = torch.empty(F, device=a.device)
+        ws = _ws(a.device)
+    check(lib.eg_linear128(a.shape[0], a.data_ptr(), w.data_ptr(), int(trans_w), _ptr(bias), _ptr(addend),
+                           out.data_ptr(), _ptr(mean), _ptr(var), _ptr(ws), WORKSPACE_BYTES if stats else 0,
+                           _stream(a)), "eg_linear128")
+    return (out, mean, var) if stats else out
+
+
+def linear128_wgrad(g: torch.Tensor, x: torch.Tensor, want_bias: bool = True):
+    g, x = _f32(g, "g"), _f32(x, "x")
+    dw = torch.empty(F, F, device=g.device)
+    db = torch.empty(F, device=g.device) if want_bias else None
+    ws = _ws(g.device)
+    check(lib.eg_linear128_wgrad(g.shape[0], g.data_ptr(), x.data_ptr(), dw.data_ptr(), _ptr(db), ws.data_ptr(),
+                                 WORKSPACE_BYTES, _stream(g)), "eg_linear128_wgrad")
+    return dw, db
+
+
+def col_stats(z: torch.Tensor):
+    z = _f32(z, "z")
+    mean = torch.empty(z.shape[1], device=z.device)
+    var = torch.empty(z.shape[1], device=z.device)
+    ws = _ws(z.device)
+    check(lib.eg_col_stats(z.shape[0], z.shape[1], z.data_ptr(), mean.data_ptr(), var.data_ptr(), ws.data_ptr(),
+                           WORKSPACE_BYTES, _stream(z)), "eg_col_stats")
+    return mean, var
+
+
+def dropout_mask(rows: int, cols: int, p: float, seed: int, device) -> torch.Tensor:
+    m = torch.empty(rows, cols, device=device)
+    check(lib.eg_dropout_mask(rows, cols, float(p), int(seed), m.data_ptr(),
+                              torch.cuda.current_stream(device).cuda_stream), "eg_dropout_mask")
+    return m
+
+
+def bn_act_fwd(h, mean, var, gamma, beta, eps, drop_p, seed, relu, res=None):
+    y = torch.empty_like(h)
+    check(lib.eg_bn_act_fwd(h.shape[0], h.shape[1], h.data_ptr(), mean.data_ptr(), var.data_ptr(),
+                            gamma.data_ptr(), beta.data_ptr(), float(eps), float(drop_p), int(seed), int(relu),
+                            _ptr(res), y.data_ptr(), _stream(h)), "eg_bn_act_fwd")
+    return y
+
+
+def bn_act_bwd(dy, h, mean, var, gamma, beta, eps, drop_p, seed, relu, batch_stats):
+    dh = torch.empty_like(h)
+    dgamma = torch.empty_like(gamma)
+    dbeta = torch.empty_like(beta)
+    ws = _ws(h.device)
+    check(lib.eg_bn_act_bwd(h.shape[0], h.shape[1], dy.data_ptr(), h.data_ptr(), mean.data_ptr(), var.data_ptr(),
+                            gamma.data_ptr(), beta.data_ptr(), float(eps), float(drop_p), int(seed), int(relu),
+                            int(batch_stats), dh.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(),
+                            WORKSPACE_BYTES, _stream(h)), "eg_bn_act_bwd")
+    return dh, dgamma, dbeta
+
+
+def node_labels(coords: torch.Tensor, frame_size: int, level_size: Sequence[int]) -> torch.Tensor:
+    """coords int32[B, C, 2] (h, w) on device -> y float32[B, n0, C] (create_node_labels on device)."""
+    if not coords.is_cuda:
+        raise EchogladError("coords must be a CUDA tensor")
+    coords = coords.to(torch.int32).contiguous()
+    b, c, _ = coords.shape
+    n0 = sum(s * s for s in level_size)
+    y = torch.empty(b, n0, c, device=coords.device)
+    ls = (C.c_int32 * len(level_size))(*level_size)
+    check(lib.eg_node_labels(b, c, frame_size, len(level_size), ls, coords.data_ptr(), y.data_ptr(),
+                             _stream(coords)), "eg_node_labels")
+    return y
+
+
+# ---------------------------------------------------------------------------------------------------------
+# autograd Functions
+# ---------------------------------------------------------------------------------------------------------
+
+class PackNodes(torch.autograd.Function):
+    """NCHW pyramid maps (+ optional connection / coordinate rows) -> node-major [B*N, 128]."""
+
+    @staticmethod
+    def forward(ctx, graph: DeviceGraph, head, tail, *maps):
+        maps = [_f32(m, "map") for m in maps]
+        meta = graph.meta
+        if len(maps) != meta.num_levels:
+            raise EchogladError(f"expected {meta.num_levels} level maps, got {len(maps)}")
+        batch = maps[0].shape[0]
+        for m, s in zip(maps, meta.level_size):
+            if tuple(m.shape) != (batch, F, s, s):
+                raise EchogladError(f"level map has shape {tuple(m.shape)}, expected {(batch, F, s, s)}")
+        head = None if head is None else _f32(head, "head")
+        tail = None if tail is None else _f32(tail, "tail")
+        x = torch.empty(batch * meta.num_nodes, F, device=maps[0].device)
+        arr = (C.c_void_p * len(maps))(*[m.data_ptr() for m in maps])
+        check(lib.eg_pack_nodes(graph.handle, batch, arr, _ptr(head), _ptr(tail), x.data_ptr(), _stream(x)),
+              "eg_pack_nodes")
+        ctx.graph, ctx.batch = graph, batch
+        ctx.has_head, ctx.has_tail = head is not None, tail is not None
+        ctx.map_shapes = [m.shape for m in maps]
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        dx = _f32(dx, "dx")
+        meta = ctx.graph.meta
+        need = ctx.needs_input_grad
+        d_maps: List[Optional[torch.Tensor]] = []
+        for i, shp in enumerate(ctx.map_shapes):
+            d_maps.append(torch.empty(shp, device=dx.device) if need[3 + i] else None)
+        d_head = torch.empty(ctx.batch, meta.first_pixel_node, F, device=dx.device) if ctx.has_head else None
+        d_tail = torch.empty(ctx.batch, meta.num_coord_nodes, F, device=dx.device) if ctx.has_tail else None
+        arr = (C.c_void_p * len(d_maps))(*[_ptr(m) for m in d_maps])
+        check(lib.eg_pack_nodes_grad(ctx.graph.handle, ctx.batch, dx.data_ptr(), arr, _ptr(d_head), _ptr(d_tail),
+                                     _stream(dx)), "eg_pack_nodes_grad")
+        return (None, d_head if need[1] else None, d_tail if need[2] else None, *d_maps)
+
+
+class Aggregate(torch.autograd.Function):
+    """y = A_hat x (A_hat symmetric => backward is the same kernel)."""
+
+    @staticmethod
+    def forward(ctx, graph: DeviceGraph, batch: int, x):
+        ctx.graph, ctx.batch = graph, batch
+        return gcn_aggregate(graph, batch, x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return None, None, gcn_aggregate(ctx.graph, ctx.batch, dy.contiguous())
+
+
+class GCNLayer(torch.autograd.Function):
+    """One reference GNN layer: GCNConv -> BatchNorm1d -> Dropout -> ReLU|Identity (+ residual)
+    (reference src/core/models.py:329-335,431-435).  Returns (Y, batch_mean, batch_var)."""
+
+    @staticmethod
+    def forward(ctx, graph: DeviceGraph, batch: int, x, w, bias, gamma, beta, mean_in, var_in, training: bool,
+                eps: float, drop_p: float, seed: int, relu: bool, residual: bool):
+        x, w = _f32(x, "x"), _f32(w, "W")
+        rows = batch * graph.meta.num_nodes
+        if tuple(x.shape) != (rows, F) or tuple(w.shape) != (F, F):
+            raise EchogladError(f"GCNLayer: x {tuple(x.shape)} / W {tuple(w.shape)} do not match rows={rows}, F={F}")
+        h = torch.empty_like(x)
+        ws = _ws(x.device)
+        if training:
+            mean = torch.empty(F, device=x.device)
+            var = torch.empty(F, device=x.device)
+        else:
+            mean, var = _f32(mean_in, "running_mean"), _f32(var_in, "running_var")
+        check(lib.eg_gcn_conv_fwd(graph.handle, batch, x.data_ptr(), w.data_ptr(), _ptr(bias), h.data_ptr(),
+                                  mean.data_ptr() if training else None, var.data_ptr() if training else None,
+                                  ws.data_ptr(), WORKSPACE_BYTES, _stream(x)), "eg_gcn_conv_fwd")
+        p = float(drop_p) if training else 0.0
+        y = bn_act_fwd(h, mean, var, gamma, beta, eps, p, seed, relu, x if residual else None)
+        ctx.save_for_backward(x, h, w, gamma, beta, mean, var)
+        ctx.cfg = (graph, batch, training, eps, p, seed, relu, residual)
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, dy, _dmean, _dvar):
+        x, h, w, gamma, beta, mean, var = ctx.saved_tensors
+        graph, batch, training, eps, p, seed, relu, residual = ctx.cfg
+        dy = _f32(dy, "dy")
+        dh, dgamma, dbeta = bn_act_bwd(dy, h, mean, var, gamma, beta, eps, p, seed, relu, training)
+        need_dx, need_dw = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        dx = torch.empty_like(x) if need_dx else None
+        dw = torch.empty_like(w) if need_dw else None
+        if need_dx or need_dw:
+            scratch = torch.empty_like(x)
+            ws = _ws(x.device)
+            check(lib.eg_gcn_conv_bwd(graph.handle, batch, x.data_ptr(), w.data_ptr(), dh.data_ptr(),
+                                      dy.data_ptr() if residual else None, _ptr(dx), _ptr(dw), None,
+                                      scratch.data_ptr(), ws.data_ptr(), WORKSPACE_BYTES, _stream(x)),
+                  "eg_gcn_conv_bwd")
+        # d bias = column sums of dH: identically 0 through a train-mode BN, gamma*invstd*dbeta in eval mode
+        if training:
+            dbias = torch.zeros_like(gamma)
+        else:
+            dbias = gamma * torch.rsqrt(var + eps) * dbeta
+        return (None, None, dx, dw, dbias, dgamma, dbeta) + (None,) * 8
+
+
+class ClassifierHeads(torch.autograd.Function):
+    """The four node classifiers (reference src/core/models.py:363-377,488-490) as stacked / block-diagonal
+    transforms.  Inputs are the STACKED parameters: w1 [128,128] (4 x [32,128]), b1 [128], g1/be1 [128],
+    w2 [4,16,32], b2 [4,16], g2/be2 [64], w3 [4,16], b3 [4].
+    Returns (out [rows,4], mean1, var1, mean2, var2)."""
+
+    @staticmethod
+    def forward(ctx, h, w1, b1, g1, be1, m1_in, v1_in, w2, b2, g2, be2, m2_in, v2_in, w3, b3, training: bool,
+                eps: float, drop_p: float, seed: int, sigmoid: bool):
+        h = _f32(h, "h")
+        rows = h.shape[0]
+        dev = h.device
+        st = _stream(h)
+        p = float(drop_p) if training else 0.0
+        ws = _ws(dev)
+        z1 = torch.empty_like(h)
+        if training:
+            m1, v1 = torch.empty(F, device=dev), torch.empty(F, device=dev)
+            m2, v2 = torch.empty(64, device=dev), torch.empty(64, device=dev)
+        else:
+            m1, v1, m2, v2 = m1_in, v1_in, m2_in, v2_in
+        check(lib.eg_linear128(rows, h.data_ptr(), w1.data_ptr(), 1, b1.data_ptr(), None, z1.data_ptr(),
+                               m1.data_ptr() if training else None, v1.data_ptr() if training else None,
+                               ws.data_ptr(), WORKSPACE_BYTES, st), "eg_linear128")
+        a1 = bn_act_fwd(z1, m1, v1, g1, be1, eps, p, seed, True)
+        z2 = torch.empty(rows, 64, device=dev)
+        check(lib.eg_clf_mid_fwd(rows, a1.data_ptr(), w2.data_ptr(), b2.data_ptr(), z2.data_ptr(),
+                                 m2.data_ptr() if training else None, v2.data_ptr() if training else None,
+                                 ws.data_ptr(), WORKSPACE_BYTES, st), "eg_clf_mid_fwd")
+        a2 = bn_act_fwd(z2, m2, v2, g2, be2, eps, p, seed + 1, True)
+        out = torch.empty(rows, 4, device=dev)
+        check(lib.eg_clf_out_fwd(rows, a2.data_ptr(), w3.data_ptr(), b3.data_ptr(), int(sigmoid), out.data_ptr(), st),
+              "eg_clf_out_fwd")
+        ctx.save_for_backward(h, w1, g1, be1, m1, v1, w2, g2, be2, m2, v2, w3, z1, a1, z2, a2, out)
+        ctx.cfg = (training, eps, p, seed, sigmoid)
+        ctx.mark_non_differentiable(m1, v1, m2, v2)
+        return out, m1, v1, m2, v2
+
+    @staticmethod
+    def backward(ctx, dout, *_):
+        h, w1, g1, be1, m1, v1, w2, g2, be2, m2, v2, w3, z1, a1, z2, a2, out = ctx.saved_tensors
+        training, eps, p, seed, sigmoid = ctx.cfg
+        dout = _f32(dout, "dout")
+        rows, dev, st = h.shape[0], h.device, _stream(h)
+        ws = _ws(dev)
+        da2 = torch.empty_like(a2)
+        dw3, db3 = torch.empty_like(w3), torch.empty(4, device=dev)
+        check(lib.eg_clf_out_bwd(rows, a2.data_ptr(), w3.data_ptr(), out.data_ptr(), dout.data_ptr(), int(sigmoid),
+                                 da2.data_ptr(), dw3.data_ptr(), db3.data_ptr(), ws.data_ptr(), WORKSPACE_BYTES, st),
+              "eg_clf_out_bwd")
+        dz2, dg2, dbe2 = bn_act_bwd(da2, z2, m2, v2, g2, be2, eps, p, seed + 1, True, training)
+        da1 = torch.empty_like(a1)
+        dw2, db2 = torch.empty_like(w2), torch.empty(4, 16, device=dev)
+        check(lib.eg_clf_mid_bwd(rows, a1.data_ptr(), w2.data_ptr(), dz2.data_ptr(), da1.data_ptr(), dw2.data_ptr(),
+                                 db2.data_ptr(), ws.data_ptr(), WORKSPACE_BYTES, st), "eg_clf_mid_bwd")
+        dz1, dg1, dbe1 = bn_act_bwd(da1, z1, m1, v1, g1, be1, eps, p, seed, True, training)
+        dw1, db1 = linear128_wgrad(dz1, h, True)
+        dh = linear128(dz1, w1, False) if ctx.needs_input_grad[0] else None
+        return (dh, dw1, db1, dg1, dbe1, None, None, dw2, db2, dg2, dbe2, None, None, dw3, db3) + (None,) * 5
+
+
+class WeightedBCEWithLogits(torch.autograd.Function):
+    """loss_weight * sum(valid * w(y) * bce(x, y)) / sum(valid)   (reference src/core/criterion.py:13-27)."""
+
+    @staticmethod
+    def forward(ctx, logits, y, valid, ones_weight: float, loss_weight: float):
+        x = _f32(logits, "logits")
+        y = _f32(y, "y")
+        valid = _f32(valid, "valid")
+        if y.numel() != x.numel() or valid.numel() != x.numel():
+            raise EchogladError("WeightedBCEWithLogits: logits / y / valid element counts differ")
+        loss = torch.empty((), device=x.device)
+        grad = torch.empty_like(x) if logits.requires_grad else None
+        ws = _ws(x.device)
+        check(lib.eg_bce_multilevel(x.numel(), x.data_ptr(), y.data_ptr(), valid.data_ptr(), float(ones_weight),
+                                    float(loss_weight), loss.data_ptr(), _ptr(grad), ws.data_ptr(), WORKSPACE_BYTES,
+                                    _stream(x)), "eg_bce_multilevel")
+        ctx.save_for_backward(grad)
+        ctx.shape = logits.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return (grad * dloss).view(ctx.shape), None, None, None, None
+
+
+class ExpectedLandmarkMSEFn(torch.autograd.Function):
+    """Per-level soft-argmax MSE (reference src/core/criterion.py:93-151)."""
+
+    @staticmethod
+    def forward(ctx, logits, y, valid, batch: int, channels: int, level_size: tuple, loss_weight: float):
+        x = _f32(logits, "logits")
+        y = _f32(y, "y")
+        valid = _f32(valid, "valid")
+        n0 = sum(s * s for s in level_size)
+        if x.numel() != batch * n0 * channels or y.numel() != x.numel() or valid.numel() != x.numel():
+            raise EchogladError(f"ExpectedLandmarkMSE: expected {batch}x{n0}x{channels} elements, got {x.numel()}")
+        loss = torch.empty((), device=x.device)
+        grad = torch.empty_like(x) if logits.requires_grad else None
+        ws = _ws(x.device)
+        ls = (C.c_int32 * len(level_size))(*level_size)
+        check(lib.eg_expected_landmark_mse(batch, channels, len(level_size), ls, x.data_ptr(), y.data_ptr(),
+                                           valid.data_ptr(), float(loss_weight), loss.data_ptr(), _ptr(grad),
+                                           ws.data_ptr(), WORKSPACE_BYTES, _stream(x)), "eg_expected_landmark_mse")
+        ctx.save_for_backward(grad)
+        ctx.shape = logits.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return (grad * dloss).view(ctx.shape), None, None, None, None, None, None

@@ -1,0 +1,192 @@
+/*
+ * echoglad_b200 — C ABI of the B200-native (sm_100a) EchoGLAD GNN hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every device pointer is a
+ * caller-owned, contiguous allocation on the device the graph handle was created on; the library
+ * never frees or retains a caller pointer past the call.  All work is enqueued on the caller's
+ * stream (a `cudaStream_t` passed as `void*`; NULL = legacy default stream); nothing synchronises
+ * the device except eg_graph_create / eg_graph_destroy.  Every entry point returns 0 (EG_OK) or a
+ * negative EG_ERR_* code; the message is available from eg_last_error() (thread-local).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the upstream
+ * DSL-Lab/echoglad tree).  F = feature width; the tensor-core paths require F == 128
+ * (`node_embedding_dim == node_hidden_dim == 128`, configs/default.yml:14-15).
+ */
+#ifndef ECHOGLAD_B200_H
+#define ECHOGLAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EG_OK 0
+#define EG_ERR_INVALID (-1)     /* bad argument / unsupported shape */
+#define EG_ERR_CUDA (-2)        /* CUDA runtime error (message has the cudaError string) */
+#define EG_ERR_UNSUPPORTED (-3) /* spec the reference itself builds malformed (e.g. 2^naux < frame/2) */
+#define EG_ERR_WORKSPACE (-4)   /* caller workspace too small */
+
+#define EG_MAX_LEVELS 16
+#define EG_F 128 /* feature width of the tensor-core paths */
+
+typedef struct eg_graph eg_graph; /* opaque, owns the device CSR of ONE frame's static graph */
+
+/* Arguments of the reference's create_graphs (src/core/datasets.py:375-467) + data.* flags
+ * (configs/default.yml:67-75). */
+typedef struct eg_graph_spec {
+  int32_t frame_size;            /* data.transform.image_size */
+  int32_t num_aux_graphs;        /* data.num_aux_graphs (ignored when use_main_graph_only) */
+  int32_t use_main_graph_only;   /* data.use_main_graph_only */
+  int32_t use_coordinate_graph;  /* data.use_coordinate_graph: 4 isolated K4 nodes appended */
+  int32_t use_connection_nodes;  /* data.use_connection_nodes: num_aux_graphs+1 hub nodes prepended */
+  int32_t main_diagonal;         /* data.main_graph_type == 'grid-diagonal' */
+  int32_t aux_diagonal;          /* data.aux_graph_type == 'grid-diagonal' */
+} eg_graph_spec;
+
+typedef struct eg_graph_info {
+  int32_t num_nodes;        /* N per frame, all node types */
+  int32_t num_edges;        /* directed edges per frame, no self loops (== edge_index.shape[1]) */
+  int32_t num_pixel_nodes;  /* N0: nodes with node_type == 0 (contiguous range) */
+  int32_t first_pixel_node; /* == number of connection nodes */
+  int32_t num_coord_nodes;  /* 0 or 4, at the end of the frame */
+  int32_t num_levels;       /* lattice levels: aux 1..n then main */
+  int32_t level_size[EG_MAX_LEVELS];   /* side length of each lattice */
+  int32_t level_offset[EG_MAX_LEVELS]; /* first node of each lattice inside the frame */
+  int32_t max_degree;       /* largest in-degree incl. the GCN self loop */
+  int32_t crop_offset;      /* centre-crop offset c of the finest aux level (datasets.py:502) */
+} eg_graph_info;
+
+const char* eg_version(void);
+const char* eg_last_error(void);
+/* Bytes of scratch the compute entry points below need (independent of the batch size). */
+size_t eg_workspace_bytes(void);
+
+/* ---- static hierarchical graph: replaces create_graphs + from_networkx + Batch collate ------------
+ * (src/core/datasets.py:375-521 and :258; PyG Batch.from_data_list offsets).  Built once, on device,
+ * as a symmetric CSR sorted by (target, source) with the GCN self loop last in every row and the
+ * symmetric normalisation deg^-1/2[u] * deg^-1/2[v] stored per entry (PyG gcn_norm, recomputed every
+ * layer every step by the reference, src/core/models.py:330). */
+int eg_graph_create(const eg_graph_spec* spec, int device, eg_graph** out);
+void eg_graph_destroy(eg_graph* g);
+int eg_graph_get_info(const eg_graph* g, eg_graph_info* info);
+/* Host-side closed form of the same graph (no GPU needed): fills info only. */
+int eg_graph_spec_info(const eg_graph_spec* spec, eg_graph_info* info);
+/* Device pointers of the per-frame CSR (rowptr int32[N+1], col int32[nnz], w float[nnz], dis float[N]);
+ * nnz = num_edges + num_nodes. */
+int eg_graph_csr(const eg_graph* g, const int32_t** rowptr, const int32_t** col, const float** w,
+                 const float** dis);
+/* edge_index exactly as the reference's loader produces it for a batch of `batch` frames:
+ * int64[2, batch*num_edges], grouped by source in the networkx insertion order, frame b offset by
+ * b*num_nodes.  `out` is a DEVICE pointer. */
+int eg_graph_export_edge_index(const eg_graph* g, int batch, int64_t* out, void* stream);
+/* Same on the host, no GPU needed (`out` is a HOST pointer): lets a data loader emit the tensor the
+ * reference builds with networkx in ~3 s per sample. */
+int eg_graph_host_edge_index(const eg_graph_spec* spec, int batch, int64_t* out);
+/* node_type float64[batch*N] (0 pixel, 1 coordinate, 2 connection; datasets.py:386-460), HOST pointer. */
+int eg_graph_host_node_type(const eg_graph_spec* spec, int batch, double* out);
+/* Validates a caller-supplied batched edge_index (DEVICE int64[2, num_cols]) against the static graph;
+ * writes the number of mismatching entries to *mismatch (DEVICE int32, set to -1 on a shape mismatch). */
+int eg_graph_check_edge_index(const eg_graph* g, int batch, const int64_t* edge_index, int64_t num_cols,
+                              int32_t* mismatch, void* stream);
+
+/* ---- node-feature packing: replaces the per-frame permute/reshape/cat loop --------------------------
+ * (src/core/models.py:722-756).  maps[l] = DEVICE float[batch, F, s_l, s_l] (NCHW) for lattice level l;
+ * `maps` itself is a HOST array of num_levels pointers.  head = float[batch, first_pixel_node, F]
+ * (connection-node rows) or NULL; tail = float[batch, num_coord_nodes, F] or NULL.
+ * X = float[batch*N, F] node-major.  The _grad form scatters dX back (d_maps etc. are outputs). */
+int eg_pack_nodes(const eg_graph* g, int batch, const float* const* maps, const float* head,
+                  const float* tail, float* X, void* stream);
+int eg_pack_nodes_grad(const eg_graph* g, int batch, const float* dX, float* const* d_maps, float* d_head,
+                       float* d_tail, void* stream);
+
+/* ---- message passing: out = A_hat * in, A_hat = D^-1/2 (A+I) D^-1/2 -------------------------------
+ * replaces PyG GCNConv.propagate / torch_scatter.scatter_add (called from src/core/models.py:431).
+ * in/out: float[batch*N, F], F in {64,128,256}.  Atomic-free segmented reduction over the sorted CSR;
+ * A_hat is symmetric, so the same call is the backward. */
+int eg_gcn_aggregate(const eg_graph* g, int batch, int feat, const float* in, float* out, void* stream);
+
+/* ---- one GCNConv: H = A_hat * X * W^T + bias, plus the batch statistics BatchNorm1d needs ----------
+ * replaces gnn_layers[i].module_0 (+ the statistics pass of module_1), src/core/models.py:329-332.
+ * X,H: float[batch*N,128]; W: float[128(out),128(in)]; bias: float[128] or NULL.
+ * If mean/var are non-NULL they receive the per-column mean and BIASED variance of H over all rows
+ * (deterministic two-stage reduction).  ws: eg_workspace_bytes() bytes of device scratch. */
+int eg_gcn_conv_fwd(const eg_graph* g, int batch, const float* X, const float* W, const float* bias,
+                    float* H, float* mean, float* var, void* ws, size_t ws_bytes, void* stream);
+/* Backward of the above given dH: dX = A_hat*(dH*W) (+ dX_add if non-NULL, the residual branch),
+ * dW = (A_hat*dH)^T X, dbias = column sums of dH.  scratch: float[batch*N,128] for A_hat*dH. */
+int eg_gcn_conv_bwd(const eg_graph* g, int batch, const float* X, const float* W, const float* dH,
+                    const float* dX_add, float* dX, float* dW, float* dbias, float* scratch, void* ws,
+                    size_t ws_bytes, void* stream);
+
+/* ---- fused BatchNorm1d-apply + Dropout + ReLU|Identity + residual ----------------------------------
+ * replaces gnn_layers[i].module_1..3 and `h + hidden_embeds[i]` (src/core/models.py:332-335,434-435)
+ * and the BN/ReLU/Dropout triples of the classifiers (:366-373).
+ * Y = act(drop(gamma*(H-mean)*rsqrt(var+eps)+beta)) + res.   rows x cols, cols in {16..128, %4==0}.
+ * Dropout keeps an element when hash(seed, row*cols+col) >= p (counter-based, recomputed in backward;
+ * eg_dropout_mask exports it for parity tests).  res may be NULL. */
+int eg_bn_act_fwd(int64_t rows, int cols, const float* H, const float* mean, const float* var,
+                  const float* gamma, const float* beta, float eps, float drop_p, uint64_t seed, int relu,
+                  const float* res, float* Y, void* stream);
+/* Backward.  batch_stats != 0: train-mode BN (gradient flows through mean/var); 0: eval mode.
+ * Outputs dH (may alias dY), dgamma, dbeta (float[cols]).  The residual gradient is dY itself. */
+int eg_bn_act_bwd(int64_t rows, int cols, const float* dY, const float* H, const float* mean,
+                  const float* var, const float* gamma, const float* beta, float eps, float drop_p,
+                  uint64_t seed, int relu, int batch_stats, float* dH, float* dgamma, float* dbeta, void* ws,
+                  size_t ws_bytes, void* stream);
+/* mask float[rows*cols] in {0, 1/(1-p)} — the factor eg_bn_act_fwd applied. */
+int eg_dropout_mask(int64_t rows, int cols, float drop_p, uint64_t seed, float* mask, void* stream);
+/* Per-column mean and biased variance of Z float[rows, cols]. */
+int eg_col_stats(int64_t rows, int cols, const float* Z, float* mean, float* var, void* ws, size_t ws_bytes,
+                 void* stream);
+
+/* ---- dense per-node transforms (tensor cores, 3xTF32 error-compensated => fp32-class accuracy) -----
+ * replaces nn.Linear inside GCNConv.lin and node_classifiers[k][0] stacked over k
+ * (src/core/models.py:330,364).  C[rows,128] = A[rows,128] * op(W) + bias, op(W) = W^T when
+ * trans_w != 0 (nn.Linear forward), W otherwise (its input gradient).  mean/var optional as above. */
+int eg_linear128(int64_t rows, const float* A, const float* W, int trans_w, const float* bias,
+                 const float* addend, float* C, float* mean, float* var, void* ws, size_t ws_bytes,
+                 void* stream);
+/* dW[128,128] = G^T X (nn.Linear weight gradient, G = dOut[rows,128], X = input[rows,128]);
+ * dbias = column sums of G (may be NULL). */
+int eg_linear128_wgrad(int64_t rows, const float* G, const float* X, float* dW, float* dbias, void* ws,
+                       size_t ws_bytes, void* stream);
+
+/* ---- classifier tail: 4 block-diagonal heads 32 -> 16 -> 1 -----------------------------------------
+ * replaces node_classifiers[k][4] and [8] for k = 0..3 (src/core/models.py:369-375).
+ * A1: float[rows,128] (activated layer-1 output, head k in columns 32k..32k+31);
+ * W2: float[4,16,32], b2: float[4,16]; Z2: float[rows,64] (+ optional column stats).
+ * A2: float[rows,64]; W3: float[4,16]; b3: float[4]; logits: float[rows,4]. */
+int eg_clf_mid_fwd(int64_t rows, const float* A1, const float* W2, const float* b2, float* Z2, float* mean,
+                   float* var, void* ws, size_t ws_bytes, void* stream);
+int eg_clf_mid_bwd(int64_t rows, const float* A1, const float* W2, const float* dZ2, float* dA1, float* dW2,
+                   float* db2, void* ws, size_t ws_bytes, void* stream);
+int eg_clf_out_fwd(int64_t rows, const float* A2, const float* W3, const float* b3, int sigmoid,
+                   float* out, void* stream);
+int eg_clf_out_bwd(int64_t rows, const float* A2, const float* W3, const float* out, const float* dout,
+                   int sigmoid, float* dA2, float* dW3, float* db3, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- losses ----------------------------------------------------------------------------------------
+ * eg_bce_multilevel: replaces WeightedBCEWithLogitsLoss.compute (src/core/criterion.py:13-27,30-34):
+ * loss = loss_weight * sum(valid * w(y) * bce_with_logits(x, y)) / sum(valid), w = ones_weight if y==1
+ * (and ones_weight > 1).  n = number of elements (B*N0*4).  loss_out: DEVICE float[1];
+ * dlogits (optional): d loss / d logits. */
+int eg_bce_multilevel(int64_t n, const float* logits, const float* y, const float* valid, float ones_weight,
+                      float loss_weight, float* loss_out, float* dlogits, void* ws, size_t ws_bytes,
+                      void* stream);
+/* eg_expected_landmark_mse: replaces ExpectedLandmarkMSE.compute (src/core/criterion.py:93-151).
+ * logits/y/valid: float[batch, n0, channels] where n0 = sum(level_size^2); levels given explicitly. */
+int eg_expected_landmark_mse(int batch, int channels, int num_levels, const int32_t* level_size,
+                             const float* logits, const float* y, const float* valid, float loss_weight,
+                             float* loss_out, float* dlogits, void* ws, size_t ws_bytes, void* stream);
+/* Multi-level one-hot labels on device from landmark pixel coordinates — replaces create_node_labels
+ * (src/core/datasets.py:523-549).  coords: DEVICE int32[batch, channels, 2] (h, w) in [0, frame);
+ * y: float[batch, n0, channels]. */
+int eg_node_labels(int batch, int channels, int frame_size, int num_levels, const int32_t* level_size,
+                   const int32_t* coords, float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECHOGLAD_B200_H */

@@ -1,0 +1,162 @@
+"""CPU tier: the C-ABI library loads and exports every symbol include/echoglad_b200.h declares; host-side
+closed forms (graph, node types) are bit-exact against the golden vectors; host logic of the drop-in
+modules (constructor kwargs, state_dict layout, registry patching) — no GPU compute calls."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def eg():
+    from echoglad_b200.build import build
+    build()
+    import echoglad_b200
+    return echoglad_b200
+
+
+def test_every_declared_symbol_is_exported_and_bound(eg):
+    header = open(os.path.join(ROOT, "include", "echoglad_b200.h")).read()
+    declared = set(re.findall(r"\b(eg_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    from echoglad_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert eg.lib.eg_workspace_bytes() > 0
+    assert b"sm_100a" in eg.lib.eg_version()
+
+
+def test_missing_library_fails_loudly():
+    code = ("import echoglad_b200._lib as l, os, sys\n")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    src = ("import importlib, sys, os\n"
+           "import echoglad_b200._lib as L\n"
+           "L.LIB_PATH = '/nonexistent/libechoglad_b200.so'\n"
+           "try:\n    L._load()\nexcept ImportError as e:\n    print('IMPORTERROR', e)\n")
+    out = subprocess.run([sys.executable, "-c", src], capture_output=True, text=True, env=env, cwd=ROOT)
+    assert "IMPORTERROR" in out.stdout and "no CPU fallback" in out.stdout, out.stdout + out.stderr
+
+
+def _spec(eg, key):
+    s, n, mo, co, cn, mt, at = key.split("_")
+    return eg.HierGraphSpec(frame_size=int(s[1:]), num_aux_graphs=max(int(n[1:]), 1),
+                            use_main_graph_only=mo == "mo1", use_coordinate_graph=co == "co1",
+                            use_connection_nodes=cn == "cn1", main_graph_type=mt, aux_graph_type=at)
+
+
+def test_host_closed_form_graph_bit_exact(eg):
+    z = np.load(os.path.join(GOLDEN, "graphs_small.npz"))
+    keys = sorted({k.split("/")[0] for k in z.files})
+    for k in keys:
+        spec = _spec(eg, k)
+        ei = spec.host_edge_index(1).numpy()
+        assert np.array_equal(ei, z[k + "/edge_index"].astype(np.int64)), k
+        assert np.array_equal(spec.host_node_type(1), z[k + "/node_type"].astype(np.float64)), k
+        meta = spec.info()
+        assert meta.num_edges == ei.shape[1] and meta.num_nodes == z[k + "/node_type"].shape[0]
+    # batched = block-diagonal offsets (PyG collate)
+    spec = _spec(eg, "S12_n3_mo0_co0_cn0_grid_grid")
+    one, three = spec.host_edge_index(1), spec.host_edge_index(3)
+    n = spec.info().num_nodes
+    assert torch.equal(three, torch.cat([one + b * n for b in range(3)], dim=1))
+
+
+def test_host_closed_form_graph_hashes_224(eg):
+    h = json.load(open(os.path.join(GOLDEN, "graph_hashes.json")))
+    for k, v in h["specs"].items():
+        spec = _spec(eg, k)
+        ei = spec.host_edge_index(1).numpy()
+        assert ei.shape[1] == v["num_edges"]
+        assert hashlib.sha256(ei.tobytes()).hexdigest() == v["edge_index_sha256"], k
+        assert hashlib.sha256(spec.host_node_type(1).tobytes()).hexdigest() == v["node_type_sha256"], k
+    meta = eg.HierGraphSpec().info()
+    assert (meta.num_nodes, meta.num_edges, meta.max_degree, meta.crop_offset) == (72020, 430200, 10, 8)
+    assert meta.level_offset == (0, 4, 20, 84, 340, 1364, 5460, 21844)
+    big = eg.HierGraphSpec(frame_size=448, num_aux_graphs=8).info()
+    assert (big.num_nodes, big.num_edges) == (288084, 1724664)
+
+
+def test_malformed_spec_is_rejected(eg):
+    with pytest.raises(eg.EchogladError, match="malformed"):
+        eg.HierGraphSpec(frame_size=448, num_aux_graphs=7).info()  # 2^7 < 448/2
+    with pytest.raises(eg.EchogladError):
+        eg.HierGraphSpec(frame_size=1, num_aux_graphs=1).info()
+    with pytest.raises(ValueError):
+        eg.HierGraphSpec(main_graph_type="hex").info()
+
+
+DEFAULT_KW = dict(frame_size=224, gnn_dropout_p=0.5, classifier_dropout_p=0.5, node_embedding_dim=128,
+                  node_hidden_dim=128, num_output_channels=4, num_gnn_layers=3, num_aux_graphs=7,
+                  gnn_jk_mode='last', classifier_hidden_dim=32, residual=True, use_coordinate_graph=False,
+                  output_activation='logit', use_connection_nodes=False, use_main_graph_only=False)
+
+
+def test_state_dict_layout_is_the_references(eg):
+    from oracle import restated as R
+    m = eg.UNETHierarchicalPatchModel(encoder_embedding_widths=[128, 64, 32, 16, 8, 4, 2],
+                                      encoder_embedding_dims=[8, 16, 32, 64, 128, 256, 512], **DEFAULT_KW)
+    sd = m.state_dict()
+    assert sum(p.numel() for p in m.parameters()) == 8073948
+    assert sd["gnn_layers.0.module_0.lin.weight"].shape == (128, 128)
+    assert sd["gnn_layers.2.module_1.num_batches_tracked"].dtype == torch.int64
+    assert sd["node_classifiers.3.8.weight"].shape == (1, 16)
+    assert sd["linears.7.weight"].shape == (128, 4, 1, 1)
+    ref_layout = R.init_landmark_state(R.Cfg())  # loaded strict=True into the REFERENCE class by make_golden.py
+    assert set(sd) == set(ref_layout)
+    for k in sd:
+        assert sd[k].shape == ref_layout[k].shape, k
+    m.load_state_dict(ref_layout, strict=True)
+    base = eg.HierarchicalPatchModel(**DEFAULT_KW)
+    assert set(base.state_dict()) == {k for k in sd if k.startswith(("gnn_layers", "node_classifiers"))}
+    emb = eg.CNN(out_channels=[4], kernel_sizes=[3], pool_sizes=[1], cnn_dropout_p=0.1)
+    emb.load_state_dict(R.init_embedder_state(4), strict=True)
+    assert sum(p.numel() for p in emb.parameters()) == 56
+
+
+def test_unsupported_configs_fail_loudly_and_cpu_inputs_are_rejected(eg):
+    kw = dict(DEFAULT_KW)
+    with pytest.raises(NotImplementedError):
+        eg.HierarchicalPatchModel(**{**kw, "node_hidden_dim": 64})
+    with pytest.raises(NotImplementedError):
+        eg.HierarchicalPatchModel(**{**kw, "use_coordinate_graph": True})
+    with pytest.raises(TypeError):
+        eg.HierarchicalPatchModel(**{**kw, "output_activation": "tanh"})
+    with pytest.raises(AssertionError):
+        eg.HierarchicalPatchModel(**{**kw, "gnn_jk_mode": "mean"})
+    m = eg.HierarchicalPatchModel(**{**kw, "frame_size": 12, "num_aux_graphs": 3})
+    with pytest.raises(eg.EchogladError, match="no CPU fallback"):
+        m(x=torch.randn(1, 128, 12, 12))
+    bce = eg.WeightedBCEWithLogitsLoss(reduction='none', ones_weight=9000, loss_weight=1)
+    with pytest.raises(eg.EchogladError):
+        bce.compute(torch.zeros(1, 4, 4), torch.zeros(1, 4, 4), torch.ones(4, 4))
+
+
+def test_registry_patch_replaces_only_hot_path_entries(eg):
+    from echoglad_b200 import register
+    models = {'cnn': object, 'unet_hierarchical_patch': object, 'hierarchicalpatch': object, 'unet': object}
+    criteria = {'mse': object, 'WeightedBceWithLogits': object, 'ExpectedLandmarkMse': object}
+    register.patch(models, criteria)
+    assert models['unet_hierarchical_patch'] is eg.UNETHierarchicalPatchModel
+    assert models['hierarchicalpatch'] is eg.HierarchicalPatchModel
+    assert models['cnn'] is object and models['unet'] is object
+    assert criteria['WeightedBceWithLogits'] is eg.WeightedBCEWithLogitsLoss
+    assert criteria['ExpectedLandmarkMse'] is eg.ExpectedLandmarkMSE and criteria['mse'] is object
+    # builder-style construction: MODELS[name](**config['landmark']) with the engine-injected keys
+    cfg = dict(encoder_embedding_widths=[128, 64, 32, 16, 8, 4, 2], encoder_embedding_dims=[8, 16, 32, 64, 128, 256, 512],
+               **DEFAULT_KW)
+    assert isinstance(models['unet_hierarchical_patch'](**cfg), torch.nn.Module)
+    c = criteria['ExpectedLandmarkMse'](batch_size=2, frame_size=224, num_aux_graphs=7, use_main_graph_only=False,
+                                        num_output_channels=4, loss_weight=10)
+    assert c.grid_sizes == [2, 4, 8, 16, 32, 64, 128, 224]

@@ -1,0 +1,459 @@
+"""GPU tier (`-m gpu`): every CUDA entry point, called through the C ABI, against the CPU oracle
+(`oracle/restated.py`) on the same seeded inputs and against the golden fixtures minted from the
+reference.  Integer work (graph, labels) is bit-exact; floating point uses
+|a-b| <= rtol*|b| + atol_frac*max|b| with rtol=1e-4, atol_frac=1e-5 for activations/logits,
+rel 1e-4 for scalar losses, and rtol=1e-3, atol_frac=1e-4 for gradients."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restated as R
+from tests._golden import GOLDEN, MODEL_CASES, close, grads_close, load_case
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import echoglad_b200 as eg
+    from echoglad_b200 import ops
+    DEV = torch.device("cuda", 0)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _spec_from_key(key):
+    s, n, mo, co, cn, mt, at = key.split("_")
+    return eg.HierGraphSpec(frame_size=int(s[1:]), num_aux_graphs=max(int(n[1:]), 1),
+                            use_main_graph_only=mo == "mo1", use_coordinate_graph=co == "co1",
+                            use_connection_nodes=cn == "cn1", main_graph_type=mt, aux_graph_type=at)
+
+
+def _oracle_edge_index(spec):
+    return R.build_edge_index(spec.frame_size, spec.num_aux_graphs, main_only=spec.use_main_graph_only,
+                              coord=spec.use_coordinate_graph, conn=spec.use_connection_nodes,
+                              main_type=spec.main_graph_type, aux_type=spec.aux_graph_type)
+
+
+# ---- graph --------------------------------------------------------------------------------------------------
+
+def test_device_edge_index_bit_exact_small_specs():
+    z = np.load(os.path.join(GOLDEN, "graphs_small.npz"))
+    for k in sorted({k.split("/")[0] for k in z.files}):
+        spec = _spec_from_key(k)
+        g = eg.DeviceGraph(spec, DEV)
+        want = torch.from_numpy(z[k + "/edge_index"].astype(np.int64))
+        n = g.meta.num_nodes
+        got = g.edge_index(3).cpu()
+        assert torch.equal(got, R.batch_edge_index(want, n, 3)), k
+        assert g.count_edge_index_mismatches(got.to(DEV), 3) == 0
+        bad = got.clone()
+        bad[1, 5] += 1
+        assert g.count_edge_index_mismatches(bad.to(DEV), 3) == 1
+        assert g.count_edge_index_mismatches(got[:, :-1].to(DEV), 3) == -1
+
+
+def test_device_edge_index_default_yml_hash_and_csr():
+    h = json.load(open(os.path.join(GOLDEN, "graph_hashes.json")))["specs"]
+    for key in ("S224_n7_mo0_co0_cn0_grid_grid", "S224_n0_mo1_co0_cn0_grid_grid", "S224_n7_mo0_co0_cn1_grid_grid"):
+        g = eg.DeviceGraph(_spec_from_key(key), DEV)
+        ei = g.edge_index(1).cpu().numpy()
+        assert hashlib.sha256(ei.tobytes()).hexdigest() == h[key]["edge_index_sha256"], key
+        rowptr, col, w, dis = (t.cpu() for t in g.csr())
+        n = g.meta.num_nodes
+        deg = torch.bincount(torch.from_numpy(ei[1]), minlength=n) + 1
+        assert torch.equal((rowptr[1:] - rowptr[:-1]).long(), deg)
+        last = col[(rowptr[1:] - 1).long()]
+        assert torch.equal(last.long(), torch.arange(n))  # self loop last
+        # rows sorted ascending (self loop excluded)
+        rows = torch.repeat_interleave(torch.arange(n), deg)
+        is_last = torch.zeros_like(col, dtype=torch.bool)
+        is_last[(rowptr[1:] - 1).long()] = True
+        same_row = rows[1:] == rows[:-1]
+        inc = col[1:] > col[:-1]
+        assert bool((inc | ~same_row | is_last[1:]).all())
+        ref_dis = deg.float().pow(-0.5)
+        assert torch.allclose(dis, ref_dis, rtol=2e-7, atol=0)
+        assert torch.allclose(w, dis[col.long()] * dis[rows], rtol=0, atol=0)
+
+
+# ---- aggregation ----------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("key,batch", [("S12_n3_mo0_co0_cn0_grid_grid", 3), ("S16_n3_mo0_co0_cn1_grid_grid", 2),
+                                       ("S12_n3_mo0_co1_cn1_grid_grid", 2), ("S9_n0_mo1_co0_cn0_grid-diagonal_grid", 4),
+                                       ("S32_n4_mo0_co0_cn0_grid_grid", 2)])
+@pytest.mark.parametrize("feat", [64, 128, 256])
+def test_aggregate_matches_oracle(key, batch, feat):
+    spec = _spec_from_key(key)
+    g = eg.DeviceGraph(spec, DEV)
+    ei, nt = _oracle_edge_index(spec)
+    n = nt.shape[0]
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(batch * n, feat, generator=gen)
+    want = R.gcn_conv(x.double(), R.batch_edge_index(ei, n, batch), torch.eye(feat, dtype=torch.float64), None)
+    got = ops.gcn_aggregate(g, batch, x.to(DEV)).cpu()
+    ok, worst = close(got, want, 1e-5, 1e-6)
+    assert ok, worst
+    again = ops.gcn_aggregate(g, batch, x.to(DEV)).cpu()
+    assert torch.equal(got, again)  # deterministic: no atomics
+
+
+def test_aggregate_full_graph_linearity_and_symmetry():
+    """default.yml size (72,020 nodes x 4 frames): properties instead of an element-wise oracle."""
+    spec = eg.HierGraphSpec()
+    g = eg.DeviceGraph.get(spec, DEV)
+    b, n = 4, g.meta.num_nodes
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(b * n, 128, device=DEV, generator=gen)
+    y = torch.randn(b * n, 128, device=DEV, generator=gen)
+    ax, ay = ops.gcn_aggregate(g, b, x), ops.gcn_aggregate(g, b, y)
+    lin = ops.gcn_aggregate(g, b, 2.0 * x - 3.0 * y)
+    ok, worst = close(lin.cpu(), (2.0 * ax - 3.0 * ay).cpu(), 1e-4, 1e-5)
+    assert ok, worst
+    # <A x, y> == <x, A y>  (A_hat symmetric)
+    lhs, rhs = (ax.double() * y.double()).sum().item(), (x.double() * ay.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), 1.0)
+    # A_hat sqrt(deg) = sqrt(deg)  (eigenvector of the normalised adjacency)
+    _, _, _, dis = g.csr()
+    v = (1.0 / dis).repeat(b).unsqueeze(1).repeat(1, 128).contiguous()
+    ok, worst = close(ops.gcn_aggregate(g, b, v).cpu(), v.cpu(), 1e-5, 1e-6)
+    assert ok, worst
+
+
+# ---- dense transforms -----------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("rows", [1, 127, 128, 1000, 40000])
+@pytest.mark.parametrize("trans", [True, False])
+def test_linear128_3xtf32_fp32_class_accuracy(rows, trans):
+    gen = torch.Generator().manual_seed(rows)
+    a = torch.randn(rows, 128, generator=gen) * 3
+    w = torch.randn(128, 128, generator=gen)
+    bias = torch.randn(128, generator=gen)
+    add = torch.randn(rows, 128, generator=gen)
+    want = a.double() @ (w.double().t() if trans else w.double()) + bias.double() + add.double()
+    got, mean, var = ops.linear128(a.to(DEV), w.to(DEV), trans, bias.to(DEV), add.to(DEV), stats=True)
+    ok, worst = close(got.cpu(), want, 2e-6, 2e-6)  # far tighter than plain TF32 (1e-3) could meet
+    assert ok, worst
+    ok, worst = close(mean.cpu(), want.mean(0), 1e-5, 1e-5)
+    assert ok, worst
+    ok, worst = close(var.cpu(), want.var(0, unbiased=False), 1e-4, 1e-5)
+    assert ok, worst
+    # in place (C aliases A) is part of the contract used by eg_gcn_conv_fwd
+    a_dev = a.to(DEV)
+    check_inplace = ops.lib.eg_linear128(rows, a_dev.data_ptr(), w.to(DEV).data_ptr(), int(trans), None, None,
+                                         a_dev.data_ptr(), None, None, None, 0,
+                                         torch.cuda.current_stream().cuda_stream)
+    assert check_inplace == 0
+    want2 = a.double() @ (w.double().t() if trans else w.double())
+    ok, worst = close(a_dev.cpu(), want2, 2e-6, 2e-6)
+    assert ok, worst
+
+
+@pytest.mark.parametrize("rows", [5, 64, 777, 50000])
+def test_linear128_wgrad(rows):
+    gen = torch.Generator().manual_seed(rows)
+    g = torch.randn(rows, 128, generator=gen)
+    x = torch.randn(rows, 128, generator=gen)
+    dw, db = ops.linear128_wgrad(g.to(DEV), x.to(DEV))
+    ok, worst = close(dw.cpu(), g.double().t() @ x.double(), 1e-5, 1e-5)
+    assert ok, worst
+    ok, worst = close(db.cpu(), g.double().sum(0), 1e-5, 1e-5)
+    assert ok, worst
+
+
+# ---- BN + dropout + act + residual ----------------------------------------------------------------------------
+
+@pytest.mark.parametrize("cols", [64, 128])
+@pytest.mark.parametrize("relu,drop_p,batch_stats,res", [(1, 0.0, 1, True), (0, 0.0, 1, False), (1, 0.5, 1, True),
+                                                         (1, 0.3, 0, False), (0, 0.0, 0, True)])
+def test_bn_act_fwd_bwd(cols, relu, drop_p, batch_stats, res):
+    rows = 3001
+    gen = torch.Generator().manual_seed(cols + relu)
+    h = (torch.randn(rows, cols, generator=gen) * 2 + 0.5).to(DEV)
+    gamma = (torch.rand(cols, generator=gen) + 0.5).to(DEV)
+    beta = torch.randn(cols, generator=gen).to(DEV)
+    resid = torch.randn(rows, cols, generator=gen).to(DEV) if res else None
+    dy = torch.randn(rows, cols, generator=gen).to(DEV)
+    seed = 1234
+    if batch_stats:
+        mean, var = ops.col_stats(h)
+        ok, worst = close(mean.cpu(), h.double().mean(0).cpu(), 1e-5, 1e-5)
+        assert ok, worst
+        ok, worst = close(var.cpu(), h.double().var(0, unbiased=False).cpu(), 1e-5, 1e-5)
+        assert ok, worst
+    else:
+        mean = torch.randn(cols, generator=gen).to(DEV) * 0.1
+        var = (torch.rand(cols, generator=gen) + 0.5).to(DEV)
+    y = ops.bn_act_fwd(h, mean, var, gamma, beta, 1e-5, drop_p, seed, relu, resid)
+    mask = ops.dropout_mask(rows, cols, drop_p, seed, DEV)
+    if drop_p > 0:
+        keep = (mask > 0).float().mean().item()
+        assert abs(keep - (1 - drop_p)) < 0.01
+        assert torch.all((mask == 0) | ((mask - 1 / (1 - drop_p)).abs() < 1e-6))
+    # oracle in fp64 with autograd
+    hd = h.double().cpu().requires_grad_(True)
+    gd, bd = gamma.double().cpu().requires_grad_(True), beta.double().cpu().requires_grad_(True)
+    if batch_stats:
+        m, v = hd.mean(0), hd.var(0, unbiased=False)
+    else:
+        m, v = mean.double().cpu(), var.double().cpu()
+    o = (hd - m) / torch.sqrt(v + 1e-5) * gd + bd
+    o = o * mask.double().cpu()
+    if relu:
+        o = torch.relu(o)
+    if res:
+        o = o + resid.double().cpu()
+    ok, worst = close(y.cpu(), o.detach(), 1e-5, 1e-5)
+    assert ok, worst
+    o.backward(dy.double().cpu())
+    dh, dg, db = ops.bn_act_bwd(dy, h, mean, var, gamma, beta, 1e-5, drop_p, seed, relu, batch_stats)
+    for got, want, name in ((dh, hd.grad, "dh"), (dg, gd.grad, "dgamma"), (db, bd.grad, "dbeta")):
+        ok, worst = close(got.cpu(), want, 1e-4, 1e-5)
+        assert ok, (name, worst)
+
+
+# ---- labels and losses ------------------------------------------------------------------------------------------
+
+def test_node_labels_bit_exact():
+    z = np.load(os.path.join(GOLDEN, "labels.npz"))
+    for k in sorted({k.split("/")[0] for k in z.files}):
+        f, n, mo = (int(v) for v in z[k + "/meta"])
+        sizes = R.level_sizes(f, n, bool(mo))
+        coords = torch.from_numpy(z[k + "/coords"].astype(np.int32)).unsqueeze(0).to(DEV)
+        y = ops.node_labels(coords, f, sizes)[0].cpu().numpy().astype(np.int8)
+        assert np.array_equal(y, z[k + "/y"]), k
+    frames, coords, y, valid = R.synthetic_batch(5, 224, 7, seed=3)
+    got = ops.node_labels(coords.to(DEV), 224, R.level_sizes(224, 7)).view(-1, 4).cpu()
+    assert torch.equal(got, y)
+
+
+@pytest.mark.parametrize("frame,naux,main_only,batch", [(12, 3, False, 3), (224, 7, False, 2), (16, 1, True, 4)])
+def test_losses_match_oracle(frame, naux, main_only, batch):
+    sizes = R.level_sizes(frame, naux, main_only)
+    n0 = sum(s * s for s in sizes)
+    gen = torch.Generator().manual_seed(frame)
+    logits = (torch.randn(batch * n0, 4, generator=gen) * 3).requires_grad_(True)
+    _, _, y, valid = R.synthetic_batch(batch, frame, naux, main_only=main_only, seed=9)
+    valid = valid.clone()
+    valid[:n0, 1] = 0.0
+    valid[n0:2 * n0:3, 3] = 0.0
+    want_bce = R.weighted_bce_with_logits(logits.view(batch, -1, 4), y.view(batch, -1, 4), valid, 9000.0, 1.0)
+    want_elm = R.expected_landmark_mse(logits, y, valid, batch_size=batch, frame_size=frame, num_aux_graphs=naux,
+                                       use_main_graph_only=main_only, loss_weight=10.0)
+    g_bce, = torch.autograd.grad(want_bce, logits)
+    g_elm, = torch.autograd.grad(want_elm, logits)
+    x = logits.detach().to(DEV).requires_grad_(True)
+    bce = eg.WeightedBCEWithLogitsLoss(reduction='none', ones_weight=9000, loss_weight=1)
+    elm = eg.ExpectedLandmarkMSE(loss_weight=10, batch_size=batch, frame_size=frame, num_aux_graphs=naux,
+                                 use_main_graph_only=main_only, num_output_channels=4)
+    l1 = bce.compute(x.view(batch, -1, 4), y.to(DEV).view(batch, -1, 4), valid.to(DEV))
+    l2 = elm.compute(x.view(batch, -1, 4), y.to(DEV).view(batch, -1, 4), valid.to(DEV))
+    assert abs(l1.item() - want_bce.item()) <= 1e-4 * abs(want_bce.item())
+    assert abs(l2.item() - want_elm.item()) <= 1e-4 * abs(want_elm.item())
+    (3.0 * l1).backward()
+    ok, worst = close(x.grad.cpu(), 3.0 * g_bce, 1e-4, 1e-6)
+    assert ok, worst
+    x.grad = None
+    l2.backward()
+    ok, worst = close(x.grad.cpu(), g_elm, 1e-3, 1e-5)
+    assert ok, worst
+
+
+# ---- packing ------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("key", ["S12_n3_mo0_co0_cn0_grid_grid", "S16_n3_mo0_co0_cn1_grid_grid",
+                                 "S16_n0_mo1_co0_cn0_grid_grid"])
+def test_pack_nodes_fwd_bwd(key):
+    spec = _spec_from_key(key)
+    g = eg.DeviceGraph(spec, DEV)
+    batch = 3
+    gen = torch.Generator().manual_seed(2)
+    maps = [torch.randn(batch, 128, s, s, generator=gen) for s in g.meta.level_size]
+    cfg = R.Cfg(frame_size=spec.frame_size, num_aux_graphs=spec.num_aux_graphs,
+                use_main_graph_only=spec.use_main_graph_only, use_connection_nodes=spec.use_connection_nodes)
+    full = maps if not spec.use_main_graph_only else maps
+    want = R.pack_nodes(cfg, full)
+    dev_maps = [m.to(DEV).requires_grad_(True) for m in maps]
+    head = None
+    if g.meta.first_pixel_node:
+        head = torch.stack([m.mean(dim=(2, 3)) for m in dev_maps], dim=1)
+    x = ops.PackNodes.apply(g, head, None, *dev_maps)
+    assert torch.allclose(x.cpu(), want, rtol=1e-6, atol=1e-6)
+    dx = torch.randn(x.shape, generator=gen)
+    x.backward(dx.to(DEV))
+    cpu_maps = [m.clone().requires_grad_(True) for m in maps]
+    R.pack_nodes(cfg, cpu_maps).backward(dx)
+    for a, b in zip(dev_maps, cpu_maps):
+        assert torch.allclose(a.grad.cpu(), b.grad, rtol=1e-5, atol=1e-6)
+
+
+# ---- whole module against the reference's golden vectors ----------------------------------------------------------
+
+def _build_module(cfg, variant):
+    kw = dict(frame_size=cfg.frame_size, gnn_dropout_p=cfg.gnn_dropout_p, classifier_dropout_p=cfg.classifier_dropout_p,
+              node_embedding_dim=128, node_hidden_dim=128, num_output_channels=4, num_gnn_layers=cfg.num_gnn_layers,
+              num_aux_graphs=cfg.num_aux_graphs, gnn_jk_mode=cfg.gnn_jk_mode, classifier_hidden_dim=32,
+              residual=cfg.residual, use_coordinate_graph=False, output_activation=cfg.output_activation,
+              use_connection_nodes=cfg.use_connection_nodes, use_main_graph_only=cfg.use_main_graph_only)
+    if variant == "unet":
+        return eg.UNETHierarchicalPatchModel(encoder_embedding_widths=[128, 64, 32, 16, 8, 4, 2],
+                                             encoder_embedding_dims=[8, 16, 32, 64, 128, 256, 512], **kw)
+    return eg.HierarchicalPatchModel(**kw)
+
+
+def _criteria(cfg, batch):
+    bce = eg.WeightedBCEWithLogitsLoss(reduction='none', ones_weight=9000, loss_weight=1)
+    elm = eg.ExpectedLandmarkMSE(loss_weight=10, batch_size=batch, frame_size=cfg.frame_size,
+                                 num_aux_graphs=cfg.num_aux_graphs, use_main_graph_only=cfg.use_main_graph_only,
+                                 num_output_channels=4)
+    return bce, elm
+
+
+@pytest.mark.parametrize("stem", list(MODEL_CASES))
+def test_module_matches_reference_golden(stem):
+    c = load_case(stem)
+    cfg, z, batch = c["cfg"], c["z"], c["batch"]
+    model = _build_module(cfg, cfg.variant).to(DEV)
+    model.load_state_dict(c["sd"], strict=True)
+    model.train(c["training"])
+    x = c["x"].to(DEV).requires_grad_(c["training"])
+    ei = model.graph_spec.host_edge_index(batch).to(DEV)  # what the reference loader would pass
+    logits, coords = model(x=x, node_coords=None, edge_index=ei, batch_idx=None, node_type=None)
+    assert coords is None
+    want_logits = z["logits"]
+    got = logits.detach().cpu()
+    if "S224" in stem:
+        got = got[::97]
+    ok, worst = close(got, want_logits, 1e-4, 1e-5)
+    assert ok, f"logits {worst}"
+    bce, elm = _criteria(cfg, batch)
+    y, valid = c["y"].to(DEV), c["valid"].to(DEV)
+    l1 = bce.compute(logits.view(batch, -1, 4), y.view(batch, -1, 4), valid)
+    l2 = elm.compute(logits.view(batch, -1, 4), y.view(batch, -1, 4), valid)
+    assert abs(l1.item() - float(z["loss_bce"])) <= 1e-4 * abs(float(z["loss_bce"]))
+    assert abs(l2.item() - float(z["loss_elmse"])) <= 1e-4 * abs(float(z["loss_elmse"]))
+    if not c["training"]:
+        return
+    (l1 + l2).backward()
+    if "grad_x" in z.files:
+        ok, worst = close(x.grad.cpu(), z["grad_x"], 1e-3, 1e-4)
+        assert ok, f"grad_x {worst}"
+    params = dict(model.named_parameters())
+    want = {k[5:]: z[k] for k in z.files if k.startswith("grad/")}
+    bad = grads_close({k: params[k].grad.cpu() for k in want}, want)
+    assert not bad, bad
+    sd = model.state_dict()
+    for k in z.files:
+        if k.startswith("stat/"):
+            ok, worst = close(sd[k[5:]].cpu(), z[k], 1e-4, 1e-5)
+            assert ok, f"{k} {worst}"
+        elif k.startswith("gradsum/"):
+            g = params[k[8:]].grad.double()
+            assert abs(g.abs().sum().item() - z[k][1]) <= 2e-3 * abs(z[k][1]) + 1e-12, k
+
+
+def test_module_train_with_dropout_matches_oracle_given_same_masks():
+    """Train mode with dropout ON: the counter-based masks are exported (eg_dropout_mask) and handed to
+    the oracle, which then must agree on logits, loss and gradients."""
+    cfg = R.Cfg(variant="avgpool", frame_size=12, num_aux_graphs=3, gnn_dropout_p=0.5, classifier_dropout_p=0.5)
+    batch = 3
+    sd = R.init_landmark_state(cfg, seed=5)
+    model = _build_module(cfg, "avgpool").to(DEV)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    gen = torch.Generator().manual_seed(6)
+    x_cpu = torch.randn(batch, 128, 12, 12, generator=gen)
+    _, _, y, valid = R.synthetic_batch(batch, 12, 3, seed=4)
+    x = x_cpu.to(DEV).requires_grad_(True)
+    seeds = {f"gnn{i}": model._seed(i) for i in range(3)}
+    clf_seed = model._seed(101)
+    logits, _ = model(x=x)
+    bce, elm = _criteria(cfg, batch)
+    loss = bce.compute(logits.view(batch, -1, 4), y.to(DEV).view(batch, -1, 4), valid.to(DEV)) + \
+        elm.compute(logits.view(batch, -1, 4), y.to(DEV).view(batch, -1, 4), valid.to(DEV))
+    loss.backward()
+    rows = batch * 228
+    masks = {k: ops.dropout_mask(rows, 128, 0.5, s, DEV).cpu() for k, s in seeds.items()}
+    ma = ops.dropout_mask(rows, 128, 0.5, clf_seed, DEV).cpu()
+    mb = ops.dropout_mask(rows, 64, 0.5, clf_seed + 1, DEV).cpu()
+    for k in range(4):
+        masks[f"clf{k}a"] = ma[:, 32 * k:32 * k + 32]
+        masks[f"clf{k}b"] = mb[:, 16 * k:16 * k + 16]
+    osd = R.clone_state(sd, requires_grad=True)
+    xo = x_cpu.clone().requires_grad_(True)
+    ei1, nt1 = R.build_edge_index(12, 3)
+    lo = R.landmark_forward(osd, cfg, xo, R.batch_edge_index(ei1, 228, batch), np.tile(nt1, batch), True, masks)
+    want = R.total_loss(lo, y, valid, cfg, batch)
+    ok, worst = close(logits.detach().cpu(), lo.detach(), 1e-4, 1e-5)
+    assert ok, worst
+    assert abs(loss.item() - want["total"].item()) <= 1e-4 * abs(want["total"].item())
+    want["total"].backward()
+    ok, worst = close(x.grad.cpu(), xo.grad, 1e-3, 1e-4)
+    assert ok, worst
+    params = dict(model.named_parameters())
+    bad = grads_close({k: params[k].grad.cpu() for k in params},
+                      {k: osd[k].grad.numpy() for k in params})
+    assert not bad, bad
+
+
+def test_module_is_deterministic_and_validates_edge_index():
+    cfg = R.Cfg(variant="avgpool", frame_size=12, num_aux_graphs=3, gnn_dropout_p=0.5, classifier_dropout_p=0.5)
+    sd = R.init_landmark_state(cfg, seed=8)
+    outs = []
+    for _ in range(2):
+        model = _build_module(cfg, "avgpool").to(DEV)
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        x = torch.randn(2, 128, 12, 12, generator=torch.Generator().manual_seed(1)).to(DEV).requires_grad_(True)
+        logits, _ = model(x=x)
+        logits.square().sum().backward()
+        outs.append((logits.detach().clone(), x.grad.clone(), model.gnn_layers[0].module_0.lin.weight.grad.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    # a foreign edge_index (here: of a different spec) is rejected on the first call
+    model = _build_module(cfg, "avgpool").to(DEV)
+    eg.DeviceGraph._cache.clear()
+    wrong = eg.HierGraphSpec(frame_size=12, num_aux_graphs=3, main_graph_type="grid-diagonal").host_edge_index(2)
+    with pytest.raises(eg.EchogladError):
+        model(x=torch.randn(2, 128, 12, 12, device=DEV), edge_index=wrong.to(DEV))
+    with pytest.raises(eg.EchogladError):
+        model(x=torch.randn(2, 128, 12, 12))  # CPU input: no fallback
+
+
+def test_default_yml_batch2_against_oracle():
+    """BASELINE.json configs[0]: default.yml, batch 2, forward + both losses (+ backward) vs the CPU oracle."""
+    cfg = R.Cfg(gnn_dropout_p=0.0, classifier_dropout_p=0.0)
+    batch = 2
+    sd = R.init_landmark_state(cfg, seed=200)
+    esd = R.init_embedder_state(4, seed=201)
+    frames, coords, y, valid = R.synthetic_batch(batch, 224, 7, seed=200)
+    model = _build_module(cfg, "unet").to(DEV)
+    model.load_state_dict(sd, strict=True)
+    emb = eg.CNN(out_channels=[4], kernel_sizes=[3], pool_sizes=[1], cnn_dropout_p=0.0).to(DEV)
+    emb.load_state_dict(esd, strict=True)
+    model.train()
+    emb.train()
+    logits, _ = model(x=emb(frames.to(DEV)))
+    bce, elm = _criteria(cfg, batch)
+    yd = ops.node_labels(coords.to(DEV), 224, R.level_sizes(224, 7)).view(-1, 4)
+    assert torch.equal(yd.cpu(), y)
+    loss = bce.compute(logits.view(batch, -1, 4), yd.view(batch, -1, 4), valid.to(DEV)) + \
+        elm.compute(logits.view(batch, -1, 4), yd.view(batch, -1, 4), valid.to(DEV))
+    loss.backward()
+    # oracle
+    osd, oesd = R.clone_state(sd, True), R.clone_state(esd, True)
+    ei, nt = R.build_edge_index(224, 7)
+    n = nt.shape[0]
+    xo = R.embedder_forward(oesd, frames, True)
+    lo = R.landmark_forward(osd, cfg, xo, R.batch_edge_index(ei, n, batch), np.tile(nt, batch), True)
+    want = R.total_loss(lo, y, valid, cfg, batch)
+    ok, worst = close(logits.detach().cpu(), lo.detach(), 1e-4, 1e-5)
+    assert ok, worst
+    assert abs(loss.item() - want["total"].item()) <= 1e-4 * abs(want["total"].item())
+    want["total"].backward()
+    params = dict(model.named_parameters())
+    keys = [k for k in params if k.startswith(("gnn_layers.", "node_classifiers.", "linears."))]
+    bad = grads_close({k: params[k].grad.cpu() for k in keys}, {k: osd[k].grad.numpy() for k in keys})
+    assert not bad, bad
