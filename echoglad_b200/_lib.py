@@ -66,6 +66,10 @@ SIGNATURES = {
     "eg_bce_multilevel": (_I, [_L, _P, _P, _P, _F, _F, _P, _P, _P, _SZ, _P]),
     "eg_expected_landmark_mse": (_I, [_I, _I, _I, C.POINTER(C.c_int32), _P, _P, _P, _F, _P, _P, _P, _SZ, _P]),
     "eg_node_labels": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int32), _P, _P, _P]),
+    "eg_profile_enable": (_I, [_I]),
+    "eg_profile_read": (_I, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(_L)]),
+    "eg_profile_names": (_I, [C.c_char_p, _SZ]),
+    "eg_launch_count": (_L, []),
 }
 
 
@@ -97,3 +101,19 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib.eg_last_error().decode(errors="replace")
         raise EchogladError(f"{what or 'echoglad_b200'} failed (code {rc}): {msg}")
+
+
+def profile_enable(on: bool) -> None:
+    check(lib.eg_profile_enable(int(on)), "eg_profile_enable")
+
+
+def profile_report() -> dict:
+    """{name: (total_ms, spans)} for everything recorded since profile_enable(True)."""
+    buf = C.create_string_buffer(4096)
+    check(lib.eg_profile_names(buf, 4096), "eg_profile_names")
+    out = {}
+    for name in filter(None, buf.value.decode().split(",")):
+        ms, cnt = C.c_double(), _L()
+        check(lib.eg_profile_read(name.encode(), C.byref(ms), C.byref(cnt)), "eg_profile_read")
+        out[name] = (ms.value, cnt.value)
+    return out

@@ -1,7 +1,8 @@
 """Builds `echoglad_b200/libechoglad_b200.so` in-tree with nvcc for sm_100a (no torch headers: the
 library is a plain C-ABI CUDA library, see include/echoglad_b200.h).
 
-    python -m echoglad_b200.build [--force] [--verbose]
+    python echoglad_b200/build.py [--force] [--verbose]      (run as a script: importing the package
+                                                              itself already requires the built library)
 """
 from __future__ import annotations
 

@@ -114,6 +114,7 @@ int launch_aggregate(const eg_graph* g, int batch, int feat, const float* in, fl
   const eg_graph_info& info = graph_info(g);
   const long long rows = (long long)batch * info.num_nodes;
   const int threads = kWarpsPerBlock * 32;
+  ProfileScope prof("aggregate", s);
   if (feat == 128) {
     unsigned blocks = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
     agg_csr_kernel<1><<<blocks, threads, 0, s>>>(graph_rowptr(g), graph_col(g), graph_w(g), info.num_nodes, rows, in, out);

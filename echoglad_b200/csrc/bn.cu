@@ -280,6 +280,7 @@ int launch_col_sums(long long rows, int cols, const float* Z, float* sums, void*
   }
   double* parts = reinterpret_cast<double*>(ws);
   const int grid = reduce_grid(rows, cols);
+  ProfileScope prof("col_stats", s);
   col_stats_kernel<<<grid, kThreads, 0, s>>>(rows, cols, Z, parts);
   EG_LAUNCH_CHECK();
   sums_finalize_kernel<<<1, 128, 0, s>>>(grid, cols, parts, sums);
@@ -299,6 +300,7 @@ int eg_bn_act_fwd(int64_t rows, int cols, const float* H, const float* mean, con
   const uint32_t thr = drop_threshold(drop_p);
   const float ks = thr ? 1.0f / (1.0f - drop_p) : 1.0f;
   const long long groups = rows * (cols / 4);
+  ProfileScope prof("bn_act_fwd", as_stream(stream));
   bn_act_fwd_kernel<<<elem_grid(groups), kThreads, 0, as_stream(stream)>>>(rows, cols, H, mean, var, gamma, beta,
                                                                            eps, thr, ks, seed, relu, res, Y);
   EG_LAUNCH_CHECK();
@@ -322,6 +324,7 @@ int eg_bn_act_bwd(int64_t rows, int cols, const float* dY, const float* H, const
   double* parts = reinterpret_cast<double*>(ws);
   float* coef = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);  // 2*cols floats
   const int grid = reduce_grid(rows, cols);
+  ProfileScope prof("bn_act_bwd", s);
   bn_act_bwd_reduce_kernel<<<grid, kThreads, 0, s>>>(rows, cols, dY, H, mean, var, gamma, beta, eps, thr, ks, seed,
                                                      relu, batch_stats ? nullptr : dH, parts);
   EG_LAUNCH_CHECK();

@@ -257,6 +257,7 @@ int eg_clf_mid_fwd(int64_t rows, const float* A1, const float* W2, const float* 
   long long ntiles = (rows + TR - 1) / TR;
   int grid = (int)(ntiles < kMaxParts ? ntiles : kMaxParts);
   double* parts = stats ? reinterpret_cast<double*>(ws) : nullptr;
+  ProfileScope prof("clf_mid_fwd", as_stream(stream));
   clf_mid_fwd_kernel<<<grid, kMidThreads, 0, as_stream(stream)>>>(rows, A1, W2, b2, Z2, parts);
   EG_LAUNCH_CHECK();
   if (stats) return launch_stats_finalize(grid, 64, 64, rows, parts, mean, var, as_stream(stream));
@@ -273,6 +274,7 @@ int eg_clf_mid_bwd(int64_t rows, const float* A1, const float* W2, const float* 
   long long ntiles = (rows + TR - 1) / TR;
   int grid = (int)(ntiles < kMaxParts ? ntiles : kMaxParts);
   float* parts = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);
+  ProfileScope prof("clf_mid_bwd", as_stream(stream));
   clf_mid_bwd_kernel<<<grid, kMidThreads, 0, as_stream(stream)>>>(rows, A1, W2, dZ2, dA1, parts);
   EG_LAUNCH_CHECK();
   parts_reduce_kernel<<<(kMidPart + 255) / 256, 256, 0, as_stream(stream)>>>(grid, kMidPart, parts, 2048, dW2, db2);
@@ -286,6 +288,7 @@ int eg_clf_out_fwd(int64_t rows, const float* A2, const float* W3, const float* 
   long long blocks = (rows * 16 + 255) / 256;
   long long cap = (long long)kNumSMs * 16;
   int grid = (int)(blocks < cap ? blocks : cap);
+  ProfileScope prof("clf_out_fwd", as_stream(stream));
   clf_out_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(rows, A2, W3, b3, sigmoid, out);
   EG_LAUNCH_CHECK();
   return EG_OK;
@@ -302,6 +305,7 @@ int eg_clf_out_bwd(int64_t rows, const float* A2, const float* W3, const float* 
   long long blocks = (rows + 15) / 16;
   int grid = (int)(blocks < kMaxParts ? blocks : kMaxParts);
   float* parts = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);
+  ProfileScope prof("clf_out_bwd", as_stream(stream));
   clf_out_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(rows, A2, W3, out, dout, sigmoid, dA2, parts);
   EG_LAUNCH_CHECK();
   parts_reduce_kernel<<<1, 128, 0, as_stream(stream)>>>(grid, kOutPart, parts, 64, dW3, db3);

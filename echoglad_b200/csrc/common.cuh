@@ -6,9 +6,25 @@
 
 #include "../../include/echoglad_b200.h"
 
+#include <atomic>
+
 namespace eg {
 
 void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+// brackets the kernels of one launch helper with CUDA events when eg_profile_enable(1) is active
+class ProfileScope {
+ public:
+  ProfileScope(const char* name, cudaStream_t s);
+  ~ProfileScope();
+ private:
+  const char* name_;
+  cudaStream_t stream_;
+  bool on_;
+  void* beg_ = nullptr;
+  void* end_ = nullptr;
+};
 
 #define EG_CHECK_ARG(cond, ...)                 \
   do {                                          \
@@ -27,7 +43,12 @@ void set_error(const char* fmt, ...);
     }                                                                                       \
   } while (0)
 
-#define EG_LAUNCH_CHECK() EG_CUDA(cudaGetLastError())
+// after every kernel launch: counts the launch (eg_launch_count) and surfaces launch errors
+#define EG_LAUNCH_CHECK()                          \
+  do {                                             \
+    eg::g_launches.fetch_add(1, std::memory_order_relaxed); \
+    EG_CUDA(cudaGetLastError());                   \
+  } while (0)
 
 constexpr int kNumSMs = 148;            // B200
 constexpr int kMaxParts = 4 * kNumSMs;  // upper bound on per-CTA partial slots of any reduction

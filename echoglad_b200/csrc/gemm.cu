@@ -308,6 +308,7 @@ int launch_linear128(long long rows, const float* A, const float* W, int trans_w
   long long ntiles = (rows + TM - 1) / TM;
   int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
   if (grid < 1) grid = 1;
+  ProfileScope prof("linear128", s);
   double* parts = stats ? reinterpret_cast<double*>(ws) : nullptr;
   linear128_kernel<<<grid, kThreads, smem, s>>>(rows, A, W, trans_w, bias, addend, C, parts);
   EG_LAUNCH_CHECK();
@@ -335,6 +336,7 @@ int launch_wgrad128(long long rows, const float* G, const float* X, float* dW, f
   if (grid < 1) grid = 1;
   double* colsum = reinterpret_cast<double*>(ws);
   float* parts = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);
+  ProfileScope prof("wgrad128", s);
   wgrad128_kernel<<<grid, kThreads, smem, s>>>(rows, G, X, parts, dbias ? colsum : nullptr);
   EG_LAUNCH_CHECK();
   wgrad_reduce_kernel<<<(128 * 128 + 255) / 256, 256, 0, s>>>(grid, parts, dbias ? colsum : nullptr, dW, dbias);

@@ -287,6 +287,7 @@ int eg_bce_multilevel(int64_t n, const float* logits, const float* y, const floa
   int grid = (int)(blocks < kMaxParts ? blocks : kMaxParts);
   double* parts = reinterpret_cast<double*>(ws);
   float* scale = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);
+  ProfileScope prof("bce", s);
   bce_kernel<<<grid, kThreads, 0, s>>>(n4, n, logits, y, valid, ones_weight, dlogits, parts);
   EG_LAUNCH_CHECK();
   bce_finalize_kernel<<<1, 32, 0, s>>>(grid, parts, loss_weight, loss_out, scale);
@@ -313,6 +314,7 @@ int eg_expected_landmark_mse(int batch, int channels, int num_levels, const int3
   }
   cudaStream_t s = as_stream(stream);
   SegStat* seg = reinterpret_cast<SegStat*>(ws);
+  ProfileScope prof("elmse", s);
   elmse_stats_kernel<<<batch * num_levels, kThreads, 0, s>>>(lv, logits, y, valid, seg);
   EG_LAUNCH_CHECK();
   elmse_finalize_kernel<<<1, 64, 0, s>>>(lv, batch, loss_weight, seg, loss_out);

@@ -67,6 +67,7 @@ int run(const eg_graph* g, int batch, float* const* maps, float* head, float* ta
         cudaStream_t s) {
   const eg_graph_info& info = graph_info(g);
   constexpr int F = EG_F;
+  ProfileScope prof(to_nodes ? "pack_nodes" : "pack_nodes_grad", s);
   for (int l = 0; l < info.num_levels; ++l) {
     if (!maps[l]) continue;  // level without a map (gradient not requested)
     const int P = info.level_size[l] * info.level_size[l];

@@ -186,6 +186,16 @@ int eg_expected_landmark_mse(int batch, int channels, int num_levels, const int3
 int eg_node_labels(int batch, int channels, int frame_size, int num_levels, const int32_t* level_size,
                    const int32_t* coords, float* y, void* stream);
 
+/* ---- measurement hooks (no reference counterpart) ---------------------------------------------------
+ * eg_profile_enable(1) clears and starts recording CUDA-event spans around every launch helper on the
+ * caller's stream; eg_profile_read sums the device time and span count recorded under `name`
+ * (synchronises on the recorded events); eg_profile_names lists the recorded names, comma separated.
+ * eg_launch_count: number of kernels this library has launched in this process. */
+int eg_profile_enable(int on);
+int eg_profile_read(const char* name, double* total_ms, int64_t* launches);
+int eg_profile_names(char* buf, size_t n);
+int64_t eg_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,8 +19,9 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 @pytest.fixture(scope="module")
 def eg():
-    from echoglad_b200.build import build
-    build()
+    sys.path.insert(0, ROOT)
+    import __graft_entry__
+    __graft_entry__.build()
     import echoglad_b200
     return echoglad_b200
 

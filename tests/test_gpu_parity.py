@@ -138,8 +138,9 @@ def test_linear128_3xtf32_fp32_class_accuracy(rows, trans):
     assert ok, worst
     ok, worst = close(mean.cpu(), want.mean(0), 1e-5, 1e-5)
     assert ok, worst
-    ok, worst = close(var.cpu(), want.var(0, unbiased=False), 1e-4, 1e-5)
-    assert ok, worst
+    # E[x^2]-E[x]^2 in double over fp32 partials: absolute error scales with E[x^2], not with var
+    tol = 1e-5 * float((want ** 2).mean(0).max())
+    assert float((var.cpu().double() - want.var(0, unbiased=False)).abs().max()) <= tol
     # in place (C aliases A) is part of the contract used by eg_gcn_conv_fwd
     a_dev = a.to(DEV)
     check_inplace = ops.lib.eg_linear128(rows, a_dev.data_ptr(), w.to(DEV).data_ptr(), int(trans), None, None,
