@@ -120,7 +120,7 @@ def cpu_oracle_step_factory(batch: int):
         loss = R.total_loss(logits, y, valid, cfg, batch)["total"]
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     return step
 
@@ -242,6 +242,21 @@ def run_native(args):
         step_resident()
     torch.cuda.synchronize()
 
+    if args.torch_profile:  # per-op CUDA time of one steady-state step (diagnostic, not a bench value)
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as p:
+            step_resident()
+            torch.cuda.synchronize()
+        with open(args.torch_profile, "w") as fh:
+            fh.write(p.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=80))
+    if args.ncu_range:  # `ncu --profile-from-start off`: only the steps below are captured
+        torch.cuda.profiler.start()
+        for _ in range(args.steps):
+            step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+
     sampler = ClockSampler(local) if rank == 0 else None
     _lib.profile_enable(True)
     launches0 = int(_lib.lib.eg_launch_count())
@@ -315,6 +330,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cudnn-tf32", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-range", action="store_true", help="wrap --steps steps in cudaProfilerStart/Stop and exit")
+    ap.add_argument("--torch-profile", default="", help="write a torch.profiler table of one step to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
