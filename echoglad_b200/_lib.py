@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libechoglad_b200.so")
+LIB_PATH = os.environ.get("EG_LIB_PATH") or os.path.join(_PKG, "libechoglad_b200.so")  # override: dev builds
 
 EG_MAX_LEVELS = 16
 
@@ -44,6 +44,7 @@ SIGNATURES = {
     "eg_graph_get_info": (_I, [_P, C.POINTER(GraphInfo)]),
     "eg_graph_spec_info": (_I, [C.POINTER(GraphSpec), C.POINTER(GraphInfo)]),
     "eg_graph_csr": (_I, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "eg_graph_tiles": (_I, [_P, C.POINTER(_P), C.POINTER(C.c_int32)]),
     "eg_graph_export_edge_index": (_I, [_P, _I, _P, _P]),
     "eg_graph_host_edge_index": (_I, [C.POINTER(GraphSpec), _I, _P]),
     "eg_graph_host_node_type": (_I, [C.POINTER(GraphSpec), _I, _P]),

@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
     "--cudart", "shared",
 ]
+NVCC_FLAGS += os.environ.get("EG_NVCC_EXTRA", "").split()  # e.g. -DEG_TC_TIMING (development only)
 
 
 def _nvcc() -> str:

@@ -16,6 +16,10 @@ int launch_linear128(long long rows, const float* A, const float* W, int trans_w
                      cudaStream_t s);
 int launch_wgrad128(long long rows, const float* G, const float* X, float* dW, float* dbias, void* ws,
                     size_t ws_bytes, cudaStream_t s);
+int launch_gcn_tc(const eg_graph* g, int batch, const float* X, const float* W, int trans_w, const float* bias,
+                  const float* addend, float* Out, float* AggOut, float* mean, float* var, void* ws, size_t ws_bytes,
+                  cudaStream_t s);
+bool legacy_mma();
 int launch_col_sums(long long rows, int cols, const float* Z, float* sums, void* ws, size_t ws_bytes,
                     cudaStream_t s);
 }  // namespace eg
@@ -29,6 +33,8 @@ int eg_gcn_conv_fwd(const eg_graph* g, int batch, const float* X, const float* W
   EG_CHECK_ARG(X != H, "eg_gcn_conv_fwd: X and H must not alias");
   cudaStream_t s = as_stream(stream);
   const long long rows = (long long)batch * graph_info(g).num_nodes;
+  if (!legacy_mma())  // one fused tcgen05 kernel: gather -> 3xTF32 MMA -> bias + statistics epilogue
+    return launch_gcn_tc(g, batch, X, W, 1, bias, nullptr, H, nullptr, mean, var, ws, ws_bytes, s);
   int rc = launch_aggregate(g, batch, EG_F, X, H, s);  // H <- A_hat X
   if (rc) return rc;
   // H <- H W^T + b, in place: every CTA reads its row tile into shared memory before writing it back
@@ -42,7 +48,12 @@ int eg_gcn_conv_bwd(const eg_graph* g, int batch, const float* X, const float* W
   EG_CHECK_ARG(scratch != dH && scratch != dX, "eg_gcn_conv_bwd: scratch must not alias dH / dX");
   cudaStream_t s = as_stream(stream);
   const long long rows = (long long)batch * graph_info(g).num_nodes;
-  int rc = launch_aggregate(g, batch, EG_F, dH, scratch, s);  // G = A_hat dH
+  int rc;
+  const bool fused = dX && !legacy_mma();
+  if (fused)  // G = A_hat dH (side output) and dX = G W + dX_add in one pass over dH
+    rc = launch_gcn_tc(g, batch, dH, W, 0, nullptr, dX_add, dX, scratch, nullptr, nullptr, ws, ws_bytes, s);
+  else
+    rc = launch_aggregate(g, batch, EG_F, dH, scratch, s);  // G = A_hat dH
   if (rc) return rc;
   if (dW) {
     EG_CHECK_ARG(X, "eg_gcn_conv_bwd: dW requested but X is NULL");
@@ -53,7 +64,7 @@ int eg_gcn_conv_bwd(const eg_graph* g, int batch, const float* X, const float* W
     rc = launch_col_sums(rows, EG_F, dH, dbias, ws, ws_bytes, s);
     if (rc) return rc;
   }
-  if (dX) {
+  if (dX && !fused) {
     rc = launch_linear128(rows, scratch, W, 0, nullptr, dX_add, dX, nullptr, nullptr, ws, ws_bytes, s);
     if (rc) return rc;
   }

@@ -5,6 +5,8 @@
 //
 // v1 of this file uses warp-level mma.sync.m16n8k8.tf32 (legacy tensor path).  The tcgen05/TMEM
 // version fused with the aggregation lives in gcn_fused.cu when present.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 using namespace eg;
@@ -288,6 +290,18 @@ __global__ void wgrad_reduce_kernel(int nparts, const float* __restrict__ parts,
 
 namespace eg {
 
+// EG_LEGACY_MMA=1 routes the dense transforms through the v1 mma.sync kernels (debug / A-B switch only)
+bool legacy_mma() {
+  static const bool v = [] {
+    const char* e = getenv("EG_LEGACY_MMA");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+int launch_linear_tc(long long rows, const float* A, const float* W, int trans_w, const float* bias,
+                     const float* addend, float* C, float* mean, float* var, void* ws, size_t ws_bytes,
+                     cudaStream_t s);
+
 int launch_stats_finalize(int nparts, int cols, int stride, long long rows, const double* parts, float* mean,
                           float* var, cudaStream_t s);  // bn.cu
 
@@ -352,6 +366,8 @@ int eg_linear128(int64_t rows, const float* A, const float* W, int trans_w, cons
                  const float* addend, float* C, float* mean, float* var, void* ws, size_t ws_bytes,
                  void* stream) {
   EG_CHECK_ARG(rows >= 1 && A && W && C, "eg_linear128: bad arguments");
+  if (!legacy_mma())
+    return launch_linear_tc(rows, A, W, trans_w, bias, addend, C, mean, var, ws, ws_bytes, as_stream(stream));
   return launch_linear128(rows, A, W, trans_w, bias, addend, C, mean, var, ws, ws_bytes, as_stream(stream));
 }
 

@@ -29,6 +29,12 @@ struct eg_graph {
   int32_t* col;     // [nnz]   sources, ascending, self loop last
   float* w;         // [nnz]   dis[src]*dis[dst]
   float* dis;       // [N]
+  // Output-tile table of the tensor-core kernels: tiles of 128 node ids (-1 = padding).  Lattice levels
+  // whose side is a multiple of 16 are cut into 8 x 16 patches so that the stencil neighbours of a tile
+  // (up/down/left/right rows, the 2x2 children, the parent) are shared inside the tile and hit L1; all
+  // other nodes are packed in index order.  Every node of the frame appears exactly once.
+  int32_t* tile_nodes;  // [tiles_per_frame][128]
+  int tiles_per_frame;
 };
 
 using namespace eg;
@@ -106,6 +112,36 @@ void fill_info(const Topo& t, eg_graph_info* info, int num_edges, int max_degree
   }
   info->max_degree = max_degree;
   info->crop_offset = t.crop;
+}
+
+std::vector<int32_t> build_tiles(const Topo& t) {
+  std::vector<int32_t> tiles, run;
+  auto flush_run = [&](bool final_flush) {
+    size_t full = run.size() / 128 * 128;
+    tiles.insert(tiles.end(), run.begin(), run.begin() + full);
+    run.erase(run.begin(), run.begin() + full);
+    if (final_flush && !run.empty()) {
+      run.resize(128, -1);
+      tiles.insert(tiles.end(), run.begin(), run.end());
+      run.clear();
+    }
+  };
+  for (int v = 0; v < t.nconn; ++v) run.push_back(v);
+  for (int l = 0; l < t.nlev; ++l) {
+    const int p = t.lsize[l], off = t.loff[l];
+    if (p % 16 == 0) {
+      for (int a0 = 0; a0 < p; a0 += 8)
+        for (int b0 = 0; b0 < p; b0 += 16)
+          for (int a = a0; a < a0 + 8; ++a)
+            for (int b = b0; b < b0 + 16; ++b) tiles.push_back(off + a * p + b);
+    } else {
+      for (int v = 0; v < p * p; ++v) run.push_back(off + v);
+    }
+  }
+  for (int v = t.N - t.ncoord; v < t.N; ++v) run.push_back(v);
+  flush_run(false);
+  flush_run(true);
+  return tiles;
 }
 
 int init_topo(const eg_graph_spec* spec, Topo& t) {
@@ -229,6 +265,12 @@ int eg_graph_create(const eg_graph_spec* spec, int device, eg_graph** out) {
   EG_TRY(cudaMalloc(&g->w, sizeof(float) * nnz));
   fill_kernel<<<blocks, threads>>>(t, g->rowptr, g->dis, g->col, g->w);
   EG_TRY(cudaGetLastError());
+  {
+    std::vector<int32_t> tiles = build_tiles(t);
+    g->tiles_per_frame = (int)(tiles.size() / 128);
+    EG_TRY(cudaMalloc(&g->tile_nodes, sizeof(int32_t) * tiles.size()));
+    EG_TRY(cudaMemcpy(g->tile_nodes, tiles.data(), sizeof(int32_t) * tiles.size(), cudaMemcpyHostToDevice));
+  }
   std::vector<int32_t> hdeg(t.N);
   EG_TRY(cudaMemcpy(hdeg.data(), deg, sizeof(int32_t) * t.N, cudaMemcpyDeviceToHost));
   int maxd = 0;
@@ -249,6 +291,7 @@ void eg_graph_destroy(eg_graph* g) {
   cudaFree(g->col);
   cudaFree(g->w);
   cudaFree(g->dis);
+  cudaFree(g->tile_nodes);
   delete g;
 }
 
@@ -265,6 +308,13 @@ int eg_graph_csr(const eg_graph* g, const int32_t** rowptr, const int32_t** col,
   if (col) *col = g->col;
   if (w) *w = g->w;
   if (dis) *dis = g->dis;
+  return EG_OK;
+}
+
+int eg_graph_tiles(const eg_graph* g, const int32_t** tile_nodes, int32_t* tiles_per_frame) {
+  EG_CHECK_ARG(g, "graph is NULL");
+  if (tile_nodes) *tile_nodes = g->tile_nodes;
+  if (tiles_per_frame) *tiles_per_frame = g->tiles_per_frame;
   return EG_OK;
 }
 
@@ -307,4 +357,6 @@ const int32_t* graph_col(const eg_graph* g) { return g->col; }
 const float* graph_w(const eg_graph* g) { return g->w; }
 const float* graph_dis(const eg_graph* g) { return g->dis; }
 int graph_nnz(const eg_graph* g) { return g->nnz; }
+const int32_t* graph_tile_nodes(const eg_graph* g) { return g->tile_nodes; }
+int graph_tiles_per_frame(const eg_graph* g) { return g->tiles_per_frame; }
 }  // namespace eg

@@ -221,15 +221,61 @@ class HierarchicalPatchModel(nn.Module):
         return out
 
 
+class _BNTrain2d(torch.autograd.Function):
+    """Train-mode BatchNorm2d written as a few full-width PyTorch passes.  cuDNN's spatial BN kernels
+    (bn_fw_tr_1C11 / bn_bw_1C11) run ONE CTA per channel, so on the 4..8-channel full-resolution levels of
+    this UNet they use 8 of 148 SMs: measured 43 ms of a 157 ms batch-64 step (profiles/r01a_launches.txt).
+    Out of the hot-path scope (the pyramid stays PyTorch); same arithmetic as nn.BatchNorm2d."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        var, mean = torch.var_mean(x, dim=(0, 2, 3), unbiased=False)
+        invstd = torch.rsqrt(var + eps)
+        scale = weight * invstd
+        y = torch.addcmul((bias - mean * scale).view(1, -1, 1, 1), x, scale.view(1, -1, 1, 1))
+        ctx.save_for_backward(x, weight, mean, invstd)
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, dy, _dm, _dv):
+        x, weight, mean, invstd = ctx.saved_tensors
+        n = x.numel() // x.shape[1]
+        xhat = (x - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
+        dbeta = dy.sum(dim=(0, 2, 3))
+        dgamma = (dy * xhat).sum(dim=(0, 2, 3))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = xhat.mul_((dgamma / n).view(1, -1, 1, 1)).neg_().add_(dy).sub_((dbeta / n).view(1, -1, 1, 1))
+            dx.mul_((weight * invstd).view(1, -1, 1, 1))
+        return dx, dgamma, dbeta, None
+
+
+class _BatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d (same parameters / buffers / state_dict keys) whose CUDA train-mode path is _BNTrain2d."""
+
+    def forward(self, x):
+        if not (self.training and x.is_cuda and self.track_running_stats and self.momentum is not None
+                and x.shape[1] <= 16):
+            return super().forward(x)
+        y, mean, var = _BNTrain2d.apply(x, self.weight, self.bias, self.eps)
+        with torch.no_grad():
+            n = x.numel() // x.shape[1]
+            self.running_mean.mul_(1 - self.momentum).add_(mean, alpha=self.momentum)
+            self.running_var.mul_(1 - self.momentum).add_(var * (n / max(n - 1, 1)), alpha=self.momentum)
+            self.num_batches_tracked += 1
+        return y
+
+
 class _DownConv(nn.Module):
     """conv3x3-ReLU-BN twice, then AdaptiveMaxPool to `out_size` (reference DownConv, models.py:841-856)."""
 
     def __init__(self, cin: int, cout: int, out_size: int):
         super().__init__()
         self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
-        self.BN1 = nn.BatchNorm2d(cout)
+        self.BN1 = _BatchNorm2d(cout)
         self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
-        self.BN2 = nn.BatchNorm2d(cout)
+        self.BN2 = _BatchNorm2d(cout)
         self.out_size = out_size
 
     def forward(self, x):
@@ -244,9 +290,9 @@ class _UpConv(nn.Module):
     def __init__(self, cin: int, cout: int, out_size: int):
         super().__init__()
         self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
-        self.BN1 = nn.BatchNorm2d(cout)
+        self.BN1 = _BatchNorm2d(cout)
         self.conv2 = nn.Conv2d(cin, cout, 3, padding=1)
-        self.BN2 = nn.BatchNorm2d(cout)
+        self.BN2 = _BatchNorm2d(cout)
         self.out_size = out_size
 
     def forward(self, x, skip):
@@ -304,7 +350,7 @@ class CNN(nn.Module):
             super().__init__()
             self.one_by_one_cnn = nn.Conv2d(cin, cout, 1) if cin != cout else None
             self.conv = nn.Conv2d(cin, cout, k, padding=(k - 1) // 2)
-            self.bn = nn.BatchNorm2d(cout)
+            self.bn = _BatchNorm2d(cout)
             self.pool = nn.MaxPool2d(pool)
             self.dropout = nn.Dropout2d(p)
 

@@ -77,6 +77,9 @@ int eg_graph_spec_info(const eg_graph_spec* spec, eg_graph_info* info);
  * nnz = num_edges + num_nodes. */
 int eg_graph_csr(const eg_graph* g, const int32_t** rowptr, const int32_t** col, const float** w,
                  const float** dis);
+/* Output-tile table used by the tensor-core kernels: DEVICE int32[tiles_per_frame][128] node ids of one
+ * frame (-1 = padding), every node exactly once; 8x16 lattice patches where the level allows it. */
+int eg_graph_tiles(const eg_graph* g, const int32_t** tile_nodes, int32_t* tiles_per_frame);
 /* edge_index exactly as the reference's loader produces it for a batch of `batch` frames:
  * int64[2, batch*num_edges], grouped by source in the networkx insertion order, frame b offset by
  * b*num_nodes.  `out` is a DEVICE pointer. */

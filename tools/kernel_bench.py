@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Per-entry-point device timing of the C-ABI library at the default.yml shapes (CUDA events, L2-exceeding
+working sets).  Development aid; the judged numbers come from bench.py.
+
+    python tools/kernel_bench.py [--batch 64] [--iters 10] [--only name,name]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import echoglad_b200 as eg  # noqa: E402
+from echoglad_b200 import ops  # noqa: E402
+from echoglad_b200._lib import WORKSPACE_BYTES, check, lib  # noqa: E402
+
+
+def timeit(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    g = eg.DeviceGraph.get(eg.HierGraphSpec(), dev)
+    B, N = args.batch, g.meta.num_nodes
+    rows = B * N
+    U = rows * 128 * 4
+    gen = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(rows, 128, device=dev, generator=gen)
+    dy = torch.randn(rows, 128, device=dev, generator=gen)
+    w = torch.randn(128, 128, device=dev, generator=gen) * 0.1
+    bias = torch.randn(128, device=dev, generator=gen)
+    gamma = torch.rand(128, device=dev, generator=gen) + 0.5
+    beta = torch.randn(128, device=dev, generator=gen)
+    h = torch.empty_like(x)
+    out = torch.empty_like(x)
+    scratch = torch.empty_like(x)
+    mean, var = torch.empty(128, device=dev), torch.empty(128, device=dev)
+    dw = torch.empty(128, 128, device=dev)
+    ws = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    P = lambda t: t.data_ptr()  # noqa: E731
+
+    cases = {
+        "aggregate": (lambda: check(lib.eg_gcn_aggregate(g.handle, B, 128, P(x), P(h), st)), 2 * U),
+        "gcn_conv_fwd": (lambda: check(lib.eg_gcn_conv_fwd(g.handle, B, P(x), P(w), P(bias), P(h), P(mean), P(var),
+                                                           P(ws), WORKSPACE_BYTES, st)), 2 * U),
+        "gcn_conv_bwd": (lambda: check(lib.eg_gcn_conv_bwd(g.handle, B, P(x), P(w), P(dy), P(h), P(out), P(dw), None,
+                                                           P(scratch), P(ws), WORKSPACE_BYTES, st)), 6 * U),
+        "linear128": (lambda: check(lib.eg_linear128(rows, P(x), P(w), 1, P(bias), None, P(h), P(mean), P(var),
+                                                     P(ws), WORKSPACE_BYTES, st)), 2 * U),
+        "wgrad128": (lambda: check(lib.eg_linear128_wgrad(rows, P(dy), P(x), P(dw), None, P(ws), WORKSPACE_BYTES,
+                                                          st)), 2 * U),
+        "bn_act_fwd": (lambda: check(lib.eg_bn_act_fwd(rows, 128, P(h), P(mean), P(var), P(gamma), P(beta), 1e-5,
+                                                       0.5, 7, 1, P(x), P(out), st)), 3 * U),
+        "bn_act_bwd": (lambda: check(lib.eg_bn_act_bwd(rows, 128, P(dy), P(h), P(mean), P(var), P(gamma), P(beta),
+                                                       1e-5, 0.5, 7, 1, 1, P(out), P(mean.clone()), P(var.clone()),
+                                                       P(ws), WORKSPACE_BYTES, st)), 5 * U),
+    }
+    only = [s for s in args.only.split(",") if s]
+    check(lib.eg_col_stats(rows, 128, P(x), P(mean), P(var), P(ws), WORKSPACE_BYTES, st))
+    res = {}
+    for name, (fn, nbytes) in cases.items():
+        if only and name not in only:
+            continue
+        ms = timeit(fn, args.iters)
+        res[name] = {"ms": round(ms, 4), "algo_GB": round(nbytes / 1e9, 3), "GBps": round(nbytes / ms / 1e6, 1)}
+        if hasattr(lib, "eg_tc_debug_read") and name in ("gcn_conv_fwd", "linear128", "gcn_conv_bwd"):
+            import ctypes as C
+            buf = (C.c_longlong * (148 * 8))()
+            torch.cuda.synchronize()
+            lib.eg_tc_debug_read(buf)
+            import numpy as np
+            a = np.array(buf).reshape(148, 8)[:, :5].mean(0)
+            print(f"   tc wait cycles/CTA: producer-wait-empty {a[0]:.0f}  mma-wait-acc-empty {a[1]:.0f}  "
+                  f"mma-wait-full {a[2]:.0f}  epilogue-wait-acc-full {a[3]:.0f}  total {a[4]:.0f}")
+        print(f"{name:14s} {ms:8.3f} ms   {nbytes / 1e9:6.2f} GB algorithmic   {nbytes / ms / 1e6:8.1f} GB/s", flush=True)
+    print(json.dumps({"batch": B, "rows": rows, "results": res}))
+
+
+if __name__ == "__main__":
+    main()
