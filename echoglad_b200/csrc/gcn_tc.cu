@@ -44,7 +44,7 @@ using namespace eg::tc;
 
 namespace {
 
-constexpr int kStages = 6;
+constexpr int kStages = 4;  // 128 KB of operand ring; the rest of the 256 KB SM array stays L1 for the gather
 constexpr int kProdWarps = 16;             // 8 tile rows per producer warp and stage
 constexpr int kRowsPerProd = 128 / kProdWarps;
 constexpr int kEpiWarps = 4;
@@ -193,6 +193,16 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
         }
       }
       if (GATHER) fbase = p.X + (tile / p.tiles_per_frame) * (long long)p.nodes_per_frame * 128;
+      {  // pull the rows of this CTA's NEXT tile into L2 (4 x 128 B lines per row, lanes j < 4 of each group)
+        const long long nt = tile + gridDim.x;
+        if (nt < p.num_tiles && j < 4) {
+#pragma unroll
+          for (int i = 0; i < kIters; ++i) {
+            const int nr = tile_row<GATHER>(p, nt, pw * kRowsPerProd + i * 4 + g);
+            if (nr >= 0) prefetch_l2(p.X + (long long)nr * 128 + j * 32);
+          }
+        }
+      }
       for (int kc = 0; kc < 4; ++kc, ++chunk) {
         const uint32_t stage = chunk % kStages, phase = (chunk / kStages) & 1u;
         TC_TIMED_WAIT(0, &empty[stage], phase ^ 1u);
@@ -213,7 +223,11 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
                 for (int k = 0; k < 8; ++k) {
                   const int c = __shfl_sync(gmask, ec[i][h], k, 8);
                   x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (k < n) x[k] = ldg4(fbase + (long long)c * 128 + coff);
+                  if (k < n) {
+                    const float* src = fbase + (long long)c * 128 + coff;
+                    x[k] = ldg4(src);
+                    if (j == 0 && kc < 3) prefetch_l1(src + 32);  // next K chunk of this neighbour row -> L1
+                  }
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {

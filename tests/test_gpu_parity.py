@@ -533,7 +533,10 @@ def _hot_path_vs_oracle(cfg, variant, batch, frames_or_x, y, valid, sd, embed_sd
     want["total"].backward()
     params = dict(model.named_parameters())
     keys = [k for k in params if k.startswith(("gnn_layers.", "node_classifiers."))]
-    bad = grads_close({k: params[k].grad.cpu() for k in keys}, {k: osd[k].grad.numpy() for k in keys})
+    # strict_full=False (the 2 x 72,020-node case): see the ReLU-threshold note below; parameter gradients are
+    # sums over 144 k rows, a flipped mask moves individual entries by up to ~1e-2 of their value.
+    gtol = dict(rtol=1e-3, atol_frac=1e-4) if strict_full else dict(rtol=1e-2, atol_frac=1e-3)
+    bad = grads_close({k: params[k].grad.cpu() for k in keys}, {k: osd[k].grad.numpy() for k in keys}, **gtol)
     assert not bad, bad
     # Gradient handed back to the PyTorch pyramid.  At full size (18 M activations per layer) a few
     # BatchNorm outputs sit within rounding of the ReLU threshold, where a 1e-7 forward difference flips the
