@@ -58,6 +58,30 @@ constexpr size_t kStatsBytes = (size_t)kMaxParts * 2 * 128 * sizeof(double);
 constexpr size_t kWgradBytes = (size_t)kNumSMs * 128 * 128 * sizeof(float);
 constexpr size_t kWorkspaceBytes = kStatsBytes + kWgradBytes + 65536;
 
+// Per-tile gather plan of the fused tensor-core kernel (built on the host in graph.cu, device arrays).
+// The unique source rows a tile reads most (own rows, lattice halo, parents) are STAGED in shared memory
+// once per K chunk; a tile row then sums up to 7 staged neighbours, up to 4 FAR neighbours read straight
+// from global (the 2x2 children of an aux node) and its self loop (staged, always last).  Rows that do
+// not fit this shape (hubs of use_connection_nodes, 'grid-diagonal' aux rows) are CSR rows: the plan
+// weights are zero and the row is summed from the device CSR instead.
+constexpr int kPlanSrc = 224;   // staged source rows per tile (224 x 128 B = 28 KB per K chunk)
+constexpr int kPlanStaged = 7;  // staged non-self edges per row
+constexpr int kPlanFar = 4;     // far edges per row
+struct alignas(16) PlanRow {    // 80 bytes
+  uint8_t slot[8];     // [0..6] staged neighbours in summation order, [7] the row itself (self loop)
+  int32_t csr_beg;     // CSR rows: first CSR entry, else 0
+  int32_t csr_deg;     // CSR rows: entries incl. the self loop, else 0
+  float w[8];          // deg^-1/2[u] deg^-1/2[v] of slot[k]; 0 = unused (slot 0 is always a valid row)
+  int32_t far_node[4]; // frame-local node ids read from global; unused = node 0 with weight 0
+  float far_w[4];
+};
+static_assert(sizeof(PlanRow) == 80, "PlanRow layout");
+struct TilePlan {
+  const int4* hdr;      // [tiles] {staged source rows, max staged non-self edges, far edges (0 / 4), has CSR rows}
+  const int32_t* src;   // [tiles][kPlanSrc] staged node ids, ascending (-1 = unused)
+  const PlanRow* rows;  // [tiles][128]
+};
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ---- counter-based dropout RNG: one 64-bit mix per group of 4 consecutive elements -----------------

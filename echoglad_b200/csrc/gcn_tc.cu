@@ -20,10 +20,16 @@
 //     the 32 lanes of a warp hold 32 consecutive features = one coalesced 128-byte store.  No staging.
 //
 // Work decomposition.  Tile = 128 output rows (8x16 lattice patches, see eg_graph::tile_nodes); K is
-// consumed in 4 chunks of 32 features, one ring stage = [128 rows x 128 B] hi + lo = 32 KB, 6 stages, so
-// the producers run up to 1.5 tiles ahead of the tensor core and the per-stage gather working set
-// (~208 neighbour rows x 128 B) stays in L1.  TMEM: 256 columns of weight + 2 x 128 of accumulator.
-// Warps: 0-3 epilogue (TMEM lane quadrant = warp id), 4 MMA issuer, 5.. producers.
+// consumed in 4 chunks of 32 features.  Per chunk, two LOADER warps copy the tile's unique source rows
+// (own rows + lattice halo + parents, <= 224 rows x 128 B, eg::TilePlan) from global into a 3-stage RAW
+// ring with cp.async -- no registers are held, so ~80 KB per SM are in flight and every neighbour row
+// crosses L2 -> SM once per tile instead of once per edge; 16 COMPUTE warps then gather / weight / sum
+// from shared memory: a row's slots and weights sit in registers for the whole tile (PlanRow), the inner
+// loop is branch-free LDS.128 + 4 FFMA per edge; the 2x2 children of an aux node are not staged (512 rows)
+// and are read from global, issued before the staged part.  The sums are split into tf32 hi/lo and fill a
+// 3-stage OPERAND ring ([128 rows x 128 B] hi + lo = 32 KB).
+// TMEM: 256 columns of weight + 2 x 128 of accumulator.
+// Warps: 0-3 epilogue (TMEM lane quadrant = warp id), 4 MMA issuer, 5-6 loaders, 7-22 compute.
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -34,7 +40,9 @@ const int32_t* graph_rowptr(const eg_graph* g);
 const int32_t* graph_col(const eg_graph* g);
 const float* graph_w(const eg_graph* g);
 const int32_t* graph_tile_nodes(const eg_graph* g);
+const int32_t* graph_tile_groups(const eg_graph* g);
 int graph_tiles_per_frame(const eg_graph* g);
+const TilePlan& graph_plan(const eg_graph* g);
 int launch_stats_finalize(int nparts, int cols, int stride, long long rows, const double* parts, float* mean,
                           float* var, cudaStream_t s);
 }  // namespace eg
@@ -44,20 +52,29 @@ using namespace eg::tc;
 
 namespace {
 
-constexpr int kStages = 4;  // 128 KB of operand ring; the rest of the 256 KB SM array stays L1 for the gather
-constexpr int kProdWarps = 16;             // 8 tile rows per producer warp and stage
+constexpr int kStages = 3;                 // operand ring (hi + lo tiles)
+constexpr int kRawStages = 3;              // raw source-row ring
+constexpr int kLoadWarps = 2;
+constexpr int kProdWarps = 16;             // compute warps: 8 tile rows per warp and stage
 constexpr int kRowsPerProd = 128 / kProdWarps;
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = kEpiWarps;
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;
+constexpr int kLoadWarp0 = kMmaWarp + 1;
+constexpr int kProdWarp0 = kLoadWarp0 + kLoadWarps;
+constexpr int kThreads = (kEpiWarps + 1 + kLoadWarps + kProdWarps) * 32;
 constexpr int kTileBytes = 128 * 128;      // one [128 rows x 32 tf32] operand tile
 constexpr uint32_t kABytes = kStages * 2 * kTileBytes;
-constexpr uint32_t kSmemBytes = kABytes + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int kRawRows = kPlanSrc;         // 224 >= 128 (linear mode stages the tile's own rows)
+constexpr uint32_t kRawBytes = kRawRows * 128;
+constexpr uint32_t kSmemBytes = kABytes + kRawStages * kRawBytes + 256 /*barriers*/ + 1024 /*align*/;
 constexpr int kTmemCols = 512;             // [0,128) W hi, [128,256) W lo, [256,384) / [384,512) accumulators
 constexpr uint32_t kTmemAcc = 256;
+static_assert(kPlanSrc % (kLoadWarps * 4) == 0 && kPlanSrc >= 128, "loader mapping");
 
 struct TcParams {
-  const int32_t* tile_nodes;  // GATHER: [tiles_per_frame][128]
+  const int32_t* tile_nodes;   // GATHER: [tiles_per_frame][128]
+  const int32_t* tile_groups;  // GATHER: [tiles_per_frame][16] first node / rows of each 16-row group
+  TilePlan plan;               // GATHER: per-tile staged sources and per-row edges
   int tiles_per_frame;
   int nodes_per_frame;
   long long num_tiles;
@@ -75,19 +92,6 @@ struct TcParams {
   double* stat_parts;         // optional: [gridDim.x][2][128] column sum / sum of squares partials
 };
 
-template <bool GATHER>
-__device__ __forceinline__ int tile_row(const TcParams& p, long long tile, int r) {
-  // global row index of tile row r, or -1
-  if (GATHER) {
-    const long long b = tile / p.tiles_per_frame;
-    const int t = (int)(tile - b * p.tiles_per_frame);
-    const int node = __ldg(p.tile_nodes + t * 128 + r);
-    return node < 0 ? -1 : (int)(b * p.nodes_per_frame + node);
-  }
-  const long long row = tile * 128 + r;
-  return row < p.rows ? (int)row : -1;
-}
-
 #ifdef EG_TC_TIMING
 __device__ long long g_tc_dbg[kNumSMs][8];  // per CTA: cycles spent waiting, by role (see eg_tc_debug_read)
 #define TC_TIMED_WAIT(slot, bar, par)            \
@@ -100,6 +104,21 @@ __device__ long long g_tc_dbg[kNumSMs][8];  // per CTA: cycles spent waiting, by
 #define TC_TIMED_WAIT(slot, bar, par) mbar_wait(bar, par)
 #endif
 
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
+  acc.x = fmaf(w, x.x, acc.x);
+  acc.y = fmaf(w, x.y, acc.y);
+  acc.z = fmaf(w, x.z, acc.z);
+  acc.w = fmaf(w, x.w, acc.w);
+}
+
 template <bool GATHER>
 __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
 #ifdef EG_TC_TIMING
@@ -109,12 +128,15 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                     // [stage][hi|lo][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kABytes);
-  uint64_t* full = bars;                  // [kStages]  producers -> MMA
-  uint64_t* empty = bars + kStages;       // [kStages]  MMA -> producers
-  uint64_t* acc_full = bars + 2 * kStages;       // [2] MMA -> epilogue
-  uint64_t* acc_empty = bars + 2 * kStages + 2;  // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint8_t* sRaw = sA + kABytes;           // [raw stage][kRawRows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + kRawStages * kRawBytes);
+  uint64_t* full = bars;                  // [kStages]     compute -> MMA
+  uint64_t* empty = full + kStages;       // [kStages]     MMA -> compute
+  uint64_t* raw_full = empty + kStages;   // [kRawStages]  loaders (cp.async completion) -> compute
+  uint64_t* raw_empty = raw_full + kRawStages;   // [kRawStages]  compute -> loaders
+  uint64_t* acc_full = raw_empty + kRawStages;   // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;            // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // Tiles are dealt round-robin: at any time the 148 CTAs work on ~148 consecutive tiles of the SAME frame,
@@ -126,6 +148,10 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], kProdWarps);
       mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < kRawStages; ++s) {
+      mbar_init(&raw_full[s], kLoadWarps * 32);  // one cp.async.mbarrier.arrive.noinc per loader thread
+      mbar_init(&raw_empty[s], kProdWarps);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
@@ -160,109 +186,165 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
   __syncthreads();
   tc_fence_after();
 
-  if (warp > kMmaWarp) {
-    // ===== producers: gather -> split -> swizzled operand tile =============================================
-    const int pw = warp - (kMmaWarp + 1);
+  if (warp >= kProdWarp0) {
+    // ===== compute warps: gather from the raw stage -> split -> swizzled operand tile =======================
+    const int pw = warp - kProdWarp0;
     const int g = lane >> 3, j = lane & 7;
-    const uint32_t gmask = 0xFFu << (lane & 24);
+    constexpr int kIters = kRowsPerProd / 4;
+    const uint32_t sA_u = smem_u32(sA), sRaw_u = smem_u32(sRaw) + j * 16;
+    uint32_t soff[kIters];  // swizzled position of this lane's 16 bytes inside an operand tile
+#pragma unroll
+    for (int i = 0; i < kIters; ++i) soff[i] = sw128_off(pw * kRowsPerProd + i * 4 + g, j);
     uint32_t chunk = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      constexpr int kIters = kRowsPerProd / 4;
-      // Per tile: this lane's rows and (GATHER) their first 16 CSR entries, one entry per lane of the
-      // 8-lane group in two register sets -- the K chunks below then need a single round of feature loads.
-      int grow[kIters], beg[kIters], deg[kIters], ec[kIters][2];
-      float ewt[kIters][2];
+      // Per tile: this lane's two rows of the gather plan (all 8 lanes of a row group hold the same copy)
+      int ks = 0, nfar = 0, has_csr = 0;
+      uint2 slots[kIters];
+      float4 w0[kIters], w1[kIters];
       const float* fbase = p.X;
+      const PlanRow* prow = nullptr;
+      const int32_t* tnode = nullptr;
+      long long frow0 = 0;
+      if (GATHER) {
+        const long long b = tile / p.tiles_per_frame;
+        const int t = (int)(tile - b * p.tiles_per_frame);
+        const int4 hdr = __ldg(p.plan.hdr + t);
+        ks = hdr.y, nfar = hdr.z, has_csr = hdr.w;
+        frow0 = b * p.nodes_per_frame;
+        fbase = p.X + frow0 * 128;
+        prow = p.plan.rows + (size_t)t * 128 + pw * kRowsPerProd + g;
+        tnode = p.tile_nodes + t * 128 + pw * kRowsPerProd + g;
 #pragma unroll
-      for (int i = 0; i < kIters; ++i) {
-        const int r = pw * kRowsPerProd + i * 4 + g;
-        grow[i] = tile_row<GATHER>(p, tile, r);
-        beg[i] = deg[i] = 0;
-        ec[i][0] = ec[i][1] = 0;
-        ewt[i][0] = ewt[i][1] = 0.f;
-        if (GATHER && grow[i] >= 0) {
-          const int node = __ldg(p.tile_nodes + (int)(tile % p.tiles_per_frame) * 128 + r);
-          beg[i] = __ldg(p.rowptr + node);
-          deg[i] = __ldg(p.rowptr + node + 1) - beg[i];
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            if (8 * h + j < deg[i]) {
-              ec[i][h] = __ldg(p.col + beg[i] + 8 * h + j);
-              ewt[i][h] = __ldg(p.w + beg[i] + 8 * h + j);
-            }
-        }
-      }
-      if (GATHER) fbase = p.X + (tile / p.tiles_per_frame) * (long long)p.nodes_per_frame * 128;
-      {  // pull the rows of this CTA's NEXT tile into L2 (4 x 128 B lines per row, lanes j < 4 of each group)
-        const long long nt = tile + gridDim.x;
-        if (nt < p.num_tiles && j < 4) {
-#pragma unroll
-          for (int i = 0; i < kIters; ++i) {
-            const int nr = tile_row<GATHER>(p, nt, pw * kRowsPerProd + i * 4 + g);
-            if (nr >= 0) prefetch_l2(p.X + (long long)nr * 128 + j * 32);
-          }
+        for (int i = 0; i < kIters; ++i) {
+          const uint4* q = reinterpret_cast<const uint4*>(prow + i * 4);
+          const uint4 a = __ldg(q);
+          slots[i] = make_uint2(a.x, a.y);
+          w0[i] = __ldg(reinterpret_cast<const float4*>(q + 1));
+          w1[i] = __ldg(reinterpret_cast<const float4*>(q + 2));
         }
       }
       for (int kc = 0; kc < 4; ++kc, ++chunk) {
         const uint32_t stage = chunk % kStages, phase = (chunk / kStages) & 1u;
-        TC_TIMED_WAIT(0, &empty[stage], phase ^ 1u);
-        uint8_t* a_hi = sA + stage * 2 * kTileBytes;
-        uint8_t* a_lo = a_hi + kTileBytes;
+        const uint32_t rs = chunk % kRawStages, rphase = (chunk / kRawStages) & 1u;
         const int coff = kc * 32 + j * 4;
+        float4 fx[4];
+        if (GATHER && nfar) {  // far rows of the first row group: in flight across the barrier waits
+          const int4 fn = __ldg(reinterpret_cast<const int4*>(prow) + 3);
+          fx[0] = ldg4(fbase + (long long)fn.x * 128 + coff);
+          fx[1] = ldg4(fbase + (long long)fn.y * 128 + coff);
+          fx[2] = ldg4(fbase + (long long)fn.z * 128 + coff);
+          fx[3] = ldg4(fbase + (long long)fn.w * 128 + coff);
+        }
+        TC_TIMED_WAIT(1, &raw_full[rs], rphase);
+        TC_TIMED_WAIT(0, &empty[stage], phase ^ 1u);
+        const uint32_t a_hi = sA_u + stage * 2 * kTileBytes, a_lo = a_hi + kTileBytes;
+        const uint32_t raw = sRaw_u + rs * kRawBytes;
 #pragma unroll
         for (int i = 0; i < kIters; ++i) {
-          const int r = pw * kRowsPerProd + i * 4 + g;
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           if (GATHER) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (8 * h < deg[i]) {  // uniform inside the 8-lane group
-                const int n = deg[i] - 8 * h;
-                float4 x[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  const int c = __shfl_sync(gmask, ec[i][h], k, 8);
-                  x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (k < n) {
-                    const float* src = fbase + (long long)c * 128 + coff;
-                    x[k] = ldg4(src);
-                    if (j == 0 && kc < 3) prefetch_l1(src + 32);  // next K chunk of this neighbour row -> L1
-                  }
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  const float wk = __shfl_sync(gmask, ewt[i][h], k, 8);  // 0 for k >= n
-                  acc.x = fmaf(wk, x[k].x, acc.x);
-                  acc.y = fmaf(wk, x[k].y, acc.y);
-                  acc.z = fmaf(wk, x[k].z, acc.z);
-                  acc.w = fmaf(wk, x[k].w, acc.w);
-                }
+            uint32_t s_lo = slots[i].x, s_hi = slots[i].y;
+            asm volatile("" : "+r"(s_lo), "+r"(s_hi));  // keep the slot -> address arithmetic inside the chunk loop
+            // staged neighbours 0..3 and 4..6: loads first, then the sums in plan order (unused entries of a
+            // row point at slot 0 with weight 0); lattice tiles use 5 (grid) or 7 entries per row
+            float4 x0 = lds4(raw + ((s_lo & 0xffu) << 7));
+            float4 x1 = lds4(raw + ((s_lo >> 1) & 0x7f80u));
+            float4 x2 = lds4(raw + ((s_lo >> 9) & 0x7f80u));
+            float4 x3 = lds4(raw + ((s_lo >> 17) & 0x7f80u));
+            float4 x4 = lds4(raw + ((s_hi & 0xffu) << 7));
+            fma4(acc, w0[i].x, x0);
+            fma4(acc, w0[i].y, x1);
+            if (ks > 5) {
+              x0 = lds4(raw + ((s_hi >> 1) & 0x7f80u));
+              x1 = lds4(raw + ((s_hi >> 9) & 0x7f80u));
+            }
+            fma4(acc, w0[i].z, x2);
+            fma4(acc, w0[i].w, x3);
+            fma4(acc, w1[i].x, x4);
+            x2 = lds4(raw + ((s_hi >> 17) & 0x7f80u));  // the row itself
+            if (ks > 5) {
+              fma4(acc, w1[i].y, x0);
+              fma4(acc, w1[i].z, x1);
+            }
+            if (nfar) {
+              const float4 fw = __ldg(reinterpret_cast<const float4*>(prow + i * 4) + 4);
+              fma4(acc, fw.x, fx[0]);
+              fma4(acc, fw.y, fx[1]);
+              fma4(acc, fw.z, fx[2]);
+              fma4(acc, fw.w, fx[3]);
+              if (i + 1 < kIters) {
+                const int4 fn = __ldg(reinterpret_cast<const int4*>(prow + (i + 1) * 4) + 3);
+                fx[0] = ldg4(fbase + (long long)fn.x * 128 + coff);
+                fx[1] = ldg4(fbase + (long long)fn.y * 128 + coff);
+                fx[2] = ldg4(fbase + (long long)fn.z * 128 + coff);
+                fx[3] = ldg4(fbase + (long long)fn.w * 128 + coff);
               }
             }
-            for (int e = beg[i] + 16; e < beg[i] + deg[i]; ++e) {  // hub rows (connection nodes) only
-              const float wk = __ldg(p.w + e);
-              const float4 x = ldg4(fbase + (long long)__ldg(p.col + e) * 128 + coff);
-              acc.x = fmaf(wk, x.x, acc.x);
-              acc.y = fmaf(wk, x.y, acc.y);
-              acc.z = fmaf(wk, x.z, acc.z);
-              acc.w = fmaf(wk, x.w, acc.w);
+            fma4(acc, w1[i].w, x2);  // self loop last
+            if (has_csr) {  // hub rows etc.: summed from the device CSR (plan weights are zero)
+              const int cbeg = __ldg(&prow[i * 4].csr_beg), cdeg = __ldg(&prow[i * 4].csr_deg);
+              for (int e = cbeg; e < cbeg + cdeg; ++e)
+                fma4(acc, __ldg(p.w + e), ldg4(fbase + (long long)__ldg(p.col + e) * 128 + coff));
             }
-            if (p.AggOut && grow[i] >= 0) st4(p.AggOut + (long long)grow[i] * 128 + coff, acc);
-          } else if (grow[i] >= 0) {
-            acc = ldg4(p.X + (long long)grow[i] * 128 + coff);
+            if (p.AggOut) {
+              const int node = __ldg(tnode + i * 4);
+              if (node >= 0) st4(p.AggOut + (frow0 + node) * 128 + coff, acc);
+            }
+          } else {
+            // linear mode: raw slot r = tile row r (rows past the end were not copied: zero them)
+            const int r = pw * kRowsPerProd + i * 4 + g;
+            if (tile * 128 + r < p.rows) acc = lds4(raw + r * 128);
           }
           uint4 hi, lo;
           split_tf32(acc.x, hi.x, lo.x);
           split_tf32(acc.y, hi.y, lo.y);
           split_tf32(acc.z, hi.z, lo.z);
           split_tf32(acc.w, hi.w, lo.w);
-          const uint32_t off = sw128_off(r, j);
-          *reinterpret_cast<uint4*>(a_hi + off) = hi;
-          *reinterpret_cast<uint4*>(a_lo + off) = lo;
+          sts4(a_hi + soff[i], hi);
+          sts4(a_lo + soff[i], lo);
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full[stage]);
+        if (lane == 0) {
+          mbar_arrive(&full[stage]);
+          mbar_arrive(&raw_empty[rs]);
+        }
+      }
+    }
+  } else if (warp >= kLoadWarp0) {
+    // ===== loader warps: unique source rows of the tile, one K chunk per raw stage, cp.async ==================
+    constexpr int kPer = kRawRows / (kLoadWarps * 4);  // source rows per thread (8 lanes x 16 B per row)
+    const int q = (warp - kLoadWarp0) * 32 + lane;
+    const int sl = q >> 3, j = q & 7;
+    uint32_t chunk = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int srow[kPer];  // global row staged in slot sl + (kLoadWarps*4) * m, or -1
+      if (GATHER) {
+        const long long b = tile / p.tiles_per_frame;
+        const int t = (int)(tile - b * p.tiles_per_frame);
+        const int nsrc = __ldg(p.plan.hdr + t).x;
+#pragma unroll
+        for (int m = 0; m < kPer; ++m) {
+          const int s2 = sl + kLoadWarps * 4 * m;
+          srow[m] = s2 < nsrc ? (int)(b * p.nodes_per_frame + __ldg(p.plan.src + (size_t)t * kPlanSrc + s2)) : -1;
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < kPer; ++m) {
+          const int s2 = sl + kLoadWarps * 4 * m;
+          const long long row = tile * 128 + s2;
+          srow[m] = (s2 < 128 && row < p.rows) ? (int)row : -1;
+        }
+      }
+      for (int kc = 0; kc < 4; ++kc, ++chunk) {
+        const uint32_t rs = chunk % kRawStages, rphase = (chunk / kRawStages) & 1u;
+        TC_TIMED_WAIT(0, &raw_empty[rs], rphase ^ 1u);
+        const uint32_t dst = smem_u32(sRaw + rs * kRawBytes) + j * 16;
+        const float* srcb = p.X + kc * 32 + j * 4;
+#pragma unroll
+        for (int m = 0; m < kPer; ++m)
+          if (srow[m] >= 0) cp_async16(dst + (sl + kLoadWarps * 4 * m) * 128, srcb + (long long)srow[m] * 128);
+        cp_async_mbar_arrive(&raw_full[rs]);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -298,6 +380,8 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
     }
   } else {
     // ===== epilogue: thread <-> output feature; TMEM -> registers -> 128-byte row segments ===================
+    // A 16-column slab of the accumulator = one 16-row group of the tile = consecutive rows of Out
+    // (tile table contract), so a slab is addressed as one base pointer + immediate offsets.
     const int ew = warp;             // TMEM lanes [32 ew, 32 ew + 32)
     const int f = ew * 32 + lane;    // output feature owned by this thread
     const float bias = p.bias ? __ldg(p.bias + f) : 0.f;
@@ -305,39 +389,59 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, acc_phase = (it >> 1) & 1u;
-      int myrow[4];  // lane i holds the global row of tile rows i, 32 + i, 64 + i, 96 + i
-#pragma unroll
-      for (int sl = 0; sl < 4; ++sl) myrow[sl] = tile_row<GATHER>(p, tile, sl * 32 + lane);
+      // lane l < 8: first global row of group l (or -1); lane 8 + l: rows in group l
+      long long gbase = -1;
+      int gcnt = 0;
+      if (GATHER) {
+        const long long b = tile / p.tiles_per_frame;
+        const int t = (int)(tile - b * p.tiles_per_frame);
+        const int v = lane < 16 ? __ldg(p.tile_groups + t * 16 + lane) : 0;
+        gcnt = v;
+        gbase = (lane < 8 && v >= 0) ? b * p.nodes_per_frame + v : -1;
+      } else {
+        const long long r0 = tile * 128 + (lane & 7) * 16;
+        gbase = r0 < p.rows ? r0 : -1;
+        gcnt = (int)max(0LL, min(16LL, p.rows - r0));
+      }
       TC_TIMED_WAIT(0, &acc_full[buf], acc_phase);
       tc_fence_after();
-#pragma unroll
+#pragma unroll 1
       for (int sl = 0; sl < 8; ++sl) {  // 16 tile rows (accumulator columns) at a time
         uint32_t v[16];
-#ifdef EG_DBG_NOLDTM
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = sl + i;
-#else
         tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + kTmemAcc + buf * 128 + sl * 16, v);
-#endif
-        int row[16];
+        const long long base = __shfl_sync(0xffffffffu, gbase, sl);
+        const int cnt = __shfl_sync(0xffffffffu, gcnt, GATHER ? 8 + sl : sl);
+        float* out = p.Out + max(base, 0LL) * 128 + f;
         float ad[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {  // all residual loads in flight before the accumulator is consumed
-          row[i] = __shfl_sync(0xffffffffu, myrow[sl >> 1], (sl & 1) * 16 + i);
-          ad[i] = 0.f;
-          if (p.addend) ad[i] = __ldg(p.addend + (long long)max(row[i], 0) * 128 + f);
+        for (int i = 0; i < 16; ++i) ad[i] = 0.f;
+        if (p.addend) {  // all residual loads in flight before the accumulator is consumed
+          const float* adp = p.addend + max(base, 0LL) * 128 + f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < cnt) ad[i] = __ldg(adp + i * 128);
         }
         tmem_ld_wait();
         float s = 0.f, q = 0.f;
+        if (cnt == 16) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float o = __uint_as_float(v[i]) + bias + ad[i];
-          if (row[i] >= 0) {  // warp-uniform
+          for (int i = 0; i < 16; ++i) {
+            const float o = __uint_as_float(v[i]) + bias + ad[i];
 #ifndef EG_DBG_NOSTORE
-            p.Out[(long long)row[i] * 128 + f] = o;
+            out[i * 128] = o;
 #endif
             s += o;
             q = fmaf(o, o, q);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float o = __uint_as_float(v[i]) + bias + ad[i];
+            if (i < cnt) {  // warp-uniform
+              out[i * 128] = o;
+              s += o;
+              q = fmaf(o, o, q);
+            }
           }
         }
         s_sum += (double)s;
@@ -356,7 +460,8 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
 #ifdef EG_TC_TIMING
   if (lane == 0) {
     long long* d = g_tc_dbg[blockIdx.x];
-    if (warp == kMmaWarp + 1) d[0] = dbg_acc[0];                    // producer warp 0: wait for a free stage
+    if (warp == kProdWarp0) { d[0] = dbg_acc[0]; d[5] = dbg_acc[1]; } // compute warp 0: wait operand stage, wait raw
+    if (warp == kLoadWarp0) d[6] = dbg_acc[0];                       // loader: wait for a free raw stage
     if (warp == kMmaWarp) { d[1] = dbg_acc[0]; d[2] = dbg_acc[1]; } // MMA: wait acc_empty, wait full
     if (warp == 0) { d[3] = dbg_acc[0]; d[4] = clock64() - dbg_t0; } // epilogue: wait acc_full; total cycles
   }
@@ -410,6 +515,8 @@ int launch_gcn_tc(const eg_graph* g, int batch, const float* X, const float* W, 
   const eg_graph_info& info = graph_info(g);
   TcParams p{};
   p.tile_nodes = graph_tile_nodes(g);
+  p.tile_groups = graph_tile_groups(g);
+  p.plan = graph_plan(g);
   p.tiles_per_frame = graph_tiles_per_frame(g);
   p.nodes_per_frame = info.num_nodes;
   p.num_tiles = (long long)batch * p.tiles_per_frame;

@@ -5,6 +5,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
+#include <cmath>
+#include <utility>
 #include <vector>
 
 #include "topology.cuh"
@@ -35,6 +38,11 @@ struct eg_graph {
   // other nodes are packed in index order.  Every node of the frame appears exactly once.
   int32_t* tile_nodes;  // [tiles_per_frame][128]
   int tiles_per_frame;
+  int32_t* tile_groups;  // [tiles_per_frame][16]: first node / row count of each 16-row group (build_groups)
+  // Gather plan of the fused kernel, per tile (see TilePlan in common.cuh): the unique source rows a tile
+  // reads most (its own rows, the lattice halo, the parents) are staged in shared memory; every edge of a
+  // tile row is either a slot of that stage or a direct global read (e.g. the 4 children of an aux node).
+  eg::TilePlan plan;
 };
 
 using namespace eg;
@@ -114,34 +122,156 @@ void fill_info(const Topo& t, eg_graph_info* info, int num_edges, int max_degree
   info->crop_offset = t.crop;
 }
 
+// Tile table contract: every aligned group of 16 tile rows is a run of CONSECUTIVE node ids, possibly
+// shorter than 16 (then padded with -1 at its end); the epilogue of the tensor-core kernels addresses a
+// group as base row + immediate offsets.
 std::vector<int32_t> build_tiles(const Topo& t) {
-  std::vector<int32_t> tiles, run;
-  auto flush_run = [&](bool final_flush) {
-    size_t full = run.size() / 128 * 128;
-    tiles.insert(tiles.end(), run.begin(), run.begin() + full);
-    run.erase(run.begin(), run.begin() + full);
-    if (final_flush && !run.empty()) {
-      run.resize(128, -1);
-      tiles.insert(tiles.end(), run.begin(), run.end());
-      run.clear();
+  std::vector<int32_t> tiles;
+  int in_group = 0, last = -2;
+  auto close_group = [&]() {
+    while (in_group % 16) {
+      tiles.push_back(-1);
+      ++in_group;
     }
+    in_group = 0;
   };
-  for (int v = 0; v < t.nconn; ++v) run.push_back(v);
+  auto push_misc = [&](int v) {
+    if (in_group == 16 || (in_group && v != last + 1)) close_group();
+    tiles.push_back(v);
+    ++in_group;
+    last = v;
+  };
+  // nodes outside the 8 x 16 patches first: connection hubs, lattices whose side is not a multiple of 16
+  // (in index order), coordinate nodes
+  for (int v = 0; v < t.nconn; ++v) push_misc(v);
   for (int l = 0; l < t.nlev; ++l) {
     const int p = t.lsize[l], off = t.loff[l];
-    if (p % 16 == 0) {
-      for (int a0 = 0; a0 < p; a0 += 8)
-        for (int b0 = 0; b0 < p; b0 += 16)
-          for (int a = a0; a < a0 + 8; ++a)
-            for (int b = b0; b < b0 + 16; ++b) tiles.push_back(off + a * p + b);
-    } else {
-      for (int v = 0; v < p * p; ++v) run.push_back(off + v);
-    }
+    if (p % 16 != 0)
+      for (int v = 0; v < p * p; ++v) push_misc(off + v);
   }
-  for (int v = t.N - t.ncoord; v < t.N; ++v) run.push_back(v);
-  flush_run(false);
-  flush_run(true);
+  for (int v = t.N - t.ncoord; v < t.N; ++v) push_misc(v);
+  close_group();
+  while (tiles.size() % 128) tiles.push_back(-1);
+  for (int l = 0; l < t.nlev; ++l) {
+    const int p = t.lsize[l], off = t.loff[l];
+    if (p % 16 != 0) continue;
+    for (int a0 = 0; a0 < p; a0 += 8)
+      for (int b0 = 0; b0 < p; b0 += 16)
+        for (int a = a0; a < a0 + 8; ++a)
+          for (int b = b0; b < b0 + 16; ++b) tiles.push_back(off + a * p + b);
+  }
   return tiles;
+}
+
+// per tile: [0..7] first node of each 16-row group (-1 = empty), [8..15] rows in the group
+std::vector<int32_t> build_groups(const std::vector<int32_t>& tiles) {
+  const size_t T = tiles.size() / 128;
+  std::vector<int32_t> grp(T * 16, 0);
+  for (size_t ti = 0; ti < T; ++ti)
+    for (int gi = 0; gi < 8; ++gi) {
+      const int32_t* q = &tiles[ti * 128 + gi * 16];
+      int cnt = 0;
+      while (cnt < 16 && q[cnt] >= 0) ++cnt;
+      grp[ti * 16 + gi] = cnt ? q[0] : -1;
+      grp[ti * 16 + 8 + gi] = cnt;
+    }
+  return grp;
+}
+
+struct HostPlan {
+  std::vector<int4> hdr;
+  std::vector<int32_t> src;
+  std::vector<PlanRow> rows;
+};
+
+// dis / weights exactly as degree_kernel / fill_kernel compute them on the device
+HostPlan build_plan(const Topo& t, const std::vector<int32_t>& tiles) {
+  const int T = (int)(tiles.size() / 128);
+  std::vector<float> dis(t.N);
+  std::vector<int32_t> rowbeg(t.N + 1, 0);
+  for (int u = 0; u < t.N; ++u) {
+    const int d = degree_of(t, u) + 1;
+    dis[u] = (float)(1.0 / sqrt((double)d));
+    rowbeg[u + 1] = rowbeg[u] + d;
+  }
+  HostPlan hp;
+  hp.hdr.assign(T, make_int4(0, 0, 0, 0));
+  hp.src.assign((size_t)T * kPlanSrc, -1);
+  PlanRow zero;
+  memset(&zero, 0, sizeof(zero));
+  hp.rows.assign((size_t)T * 128, zero);
+  std::vector<std::pair<int, int>> uses;  // (source, count)
+  std::vector<int> nb, st, far;
+  for (int ti = 0; ti < T; ++ti) {
+    uses.clear();
+    // hub rows have thousands of neighbours: they are CSR rows and do not vote for staged sources
+    constexpr int kVoteDegree = kPlanStaged + kPlanFar;
+    for (int r = 0; r < 128; ++r) {
+      const int v = tiles[(size_t)ti * 128 + r];
+      if (v < 0) continue;
+      uses.emplace_back(v, 1 << 20);  // own rows always staged (the self loop is read from the stage)
+      if (degree_of(t, v) > kVoteDegree) continue;
+      for_each_neighbor(t, v, true, [&](int u) { uses.emplace_back(u, 1); });
+    }
+    std::sort(uses.begin(), uses.end());
+    {  // merge duplicates
+      size_t o = 0;
+      for (size_t i = 0; i < uses.size(); ++i) {
+        if (o && uses[o - 1].first == uses[i].first) uses[o - 1].second += uses[i].second;
+        else uses[o++] = uses[i];
+      }
+      uses.resize(o);
+    }
+    // keep the most used sources (ties: lower index), then number the slots in ascending source order
+    std::stable_sort(uses.begin(), uses.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+      return a.second != b.second ? a.second > b.second : a.first < b.first;
+    });
+    if ((int)uses.size() > kPlanSrc) uses.resize(kPlanSrc);
+    std::sort(uses.begin(), uses.end());
+    for (int s2 = 0; s2 < (int)uses.size(); ++s2) hp.src[(size_t)ti * kPlanSrc + s2] = uses[s2].first;
+    auto slot_of = [&](int u) {
+      auto it = std::lower_bound(uses.begin(), uses.end(), std::make_pair(u, 0),
+                                 [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+      return (it != uses.end() && it->first == u) ? (int)(it - uses.begin()) : -1;
+    };
+    int ks = 0, nfar = 0, has_csr = 0;
+    for (int r = 0; r < 128; ++r) {
+      const int v = tiles[(size_t)ti * 128 + r];
+      if (v < 0) continue;
+      PlanRow& pr = hp.rows[(size_t)ti * 128 + r];
+      nb.clear();
+      st.clear();
+      far.clear();
+      bool fits = degree_of(t, v) <= 4096;
+      if (fits) for_each_neighbor(t, v, true, [&](int u) { nb.push_back(u); });
+      for (int u : nb) {
+        if (slot_of(u) >= 0 && (int)st.size() < kPlanStaged) st.push_back(u);
+        else far.push_back(u);
+      }
+      const int self_slot = slot_of(v);
+      fits = fits && (int)far.size() <= kPlanFar && self_slot >= 0;
+      if (!fits) {
+        pr.csr_beg = rowbeg[v];
+        pr.csr_deg = rowbeg[v + 1] - rowbeg[v];
+        has_csr = 1;
+        continue;
+      }
+      for (int k = 0; k < (int)st.size(); ++k) {
+        pr.slot[k] = (uint8_t)slot_of(st[k]);
+        pr.w[k] = dis[st[k]] * dis[v];
+      }
+      pr.slot[7] = (uint8_t)self_slot;
+      pr.w[7] = dis[v] * dis[v];
+      for (int k = 0; k < (int)far.size(); ++k) {
+        pr.far_node[k] = far[k];
+        pr.far_w[k] = dis[far[k]] * dis[v];
+      }
+      ks = std::max(ks, (int)st.size());
+      if (!far.empty()) nfar = kPlanFar;
+    }
+    hp.hdr[ti] = make_int4((int)uses.size(), ks, nfar, has_csr);
+  }
+  return hp;
 }
 
 int init_topo(const eg_graph_spec* spec, Topo& t) {
@@ -270,6 +400,16 @@ int eg_graph_create(const eg_graph_spec* spec, int device, eg_graph** out) {
     g->tiles_per_frame = (int)(tiles.size() / 128);
     EG_TRY(cudaMalloc(&g->tile_nodes, sizeof(int32_t) * tiles.size()));
     EG_TRY(cudaMemcpy(g->tile_nodes, tiles.data(), sizeof(int32_t) * tiles.size(), cudaMemcpyHostToDevice));
+    std::vector<int32_t> grp = build_groups(tiles);
+    HostPlan hp = build_plan(t, tiles);
+    auto up = [&](const void* h, size_t bytes, void** d) {
+      cudaError_t e = cudaMalloc(d, bytes);
+      return e != cudaSuccess ? e : cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+    };
+    EG_TRY(up(grp.data(), grp.size() * sizeof(int32_t), (void**)&g->tile_groups));
+    EG_TRY(up(hp.hdr.data(), hp.hdr.size() * sizeof(int4), (void**)&g->plan.hdr));
+    EG_TRY(up(hp.src.data(), hp.src.size() * sizeof(int32_t), (void**)&g->plan.src));
+    EG_TRY(up(hp.rows.data(), hp.rows.size() * sizeof(PlanRow), (void**)&g->plan.rows));
   }
   std::vector<int32_t> hdeg(t.N);
   EG_TRY(cudaMemcpy(hdeg.data(), deg, sizeof(int32_t) * t.N, cudaMemcpyDeviceToHost));
@@ -292,6 +432,10 @@ void eg_graph_destroy(eg_graph* g) {
   cudaFree(g->w);
   cudaFree(g->dis);
   cudaFree(g->tile_nodes);
+  cudaFree(g->tile_groups);
+  cudaFree((void*)g->plan.hdr);
+  cudaFree((void*)g->plan.src);
+  cudaFree((void*)g->plan.rows);
   delete g;
 }
 
@@ -359,4 +503,6 @@ const float* graph_dis(const eg_graph* g) { return g->dis; }
 int graph_nnz(const eg_graph* g) { return g->nnz; }
 const int32_t* graph_tile_nodes(const eg_graph* g) { return g->tile_nodes; }
 int graph_tiles_per_frame(const eg_graph* g) { return g->tiles_per_frame; }
+const int32_t* graph_tile_groups(const eg_graph* g) { return g->tile_groups; }
+const TilePlan& graph_plan(const eg_graph* g) { return g->plan; }
 }  // namespace eg
