@@ -549,7 +549,10 @@ def _hot_path_vs_oracle(cfg, variant, batch, frames_or_x, y, valid, sd, embed_sd
         bound = 1e-3 * gb.abs() + 1e-4 * gb.abs().max()
         viol = int(((ga - gb).abs() > bound).sum())
         rms = float((ga - gb).pow(2).mean().sqrt() / gb.pow(2).mean().sqrt())
-        limit = int(1e-3 * ga.numel()) if strict_full is False else 0
+        # tools/fp64_noise.py: the fp32 ORACLE itself differs from its own fp64 run by 82 / 659 / 1406 / 3657
+        # such entries on levels 4-7 of this case (rms 6e-5 .. 7e-4); one flipped (node, feature) moves
+        # ~100-1000 gradient entries of its 2-hop neighbourhood, hence the floor of 256 on small levels.
+        limit = max(int(1e-3 * ga.numel()), 256) if strict_full is False else 0
         assert viol <= limit and rms <= 2e-3, \
             f"d(map) level {lvl}: {viol} of {ga.numel()} outside tolerance, rms rel {rms:.2e}"
 
