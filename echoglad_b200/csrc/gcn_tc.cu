@@ -66,7 +66,9 @@ constexpr int kTileBytes = 128 * 128;      // one [128 rows x 32 tf32] operand t
 constexpr uint32_t kABytes = kStages * 2 * kTileBytes;
 constexpr int kRawRows = kPlanSrc;         // 224 >= 128 (linear mode stages the tile's own rows)
 constexpr uint32_t kRawBytes = kRawRows * 128;
-constexpr uint32_t kSmemBytes = kABytes + kRawStages * kRawBytes + 256 /*barriers*/ + 1024 /*align*/;
+constexpr uint32_t kPlanWarpBytes = kRowsPerProd * sizeof(PlanRow) + 16;  // a compute warp's 8 plan rows + tile header
+constexpr uint32_t kPlanBytes = kProdWarps * 2 * kPlanWarpBytes;           // double-buffered per warp
+constexpr uint32_t kSmemBytes = kABytes + kRawStages * kRawBytes + kPlanBytes + 256 /*barriers*/ + 1024 /*align*/;
 constexpr int kTmemCols = 512;             // [0,128) W hi, [128,256) W lo, [256,384) / [384,512) accumulators
 constexpr uint32_t kTmemAcc = 256;
 static_assert(kPlanSrc % (kLoadWarps * 4) == 0 && kPlanSrc >= 128, "loader mapping");
@@ -129,7 +131,8 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                     // [stage][hi|lo][16 KB]
   uint8_t* sRaw = sA + kABytes;           // [raw stage][kRawRows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + kRawStages * kRawBytes);
+  uint8_t* sPlan = sRaw + kRawStages * kRawBytes;  // [compute warp][2][kPlanWarpBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPlan + kPlanBytes);
   uint64_t* full = bars;                  // [kStages]     compute -> MMA
   uint64_t* empty = full + kStages;       // [kStages]     MMA -> compute
   uint64_t* raw_full = empty + kStages;   // [kRawStages]  loaders (cp.async completion) -> compute
@@ -192,36 +195,54 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
     const int g = lane >> 3, j = lane & 7;
     constexpr int kIters = kRowsPerProd / 4;
     const uint32_t sA_u = smem_u32(sA), sRaw_u = smem_u32(sRaw) + j * 16;
+    const uint32_t bar_full = smem_u32(full), bar_empty = smem_u32(empty);
+    const uint32_t bar_raw_full = smem_u32(raw_full), bar_raw_empty = smem_u32(raw_empty);
+    const uint32_t plan_u = smem_u32(sPlan) + pw * 2 * kPlanWarpBytes;  // this warp's two plan buffers
+    const bool agg_out = p.AggOut != nullptr;
     uint32_t soff[kIters];  // swizzled position of this lane's 16 bytes inside an operand tile
 #pragma unroll
     for (int i = 0; i < kIters; ++i) soff[i] = sw128_off(pw * kRowsPerProd + i * 4 + g, j);
-    uint32_t chunk = 0;
-    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    // The warp's plan rows (8 x 80 B, contiguous) + the tile header travel global -> shared with cp.async one
+    // tile ahead, so a tile starts with LDS instead of an exposed L2 round trip.
+    auto prefetch_plan = [&](long long tile, uint32_t buf) {
+      if (tile >= p.num_tiles) return;
+      const int t = (int)(tile % p.tiles_per_frame);
+      const uint32_t dst = plan_u + buf * kPlanWarpBytes;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.plan.rows + (size_t)t * 128 + pw * kRowsPerProd);
+      cp_async16(dst + lane * 16, src + lane * 16);
+      if (lane < 8) cp_async16(dst + (32 + lane) * 16, src + (32 + lane) * 16);
+      if (lane == 8) cp_async16(dst + kRowsPerProd * sizeof(PlanRow), p.plan.hdr + t);
+    };
+    uint32_t chunk = 0, pbuf = 0;
+    if (GATHER) prefetch_plan(blockIdx.x, 0);
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, pbuf ^= 1u) {
       // Per tile: this lane's two rows of the gather plan (all 8 lanes of a row group hold the same copy)
       int ks = 0, nfar = 0, has_csr = 0;
       uint2 slots[kIters];
       float4 w0[kIters], w1[kIters];
       const float* fbase = p.X;
-      const PlanRow* prow = nullptr;
       const int32_t* tnode = nullptr;
       long long frow0 = 0;
+      const uint32_t prow = plan_u + pbuf * kPlanWarpBytes + g * sizeof(PlanRow);  // + i * 4 rows
       if (GATHER) {
         const long long b = tile / p.tiles_per_frame;
         const int t = (int)(tile - b * p.tiles_per_frame);
-        const int4 hdr = __ldg(p.plan.hdr + t);
-        ks = hdr.y, nfar = hdr.z, has_csr = hdr.w;
+        cp_async_wait_all();
+        __syncwarp();
+        const float4 hdr = lds4(plan_u + pbuf * kPlanWarpBytes + kRowsPerProd * sizeof(PlanRow));
+        ks = __float_as_int(hdr.y), nfar = __float_as_int(hdr.z), has_csr = __float_as_int(hdr.w);
         frow0 = b * p.nodes_per_frame;
         fbase = p.X + frow0 * 128;
-        prow = p.plan.rows + (size_t)t * 128 + pw * kRowsPerProd + g;
         tnode = p.tile_nodes + t * 128 + pw * kRowsPerProd + g;
 #pragma unroll
         for (int i = 0; i < kIters; ++i) {
-          const uint4* q = reinterpret_cast<const uint4*>(prow + i * 4);
-          const uint4 a = __ldg(q);
-          slots[i] = make_uint2(a.x, a.y);
-          w0[i] = __ldg(reinterpret_cast<const float4*>(q + 1));
-          w1[i] = __ldg(reinterpret_cast<const float4*>(q + 2));
+          const float4 a = lds4(prow + i * 4 * sizeof(PlanRow));
+          slots[i] = make_uint2(__float_as_uint(a.x), __float_as_uint(a.y));
+          w0[i] = lds4(prow + i * 4 * sizeof(PlanRow) + 16);
+          w1[i] = lds4(prow + i * 4 * sizeof(PlanRow) + 32);
         }
+        prefetch_plan(tile + gridDim.x, pbuf ^ 1u);
+        cp_async_commit();
       }
       for (int kc = 0; kc < 4; ++kc, ++chunk) {
         const uint32_t stage = chunk % kStages, phase = (chunk / kStages) & 1u;
@@ -229,14 +250,25 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
         const int coff = kc * 32 + j * 4;
         float4 fx[4];
         if (GATHER && nfar) {  // far rows of the first row group: in flight across the barrier waits
-          const int4 fn = __ldg(reinterpret_cast<const int4*>(prow) + 3);
-          fx[0] = ldg4(fbase + (long long)fn.x * 128 + coff);
-          fx[1] = ldg4(fbase + (long long)fn.y * 128 + coff);
-          fx[2] = ldg4(fbase + (long long)fn.z * 128 + coff);
-          fx[3] = ldg4(fbase + (long long)fn.w * 128 + coff);
+          const float4 fn = lds4(prow + 48);
+          fx[0] = ldg4(fbase + (long long)__float_as_int(fn.x) * 128 + coff);
+          fx[1] = ldg4(fbase + (long long)__float_as_int(fn.y) * 128 + coff);
+          fx[2] = ldg4(fbase + (long long)__float_as_int(fn.z) * 128 + coff);
+          fx[3] = ldg4(fbase + (long long)__float_as_int(fn.w) * 128 + coff);
         }
-        TC_TIMED_WAIT(1, &raw_full[rs], rphase);
-        TC_TIMED_WAIT(0, &empty[stage], phase ^ 1u);
+#ifdef EG_TC_TIMING
+        {
+          const long long _t = clock64();
+          mbar_wait_a(bar_raw_full + rs * 8, rphase);
+          dbg_acc[1] += clock64() - _t;
+          const long long _t2 = clock64();
+          mbar_wait_a(bar_empty + stage * 8, phase ^ 1u);
+          dbg_acc[0] += clock64() - _t2;
+        }
+#else
+        mbar_wait_a(bar_raw_full + rs * 8, rphase);
+        mbar_wait_a(bar_empty + stage * 8, phase ^ 1u);
+#endif
         const uint32_t a_hi = sA_u + stage * 2 * kTileBytes, a_lo = a_hi + kTileBytes;
         const uint32_t raw = sRaw_u + rs * kRawBytes;
 #pragma unroll
@@ -245,48 +277,49 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
           if (GATHER) {
             uint32_t s_lo = slots[i].x, s_hi = slots[i].y;
             asm volatile("" : "+r"(s_lo), "+r"(s_hi));  // keep the slot -> address arithmetic inside the chunk loop
-            // staged neighbours 0..3 and 4..6: loads first, then the sums in plan order (unused entries of a
-            // row point at slot 0 with weight 0); lattice tiles use 5 (grid) or 7 entries per row
-            float4 x0 = lds4(raw + ((s_lo & 0xffu) << 7));
-            float4 x1 = lds4(raw + ((s_lo >> 1) & 0x7f80u));
-            float4 x2 = lds4(raw + ((s_lo >> 9) & 0x7f80u));
-            float4 x3 = lds4(raw + ((s_lo >> 17) & 0x7f80u));
-            float4 x4 = lds4(raw + ((s_hi & 0xffu) << 7));
+            // staged neighbours 0..4 (+ 5, 6 on tiles that have them): loads first, then the sums in plan
+            // order (unused entries of a row point at slot 0 with weight 0)
+            float4 x0 = lds4(raw + (__byte_perm(s_lo, 0, 0x4440) << 7));
+            float4 x1 = lds4(raw + (__byte_perm(s_lo, 0, 0x4441) << 7));
+            float4 x2 = lds4(raw + (__byte_perm(s_lo, 0, 0x4442) << 7));
+            float4 x3 = lds4(raw + (__byte_perm(s_lo, 0, 0x4443) << 7));
+            float4 x4 = lds4(raw + (__byte_perm(s_hi, 0, 0x4440) << 7));
             fma4(acc, w0[i].x, x0);
             fma4(acc, w0[i].y, x1);
             if (ks > 5) {
-              x0 = lds4(raw + ((s_hi >> 1) & 0x7f80u));
-              x1 = lds4(raw + ((s_hi >> 9) & 0x7f80u));
+              x0 = lds4(raw + (__byte_perm(s_hi, 0, 0x4441) << 7));
+              x1 = lds4(raw + (__byte_perm(s_hi, 0, 0x4442) << 7));
             }
             fma4(acc, w0[i].z, x2);
             fma4(acc, w0[i].w, x3);
             fma4(acc, w1[i].x, x4);
-            x2 = lds4(raw + ((s_hi >> 17) & 0x7f80u));  // the row itself
+            x2 = lds4(raw + (__byte_perm(s_hi, 0, 0x4443) << 7));  // the row itself
             if (ks > 5) {
               fma4(acc, w1[i].y, x0);
               fma4(acc, w1[i].z, x1);
             }
             if (nfar) {
-              const float4 fw = __ldg(reinterpret_cast<const float4*>(prow + i * 4) + 4);
+              const float4 fw = lds4(prow + i * 4 * sizeof(PlanRow) + 64);
               fma4(acc, fw.x, fx[0]);
               fma4(acc, fw.y, fx[1]);
               fma4(acc, fw.z, fx[2]);
               fma4(acc, fw.w, fx[3]);
               if (i + 1 < kIters) {
-                const int4 fn = __ldg(reinterpret_cast<const int4*>(prow + (i + 1) * 4) + 3);
-                fx[0] = ldg4(fbase + (long long)fn.x * 128 + coff);
-                fx[1] = ldg4(fbase + (long long)fn.y * 128 + coff);
-                fx[2] = ldg4(fbase + (long long)fn.z * 128 + coff);
-                fx[3] = ldg4(fbase + (long long)fn.w * 128 + coff);
+                const float4 fn = lds4(prow + (i + 1) * 4 * sizeof(PlanRow) + 48);
+                fx[0] = ldg4(fbase + (long long)__float_as_int(fn.x) * 128 + coff);
+                fx[1] = ldg4(fbase + (long long)__float_as_int(fn.y) * 128 + coff);
+                fx[2] = ldg4(fbase + (long long)__float_as_int(fn.z) * 128 + coff);
+                fx[3] = ldg4(fbase + (long long)__float_as_int(fn.w) * 128 + coff);
               }
             }
             fma4(acc, w1[i].w, x2);  // self loop last
             if (has_csr) {  // hub rows etc.: summed from the device CSR (plan weights are zero)
-              const int cbeg = __ldg(&prow[i * 4].csr_beg), cdeg = __ldg(&prow[i * 4].csr_deg);
+              const float4 a = lds4(prow + i * 4 * sizeof(PlanRow));
+              const int cbeg = __float_as_int(a.z), cdeg = __float_as_int(a.w);
               for (int e = cbeg; e < cbeg + cdeg; ++e)
                 fma4(acc, __ldg(p.w + e), ldg4(fbase + (long long)__ldg(p.col + e) * 128 + coff));
             }
-            if (p.AggOut) {
+            if (agg_out) {
               const int node = __ldg(tnode + i * 4);
               if (node >= 0) st4(p.AggOut + (frow0 + node) * 128 + coff, acc);
             }
@@ -296,18 +329,18 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
             if (tile * 128 + r < p.rows) acc = lds4(raw + r * 128);
           }
           uint4 hi, lo;
-          split_tf32(acc.x, hi.x, lo.x);
-          split_tf32(acc.y, hi.y, lo.y);
-          split_tf32(acc.z, hi.z, lo.z);
-          split_tf32(acc.w, hi.w, lo.w);
+          split_tf32_fast(acc.x, hi.x, lo.x);
+          split_tf32_fast(acc.y, hi.y, lo.y);
+          split_tf32_fast(acc.z, hi.z, lo.z);
+          split_tf32_fast(acc.w, hi.w, lo.w);
           sts4(a_hi + soff[i], hi);
           sts4(a_lo + soff[i], lo);
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&full[stage]);
-          mbar_arrive(&raw_empty[rs]);
+          mbar_arrive_a(bar_full + stage * 8);
+          mbar_arrive_a(bar_raw_empty + rs * 8);
         }
       }
     }
@@ -316,18 +349,26 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
     constexpr int kPer = kRawRows / (kLoadWarps * 4);  // source rows per thread (8 lanes x 16 B per row)
     const int q = (warp - kLoadWarp0) * 32 + lane;
     const int sl = q >> 3, j = q & 7;
+    const uint32_t bar_raw_full = smem_u32(raw_full), bar_raw_empty = smem_u32(raw_empty);
+    const uint32_t dst0 = smem_u32(sRaw) + sl * 128 + j * 16;
+    // frame-local node staged in slot sl + (kLoadWarps*4) * m (-1 = none), fetched one tile ahead
+    auto load_src = [&](long long tile, int (&node)[kPer]) {
+      if (GATHER && tile < p.num_tiles) {
+        const int t = (int)(tile % p.tiles_per_frame);
+#pragma unroll
+        for (int m = 0; m < kPer; ++m) node[m] = __ldg(p.plan.src + (size_t)t * kPlanSrc + sl + kLoadWarps * 4 * m);
+      }
+    };
+    int nxt[kPer];
+    load_src(blockIdx.x, nxt);
     uint32_t chunk = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int srow[kPer];  // global row staged in slot sl + (kLoadWarps*4) * m, or -1
+      int srow[kPer];  // global row (< 2^31, checked by the launcher), or -1
       if (GATHER) {
-        const long long b = tile / p.tiles_per_frame;
-        const int t = (int)(tile - b * p.tiles_per_frame);
-        const int nsrc = __ldg(p.plan.hdr + t).x;
+        const int base = (int)(tile / p.tiles_per_frame) * p.nodes_per_frame;
 #pragma unroll
-        for (int m = 0; m < kPer; ++m) {
-          const int s2 = sl + kLoadWarps * 4 * m;
-          srow[m] = s2 < nsrc ? (int)(b * p.nodes_per_frame + __ldg(p.plan.src + (size_t)t * kPlanSrc + s2)) : -1;
-        }
+        for (int m = 0; m < kPer; ++m) srow[m] = nxt[m] >= 0 ? base + nxt[m] : -1;
+        load_src(tile + gridDim.x, nxt);
       } else {
 #pragma unroll
         for (int m = 0; m < kPer; ++m) {
@@ -338,13 +379,19 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
       }
       for (int kc = 0; kc < 4; ++kc, ++chunk) {
         const uint32_t rs = chunk % kRawStages, rphase = (chunk / kRawStages) & 1u;
-        TC_TIMED_WAIT(0, &raw_empty[rs], rphase ^ 1u);
-        const uint32_t dst = smem_u32(sRaw + rs * kRawBytes) + j * 16;
+#ifdef EG_TC_TIMING
+        const long long _t = clock64();
+        mbar_wait_a(bar_raw_empty + rs * 8, rphase ^ 1u);
+        dbg_acc[0] += clock64() - _t;
+#else
+        mbar_wait_a(bar_raw_empty + rs * 8, rphase ^ 1u);
+#endif
+        const uint32_t dst = dst0 + rs * kRawBytes;
         const float* srcb = p.X + kc * 32 + j * 4;
 #pragma unroll
         for (int m = 0; m < kPer; ++m)
-          if (srow[m] >= 0) cp_async16(dst + (sl + kLoadWarps * 4 * m) * 128, srcb + (long long)srow[m] * 128);
-        cp_async_mbar_arrive(&raw_full[rs]);
+          if (srow[m] >= 0) cp_async16(dst + kLoadWarps * 4 * m * 128, srcb + (long long)srow[m] * 128);
+        cp_async_mbar_arrive_a(bar_raw_full + rs * 8);
       }
     }
   } else if (warp == kMmaWarp) {

@@ -181,6 +181,12 @@ class Aggregate(torch.autograd.Function):
         return None, None, gcn_aggregate(ctx.graph, ctx.batch, dy.contiguous())
 
 
+# Test hook: when set to a list, every layer appends the sign pattern (bool tensor) of its ReLU input so a
+# parity test can impose the same pattern on the CPU oracle (see oracle/restated.py:_relu).  Never set in
+# production; costs one extra bn_act_fwd per GCN layer while active.
+CAPTURE_RELU = None
+
+
 class GCNLayer(torch.autograd.Function):
     """One reference GNN layer: GCNConv -> BatchNorm1d -> Dropout -> ReLU|Identity (+ residual)
     (reference src/core/models.py:329-335,431-435).  Returns (Y, batch_mean, batch_var)."""
@@ -204,6 +210,9 @@ class GCNLayer(torch.autograd.Function):
                                   ws.data_ptr(), WORKSPACE_BYTES, _stream(x)), "eg_gcn_conv_fwd")
         p = float(drop_p) if training else 0.0
         y = bn_act_fwd(h, mean, var, gamma, beta, eps, p, seed, relu, x if residual else None)
+        if CAPTURE_RELU is not None and relu:
+            CAPTURE_RELU.append(("gnn", (y if not residual else
+                                         bn_act_fwd(h, mean, var, gamma, beta, eps, 0.0, seed, relu, None)) > 0))
         ctx.save_for_backward(x, h, w, gamma, beta, mean, var)
         ctx.cfg = (graph, batch, training, eps, p, seed, relu, residual)
         ctx.mark_non_differentiable(mean, var)
@@ -263,6 +272,9 @@ class ClassifierHeads(torch.autograd.Function):
                                  m2.data_ptr() if training else None, v2.data_ptr() if training else None,
                                  ws.data_ptr(), WORKSPACE_BYTES, st), "eg_clf_mid_fwd")
         a2 = bn_act_fwd(z2, m2, v2, g2, be2, eps, p, seed + 1, True)
+        if CAPTURE_RELU is not None:
+            CAPTURE_RELU.append(("clf_a", (a1 if p == 0.0 else bn_act_fwd(z1, m1, v1, g1, be1, eps, 0.0, seed, True)) > 0))
+            CAPTURE_RELU.append(("clf_b", (a2 if p == 0.0 else bn_act_fwd(z2, m2, v2, g2, be2, eps, 0.0, seed, True)) > 0))
         out = torch.empty(rows, 4, device=dev)
         check(lib.eg_clf_out_fwd(rows, a2.data_ptr(), w3.data_ptr(), b3.data_ptr(), int(sigmoid), out.data_ptr(), st),
               "eg_clf_out_fwd")

@@ -275,6 +275,21 @@ def _drop(x, p, training, masks, key):
     return F.dropout(x, p, training)
 
 
+def _relu(x, masks, key):
+    """ReLU; when the caller supplies the sign pattern of another implementation (masks['relu:'+key], bool),
+    that pattern is imposed instead, so both sides differentiate the SAME piecewise-linear function (a
+    pre-activation within rounding of 0 otherwise flips between any two fp32 implementations and changes the
+    gradient of its whole 2-hop neighbourhood).  The largest |x| at a disagreeing position is recorded in
+    masks['relu_margin'] so the test can check that every disagreement is a rounding-level one."""
+    if masks is not None and ("relu:" + key) in masks:
+        m = masks["relu:" + key]
+        bad = (x.detach() > 0) != m
+        if bool(bad.any()):
+            masks.setdefault("relu_margin", []).append((key, int(bad.sum()), float(x.detach()[bad].abs().max())))
+        return x * m.to(x.dtype)
+    return F.relu(x)
+
+
 def embedder_forward(sd: Dict[str, Tensor], frames: Tensor, training: bool, dropout_p: float = 0.0):
     """default.yml embedder: one CNNResBlock 1->C (src/core/models.py:137-158): conv3x3 -> BN ->
     + 1x1 skip -> MaxPool(1) -> ReLU -> Dropout2d."""
@@ -364,7 +379,7 @@ def gnn_stack(sd, cfg: Cfg, feats: Tensor, edge_index: Tensor, training: bool, m
         h = _bn(sd, p + "module_1.", h, training)
         h = _drop(h, cfg.gnn_dropout_p, training, masks, f"gnn{i}")
         if i != L - 1:
-            h = F.relu(h)
+            h = _relu(h, masks, f"gnn{i}")
         if cfg.residual and h.shape[1] == hidden[i].shape[1]:
             h = h + hidden[i]
         hidden.append(h)
@@ -384,10 +399,10 @@ def classifiers(sd, cfg: Cfg, h: Tensor, training: bool, masks=None) -> Tensor:
     for k in range(cfg.num_output_channels):
         p = f"node_classifiers.{k}."
         z = F.linear(h, sd[p + "0.weight"], sd[p + "0.bias"])
-        z = F.relu(_bn(sd, p + "1.", z, training))
+        z = _relu(_bn(sd, p + "1.", z, training), masks, f"clf{k}a")
         z = _drop(z, cfg.classifier_dropout_p, training, masks, f"clf{k}a")
         z = F.linear(z, sd[p + "4.weight"], sd[p + "4.bias"])
-        z = F.relu(_bn(sd, p + "5.", z, training))
+        z = _relu(_bn(sd, p + "5.", z, training), masks, f"clf{k}b")
         z = _drop(z, cfg.classifier_dropout_p, training, masks, f"clf{k}b")
         z = F.linear(z, sd[p + "8.weight"], sd[p + "8.bias"])
         outs.append(torch.sigmoid(z) if cfg.output_activation == "sigmoid" else z)
