@@ -64,7 +64,7 @@ constexpr size_t kWorkspaceBytes = kStatsBytes + kWgradBytes + 65536;
 // from global (the 2x2 children of an aux node) and its self loop (staged, always last).  Rows that do
 // not fit this shape (hubs of use_connection_nodes, 'grid-diagonal' aux rows) are CSR rows: the plan
 // weights are zero and the row is summed from the device CSR instead.
-constexpr int kPlanSrc = 224;   // staged source rows per tile (224 x 128 B = 28 KB per K chunk)
+constexpr int kPlanSrc = 216;   // staged source rows per tile (216 x 128 B = 27 KB per K chunk)
 constexpr int kPlanStaged = 7;  // staged non-self edges per row
 constexpr int kPlanFar = 4;     // far edges per row
 struct alignas(16) PlanRow {    // 80 bytes

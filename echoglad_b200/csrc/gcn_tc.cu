@@ -21,7 +21,7 @@
 //
 // Work decomposition.  Tile = 128 output rows (8x16 lattice patches, see eg_graph::tile_nodes); K is
 // consumed in 4 chunks of 32 features.  Per chunk, two LOADER warps copy the tile's unique source rows
-// (own rows + lattice halo + parents, <= 224 rows x 128 B, eg::TilePlan) from global into a 3-stage RAW
+// (own rows + lattice halo + parents, <= 216 rows x 128 B, eg::TilePlan) from global into a 3-stage RAW
 // ring with cp.async -- no registers are held, so ~80 KB per SM are in flight and every neighbour row
 // crosses L2 -> SM once per tile instead of once per edge; 16 COMPUTE warps then gather / weight / sum
 // from shared memory: a row's slots and weights sit in registers for the whole tile (PlanRow), the inner
@@ -29,7 +29,8 @@
 // and are read from global, issued before the staged part.  The sums are split into tf32 hi/lo and fill a
 // 3-stage OPERAND ring ([128 rows x 128 B] hi + lo = 32 KB).
 // TMEM: 256 columns of weight + 2 x 128 of accumulator.
-// Warps: 0-3 epilogue (TMEM lane quadrant = warp id), 4 MMA issuer, 5-6 loaders, 7-22 compute.
+// Warps: 0-3 epilogue (TMEM lane quadrant = warp id), 4 MMA issuer, 5-7 loaders, 8-23 compute; the compute
+// warpgroups raise their register budget to 96 with setmaxnreg, the others drop to 64.
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -54,7 +55,7 @@ namespace {
 
 constexpr int kStages = 3;                 // operand ring (hi + lo tiles)
 constexpr int kRawStages = 3;              // raw source-row ring
-constexpr int kLoadWarps = 2;
+constexpr int kLoadWarps = 3;
 constexpr int kProdWarps = 16;             // compute warps: 8 tile rows per warp and stage
 constexpr int kRowsPerProd = 128 / kProdWarps;
 constexpr int kEpiWarps = 4;
@@ -62,13 +63,23 @@ constexpr int kMmaWarp = kEpiWarps;
 constexpr int kLoadWarp0 = kMmaWarp + 1;
 constexpr int kProdWarp0 = kLoadWarp0 + kLoadWarps;
 constexpr int kThreads = (kEpiWarps + 1 + kLoadWarps + kProdWarps) * 32;
+// Register budget by warpgroup (setmaxnreg): 8 non-compute warps drop to 56, 16 compute warps rise to 88.
+constexpr int kRegsCompute = 88, kRegsOther = 56;  // within the 768 x 80 registers the CTA is launched with
+static_assert(kEpiWarps == 4 && kLoadWarps == 3 && kProdWarps == 16, "warpgroup layout of setmaxnreg");
+static_assert((kEpiWarps + 1 + kLoadWarps) * 32 * kRegsOther + kProdWarps * 32 * kRegsCompute <= kThreads * 80, "register pool of the CTA");
 constexpr int kTileBytes = 128 * 128;      // one [128 rows x 32 tf32] operand tile
 constexpr uint32_t kABytes = kStages * 2 * kTileBytes;
-constexpr int kRawRows = kPlanSrc;         // 224 >= 128 (linear mode stages the tile's own rows)
+constexpr int kRawRows = kPlanSrc;         // 216 >= 128 (linear mode stages the tile's own rows)
 constexpr uint32_t kRawBytes = kRawRows * 128;
 constexpr uint32_t kPlanWarpBytes = kRowsPerProd * sizeof(PlanRow) + 16;  // a compute warp's 8 plan rows + tile header
 constexpr uint32_t kPlanBytes = kProdWarps * 2 * kPlanWarpBytes;           // double-buffered per warp
 constexpr uint32_t kSmemBytes = kABytes + kRawStages * kRawBytes + kPlanBytes + 256 /*barriers*/ + 1024 /*align*/;
+// shared-memory map, byte offsets from the 1024-byte aligned base
+constexpr uint32_t kOffRaw = kABytes;
+constexpr uint32_t kOffPlan = kOffRaw + kRawStages * kRawBytes;
+constexpr uint32_t kOffBars = kOffPlan + kPlanBytes;
+constexpr uint32_t kOffFull = kOffBars, kOffEmpty = kOffFull + 8 * kStages, kOffRawFull = kOffEmpty + 8 * kStages,
+                   kOffRawEmpty = kOffRawFull + 8 * kRawStages;
 constexpr int kTmemCols = 512;             // [0,128) W hi, [128,256) W lo, [256,384) / [384,512) accumulators
 constexpr uint32_t kTmemAcc = 256;
 static_assert(kPlanSrc % (kLoadWarps * 4) == 0 && kPlanSrc >= 128, "loader mapping");
@@ -79,7 +90,7 @@ struct TcParams {
   TilePlan plan;               // GATHER: per-tile staged sources and per-row edges
   int tiles_per_frame;
   int nodes_per_frame;
-  long long num_tiles;
+  int num_tiles;              // < 2^31 / 128 (rows < 2^31, checked by the launchers)
   long long rows;             // total rows of X / Out
   const int32_t* rowptr;
   const int32_t* col;
@@ -189,24 +200,33 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
   __syncthreads();
   tc_fence_after();
 
+  // one setmaxnreg per warpgroup: warps 0-7 (epilogue, MMA, loaders) release registers, warps 8-23 take them
+#ifndef EG_NO_SETMAXNREG
+  if (warp >= kProdWarp0) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
+  }
+#endif
   if (warp >= kProdWarp0) {
     // ===== compute warps: gather from the raw stage -> split -> swizzled operand tile =======================
     const int pw = warp - kProdWarp0;
     const int g = lane >> 3, j = lane & 7;
     constexpr int kIters = kRowsPerProd / 4;
-    const uint32_t sA_u = smem_u32(sA), sRaw_u = smem_u32(sRaw) + j * 16;
-    const uint32_t bar_full = smem_u32(full), bar_empty = smem_u32(empty);
-    const uint32_t bar_raw_full = smem_u32(raw_full), bar_raw_empty = smem_u32(raw_empty);
-    const uint32_t plan_u = smem_u32(sPlan) + pw * 2 * kPlanWarpBytes;  // this warp's two plan buffers
+    const uint32_t sm = smem_u32(smem);  // every shared address below is sm + a compile-time offset
+    const uint32_t sA_u = sm, sRaw_u = sm + kOffRaw + j * 16;
+    const uint32_t bar_full = sm + kOffFull, bar_empty = sm + kOffEmpty;
+    const uint32_t bar_raw_full = sm + kOffRawFull, bar_raw_empty = sm + kOffRawEmpty;
+    const uint32_t plan_u = sm + kOffPlan + pw * 2 * kPlanWarpBytes;  // this warp's two plan buffers
     const bool agg_out = p.AggOut != nullptr;
     uint32_t soff[kIters];  // swizzled position of this lane's 16 bytes inside an operand tile
 #pragma unroll
     for (int i = 0; i < kIters; ++i) soff[i] = sw128_off(pw * kRowsPerProd + i * 4 + g, j);
     // The warp's plan rows (8 x 80 B, contiguous) + the tile header travel global -> shared with cp.async one
     // tile ahead, so a tile starts with LDS instead of an exposed L2 round trip.
-    auto prefetch_plan = [&](long long tile, uint32_t buf) {
+    auto prefetch_plan = [&](int tile, uint32_t buf) {
       if (tile >= p.num_tiles) return;
-      const int t = (int)(tile % p.tiles_per_frame);
+      const int t = tile % p.tiles_per_frame;
       const uint32_t dst = plan_u + buf * kPlanWarpBytes;
       const uint8_t* src = reinterpret_cast<const uint8_t*>(p.plan.rows + (size_t)t * 128 + pw * kRowsPerProd);
       cp_async16(dst + lane * 16, src + lane * 16);
@@ -215,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
     };
     uint32_t chunk = 0, pbuf = 0;
     if (GATHER) prefetch_plan(blockIdx.x, 0);
-    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, pbuf ^= 1u) {
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, pbuf ^= 1u) {
       // Per tile: this lane's two rows of the gather plan (all 8 lanes of a row group hold the same copy)
       int ks = 0, nfar = 0, has_csr = 0;
       uint2 slots[kIters];
@@ -225,13 +245,13 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
       long long frow0 = 0;
       const uint32_t prow = plan_u + pbuf * kPlanWarpBytes + g * sizeof(PlanRow);  // + i * 4 rows
       if (GATHER) {
-        const long long b = tile / p.tiles_per_frame;
-        const int t = (int)(tile - b * p.tiles_per_frame);
+        const int b = tile / p.tiles_per_frame;
+        const int t = tile - b * p.tiles_per_frame;
         cp_async_wait_all();
         __syncwarp();
         const float4 hdr = lds4(plan_u + pbuf * kPlanWarpBytes + kRowsPerProd * sizeof(PlanRow));
         ks = __float_as_int(hdr.y), nfar = __float_as_int(hdr.z), has_csr = __float_as_int(hdr.w);
-        frow0 = b * p.nodes_per_frame;
+        frow0 = (long long)b * p.nodes_per_frame;
         fbase = p.X + frow0 * 128;
         tnode = p.tile_nodes + t * 128 + pw * kRowsPerProd + g;
 #pragma unroll
@@ -242,7 +262,6 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
           w1[i] = lds4(prow + i * 4 * sizeof(PlanRow) + 32);
         }
         prefetch_plan(tile + gridDim.x, pbuf ^ 1u);
-        cp_async_commit();
       }
       for (int kc = 0; kc < 4; ++kc, ++chunk) {
         const uint32_t stage = chunk % kStages, phase = (chunk / kStages) & 1u;
@@ -326,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
           } else {
             // linear mode: raw slot r = tile row r (rows past the end were not copied: zero them)
             const int r = pw * kRowsPerProd + i * 4 + g;
-            if (tile * 128 + r < p.rows) acc = lds4(raw + r * 128);
+            if ((long long)tile * 128 + r < p.rows) acc = lds4(raw + r * 128);
           }
           uint4 hi, lo;
           split_tf32_fast(acc.x, hi.x, lo.x);
@@ -349,12 +368,13 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
     constexpr int kPer = kRawRows / (kLoadWarps * 4);  // source rows per thread (8 lanes x 16 B per row)
     const int q = (warp - kLoadWarp0) * 32 + lane;
     const int sl = q >> 3, j = q & 7;
-    const uint32_t bar_raw_full = smem_u32(raw_full), bar_raw_empty = smem_u32(raw_empty);
-    const uint32_t dst0 = smem_u32(sRaw) + sl * 128 + j * 16;
+    const uint32_t sm = smem_u32(smem);
+    const uint32_t bar_raw_full = sm + kOffRawFull, bar_raw_empty = sm + kOffRawEmpty;
+    const uint32_t dst0 = sm + kOffRaw + sl * 128 + j * 16;
     // frame-local node staged in slot sl + (kLoadWarps*4) * m (-1 = none), fetched one tile ahead
-    auto load_src = [&](long long tile, int (&node)[kPer]) {
+    auto load_src = [&](int tile, int (&node)[kPer]) {
       if (GATHER && tile < p.num_tiles) {
-        const int t = (int)(tile % p.tiles_per_frame);
+        const int t = tile % p.tiles_per_frame;
 #pragma unroll
         for (int m = 0; m < kPer; ++m) node[m] = __ldg(p.plan.src + (size_t)t * kPlanSrc + sl + kLoadWarps * 4 * m);
       }
@@ -362,10 +382,10 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
     int nxt[kPer];
     load_src(blockIdx.x, nxt);
     uint32_t chunk = 0;
-    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       int srow[kPer];  // global row (< 2^31, checked by the launcher), or -1
       if (GATHER) {
-        const int base = (int)(tile / p.tiles_per_frame) * p.nodes_per_frame;
+        const int base = (tile / p.tiles_per_frame) * p.nodes_per_frame;
 #pragma unroll
         for (int m = 0; m < kPer; ++m) srow[m] = nxt[m] >= 0 ? base + nxt[m] : -1;
         load_src(tile + gridDim.x, nxt);
@@ -373,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
 #pragma unroll
         for (int m = 0; m < kPer; ++m) {
           const int s2 = sl + kLoadWarps * 4 * m;
-          const long long row = tile * 128 + s2;
+          const long long row = (long long)tile * 128 + s2;
           srow[m] = (s2 < 128 && row < p.rows) ? (int)row : -1;
         }
       }
@@ -398,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
     // ===== MMA issuer ======================================================================================
     constexpr uint32_t idesc = umma_idesc_tf32(128, 128, 0, 0);
     uint32_t chunk = 0, it = 0;
-    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, acc_phase = (it >> 1) & 1u;
       TC_TIMED_WAIT(0, &acc_empty[buf], acc_phase ^ 1u);
       tc_fence_after();
@@ -434,19 +454,19 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
     const float bias = p.bias ? __ldg(p.bias + f) : 0.f;
     double s_sum = 0.0, s_sq = 0.0;
     uint32_t it = 0;
-    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, acc_phase = (it >> 1) & 1u;
       // lane l < 8: first global row of group l (or -1); lane 8 + l: rows in group l
       long long gbase = -1;
       int gcnt = 0;
       if (GATHER) {
-        const long long b = tile / p.tiles_per_frame;
-        const int t = (int)(tile - b * p.tiles_per_frame);
+        const int b = tile / p.tiles_per_frame;
+        const int t = tile - b * p.tiles_per_frame;
         const int v = lane < 16 ? __ldg(p.tile_groups + t * 16 + lane) : 0;
         gcnt = v;
-        gbase = (lane < 8 && v >= 0) ? b * p.nodes_per_frame + v : -1;
+        gbase = (lane < 8 && v >= 0) ? (long long)b * p.nodes_per_frame + v : -1;
       } else {
-        const long long r0 = tile * 128 + (lane & 7) * 16;
+        const long long r0 = (long long)tile * 128 + (lane & 7) * 16;
         gbase = r0 < p.rows ? r0 : -1;
         gcnt = (int)max(0LL, min(16LL, p.rows - r0));
       }
@@ -566,7 +586,7 @@ int launch_gcn_tc(const eg_graph* g, int batch, const float* X, const float* W, 
   p.plan = graph_plan(g);
   p.tiles_per_frame = graph_tiles_per_frame(g);
   p.nodes_per_frame = info.num_nodes;
-  p.num_tiles = (long long)batch * p.tiles_per_frame;
+  p.num_tiles = batch * p.tiles_per_frame;
   p.rows = (long long)batch * info.num_nodes;
   if (p.rows >= (1LL << 31)) {
     set_error("batch * num_nodes = %lld does not fit the 32-bit row index of the tensor-core kernels", p.rows);
@@ -594,7 +614,7 @@ int launch_linear_tc(long long rows, const float* A, const float* W, int trans_w
     return EG_ERR_INVALID;
   }
   TcParams p{};
-  p.num_tiles = (rows + 127) / 128;
+  p.num_tiles = (int)((rows + 127) / 128);
   p.rows = rows;
   p.X = A;
   p.W = W;

@@ -462,6 +462,93 @@ int eg_graph_tiles(const eg_graph* g, const int32_t** tile_nodes, int32_t* tiles
   return EG_OK;
 }
 
+// Host-only self check of the tile table and the gather plan (no GPU needed): every node in exactly one
+// tile, 16-row groups consecutive, and for every row the plan (staged slots -> node ids, far nodes, self
+// loop) or its CSR flag reproduces the neighbour list and the gcn_norm weights.  stats (optional, int64[6]):
+// tiles, plan rows, CSR rows, far edges, staged edges, largest staged-source count.  Returns the number of
+// violations (0 = consistent) or a negative error code.
+int eg_graph_plan_check(const eg_graph_spec* spec, int64_t* stats) {
+  Topo t;
+  int rc = init_topo(spec, t);
+  if (rc) return rc;
+  const std::vector<int32_t> tiles = build_tiles(t);
+  const std::vector<int32_t> grp = build_groups(tiles);
+  const HostPlan hp = build_plan(t, tiles);
+  const int T = (int)(tiles.size() / 128);
+  long long bad = 0, plan_rows = 0, csr_rows = 0, far_edges = 0, staged_edges = 0, max_src = 0;
+  std::vector<int> seen(t.N, 0);
+  for (int32_t v : tiles)
+    if (v >= 0) {
+      if (v >= t.N) ++bad;
+      else ++seen[v];
+    }
+  for (int v = 0; v < t.N; ++v) bad += seen[v] != 1;
+  for (int ti = 0; ti < T; ++ti)
+    for (int gi = 0; gi < 8; ++gi) {
+      const int base = grp[ti * 16 + gi], cnt = grp[ti * 16 + 8 + gi];
+      for (int k = 0; k < 16; ++k) {
+        const int v = tiles[(size_t)ti * 128 + gi * 16 + k];
+        bad += (k < cnt) ? (v != base + k) : (v != -1);
+      }
+    }
+  std::vector<float> dis(t.N);
+  for (int u = 0; u < t.N; ++u) dis[u] = (float)(1.0 / sqrt((double)(degree_of(t, u) + 1)));
+  std::vector<std::pair<int, float>> want, got;
+  for (int ti = 0; ti < T; ++ti) {
+    const int4 h = hp.hdr[ti];
+    max_src = std::max<long long>(max_src, h.x);
+    bad += h.x < 1 || h.x > kPlanSrc || h.y < 0 || h.y > kPlanStaged || (h.z != 0 && h.z != kPlanFar);
+    const int32_t* src = &hp.src[(size_t)ti * kPlanSrc];
+    for (int k = 0; k < kPlanSrc; ++k) bad += (k < h.x) ? (src[k] < 0 || src[k] >= t.N) : (src[k] != -1);
+    for (int r = 0; r < 128; ++r) {
+      const int v = tiles[(size_t)ti * 128 + r];
+      const PlanRow& pr = hp.rows[(size_t)ti * 128 + r];
+      got.clear();
+      for (int k = 0; k < 8; ++k)
+        if (pr.w[k] != 0.f) {
+          if (pr.slot[k] >= h.x || (k < 7 && k >= h.y)) ++bad;
+          else got.emplace_back(src[pr.slot[k]], pr.w[k]);
+          staged_edges += k < 7;
+        } else if (pr.slot[k] != 0) {
+          ++bad;
+        }
+      for (int k = 0; k < 4; ++k)
+        if (pr.far_w[k] != 0.f) {
+          bad += h.z == 0;
+          got.emplace_back(pr.far_node[k], pr.far_w[k]);
+          ++far_edges;
+        } else if (pr.far_node[k] != 0) {
+          ++bad;
+        }
+      if (v < 0) {
+        bad += !got.empty() || pr.csr_deg != 0;
+        continue;
+      }
+      if (pr.csr_deg) {
+        ++csr_rows;
+        bad += !got.empty() || !h.w || pr.csr_deg != degree_of(t, v) + 1;
+        int beg = 0;
+        for (int u = 0; u < v; ++u) beg += degree_of(t, u) + 1;
+        bad += pr.csr_beg != beg;
+        continue;
+      }
+      ++plan_rows;
+      want.clear();
+      for_each_neighbor(t, v, true, [&](int u) { want.emplace_back(u, dis[u] * dis[v]); });
+      want.emplace_back(v, dis[v] * dis[v]);
+      bad += pr.w[7] == 0.f || src[pr.slot[7]] != v;  // entry 7 (summed last) is the self loop
+      std::sort(want.begin(), want.end());
+      std::sort(got.begin(), got.end());
+      bad += want != got;
+    }
+  }
+  if (stats) {
+    stats[0] = T, stats[1] = plan_rows, stats[2] = csr_rows, stats[3] = far_edges, stats[4] = staged_edges;
+    stats[5] = max_src;
+  }
+  return (int)std::min<long long>(bad, 1 << 30);
+}
+
 int eg_graph_export_edge_index(const eg_graph* g, int batch, int64_t* out, void* stream) {
   EG_CHECK_ARG(g && out && batch >= 1, "bad arguments");
   long long total = (long long)batch * g->topo.N;
