@@ -63,7 +63,7 @@ bn_act_fwd_kernel(long long rows, int cols, const float* __restrict__ H, const f
 // Pass 1 of the backward: per-column sums of dA and dA*xhat, where dA = dY * dropmask * relumask.
 // Block = (cols/4) column groups x RY row lanes; each thread keeps its column group for all its rows.
 // If dH_eval != NULL (eval-mode BN) dH = sc * dA is written in the same pass.
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 bn_act_bwd_reduce_kernel(long long rows, int cols, const float* __restrict__ dY, const float* __restrict__ H,
                          const float* __restrict__ mean, const float* __restrict__ var,
                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -79,24 +79,35 @@ bn_act_bwd_reduce_kernel(long long rows, int cols, const float* __restrict__ dY,
   double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
   int since_flush = 0;
   if (ty < ry) {
-    for (long long r = (long long)blockIdx.x * ry + ty; r < rows; r += (long long)gridDim.x * ry) {
-      const long long i = r * cg + tx;
-      float4 h = ldg4(H + i * 4), g = ldg4(dY + i * 4);
-      float hv[4] = {h.x, h.y, h.z, h.w}, gv[4] = {g.x, g.y, g.z, g.w}, o[4];
-      uint32_t keep = thr ? drop_keep4(seed, (uint64_t)i, thr) : 0xfu;
+    // two rows per iteration: 4 independent 128-bit loads in flight per thread (the pass is pure streaming)
+    const long long rstep = (long long)gridDim.x * ry;
+    for (long long r = (long long)blockIdx.x * ry + ty; r < rows; r += 2 * rstep) {
+      const long long ia = r * cg + tx;
+      const bool two = r + rstep < rows;
+      const long long ib = two ? ia + rstep * cg : ia;
+      const float4 ha = ldg4(H + ia * 4), ga = ldg4(dY + ia * 4);
+      const float4 hb = ldg4(H + ib * 4), gb = ldg4(dY + ib * 4);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const ColParams p = sp[tx * 4 + k];
-        float xc = hv[k] - p.mean;
-        float bn = fmaf(xc, p.sc, p.beta);
-        bool pass = ((keep >> k) & 1u) && (!relu || bn > 0.f);
-        float dA = pass ? gv[k] * keep_scale : 0.f;
-        s1[k] += dA;
-        s2[k] = fmaf(dA, xc * p.invstd, s2[k]);
-        o[k] = dA * p.sc;
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+        const long long i = u ? ib : ia;
+        const float4 h = u ? hb : ha, g = u ? gb : ga;
+        float hv[4] = {h.x, h.y, h.z, h.w}, gv[4] = {g.x, g.y, g.z, g.w}, o[4];
+        uint32_t keep = thr ? drop_keep4(seed, (uint64_t)i, thr) : 0xfu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const ColParams p = sp[tx * 4 + k];
+          float xc = hv[k] - p.mean;
+          float bn = fmaf(xc, p.sc, p.beta);
+          bool pass = ((keep >> k) & 1u) && (!relu || bn > 0.f);
+          float dA = pass ? gv[k] * keep_scale : 0.f;
+          s1[k] += dA;
+          s2[k] = fmaf(dA, xc * p.invstd, s2[k]);
+          o[k] = dA * p.sc;
+        }
+        if (dH_eval) st4(dH_eval + i * 4, make_float4(o[0], o[1], o[2], o[3]));
       }
-      if (dH_eval) st4(dH_eval + i * 4, make_float4(o[0], o[1], o[2], o[3]));
-      if (++since_flush == 64) {
+      if (++since_flush == 32) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) { d1[k] += s1[k]; d2[k] += s2[k]; s1[k] = s2[k] = 0.f; }
         since_flush = 0;

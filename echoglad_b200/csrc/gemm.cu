@@ -333,8 +333,12 @@ int launch_linear128(long long rows, const float* A, const float* W, int trans_w
   return EG_OK;
 }
 
+int launch_wgrad_tc(long long rows, const float* G, const float* X, float* dW, float* dbias, void* ws,
+                    size_t ws_bytes, cudaStream_t s);  // wgrad_tc.cu
+
 int launch_wgrad128(long long rows, const float* G, const float* X, float* dW, float* dbias, void* ws,
                     size_t ws_bytes, cudaStream_t s) {
+  if (!legacy_mma()) return launch_wgrad_tc(rows, G, X, dW, dbias, ws, ws_bytes, s);
   if (!ws || ws_bytes < kWorkspaceBytes) {
     set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
     return EG_ERR_WORKSPACE;

@@ -1,0 +1,254 @@
+// Weight gradient of the per-node transforms on the 5th-generation tensor cores:
+//
+//     dW[o][i] = sum_n G[n][o] * X[n][i]      (G = A_hat dH of a GCNConv, or dZ of classifier layer 0)
+//     dbias[o] = sum_n G[n][o]                 (optional)
+//
+// Replaces the autograd of nn.Linear inside PyG GCNConv.lin and node_classifiers[k][0]
+// (src/core/models.py:330,364; loss.backward() at src/engine.py:272).  HBM-bound: both [rows,128] operands
+// are read exactly once (2 U), the result is 64 KB.
+//
+// The reduction runs over the ROWS, so both operands are "MN-major" for the MMA (the 128 features of a row
+// are contiguous, the K index is the row): a block of 16 rows of G and of X travels global -> shared with
+// cp.async straight into the canonical MN-major SWIZZLE_128B layout (4 atoms of 32 features x 8 rows x 2
+// row groups), no transpose anywhere.  3xTF32: split warps rewrite the raw block in place as its tf32 hi part
+// and write the lo part to a second ring; one elected thread issues, per 8-row group,
+//     D += G_lo^T X_hi,  D += G_hi^T X_lo,  D += G_hi^T X_hi        (tcgen05.mma kind::tf32, M = N = 128, K = 8)
+// into ONE 128-column TMEM accumulator that lives for the whole kernel.  Each CTA drains its accumulator once
+// at the end ([148][128][128] partials) and a fixed-order second stage sums the partials in double: no atomics,
+// bit-reproducible.
+//
+// Rings: RAW/hi ring of kRaw blocks (16 KB: G and X) deep enough to cover the HBM latency, LO ring of kLo blocks.
+// Warps: 0-3 loaders (and the final epilogue: TMEM lane quadrant = warp id), 4 MMA issuer, 5-12 split.
+#include "common.cuh"
+#include "tc05.cuh"
+
+using namespace eg;
+using namespace eg::tc;
+
+namespace {
+
+constexpr int kRows = 16;                      // rows per block (2 MMA k-steps of 8)
+constexpr int kRaw = 9;                        // raw / hi ring depth
+constexpr int kLo = 4;                         // lo ring depth
+constexpr int kLoadWarps = 4, kSplitWarps = 8;
+constexpr int kMmaWarp = kLoadWarps;
+constexpr int kSplitWarp0 = kMmaWarp + 1;
+constexpr int kThreads = (kLoadWarps + 1 + kSplitWarps) * 32;
+constexpr uint32_t kOpBytes = kRows * 512;     // one operand (G or X) of a block: 8 KB
+constexpr uint32_t kBlockBytes = 2 * kOpBytes; // G + X
+constexpr uint32_t kOffLo = kRaw * kBlockBytes;
+constexpr uint32_t kOffBars = kOffLo + kLo * kBlockBytes;
+constexpr uint32_t kSmemBytes = kOffBars + 8 * (2 * kRaw + 2 * kLo + 1) + 16 + 1024;
+constexpr uint32_t kLbo = (kRows / 8) * 1024;  // byte stride between the 32-feature atoms of an operand
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+// byte offset of 16-byte chunk c (0..31: features 4c..4c+3) of row r (0..kRows-1) inside an operand block:
+// atom a = c / 8 (32 features), row group kg = r / 8; inside the 1 KB atom the chunk position is XOR-swizzled.
+__device__ __forceinline__ uint32_t op_off(int r, int c) {
+  return (uint32_t)((((c >> 3) * (kRows / 8) + (r >> 3)) << 10) + ((r & 7) << 7) + (((c & 7) ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool ok) {
+  const int sz = ok ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void split4(const float4& x, uint4& hi, uint4& lo) {
+  split_tf32_fast(x.x, hi.x, lo.x);
+  split_tf32_fast(x.y, hi.y, lo.y);
+  split_tf32_fast(x.z, hi.z, lo.z);
+  split_tf32_fast(x.w, hi.w, lo.w);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(long long rows, const float* __restrict__ G, const float* __restrict__ X,
+                float* __restrict__ parts, double* __restrict__ colsum_parts) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sm = smem_u32(smem);
+  const uint32_t bar_raw_full = sm + kOffBars, bar_raw_empty = bar_raw_full + 8 * kRaw,
+                 bar_lo_full = bar_raw_empty + 8 * kRaw, bar_lo_empty = bar_lo_full + 8 * kLo,
+                 bar_acc = bar_lo_empty + 8 * kLo;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRaw + 2 * kLo + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long nblocks = (rows + kRows - 1) / kRows;
+
+  if (warp == kMmaWarp && lane == 0) {
+    for (int s = 0; s < kRaw; ++s) {
+      mbar_init(bars + s, kLoadWarps * 32);  // raw_full: one cp.async arrival per loader thread
+      mbar_init(bars + kRaw + s, 1);         // raw_empty: tcgen05.commit
+    }
+    for (int s = 0; s < kLo; ++s) {
+      mbar_init(bars + 2 * kRaw + s, kSplitWarps);  // lo_full
+      mbar_init(bars + 2 * kRaw + kLo + s, 1);      // lo_empty: tcgen05.commit
+    }
+    mbar_init(bars + 2 * kRaw + 2 * kLo, 1);        // accumulator complete
+    mbar_init_fence();
+  }
+  if (warp == 0) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kLoadWarps) {
+    // ===== loaders: 16 rows x 512 B of G and of X per block, one global row per warp instruction ================
+    const int c = lane;
+    uint32_t it = 0;
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
+      const uint32_t rs = it % kRaw, rphase = (it / kRaw) & 1u;
+      mbar_wait_a(bar_raw_empty + rs * 8, rphase ^ 1u);
+      const uint32_t dst = sm + rs * kBlockBytes;
+      const long long row0 = blk * kRows;
+#pragma unroll
+      for (int m = 0; m < kRows / kLoadWarps; ++m) {
+        const int r = warp + kLoadWarps * m;
+        const bool ok = row0 + r < rows;
+        const long long off = ok ? (row0 + r) * 128 + c * 4 : 0;
+        cp_async16_zfill(dst + op_off(r, c), G + off, ok);
+        cp_async16_zfill(dst + kOpBytes + op_off(r, c), X + off, ok);
+      }
+      cp_async_mbar_arrive_a(bar_raw_full + rs * 8);
+    }
+    // ===== epilogue: the CTA's partial dW, thread <-> output feature o = TMEM lane ==============================
+    mbar_wait_a(bar_acc, 0);
+    tc_fence_after();
+    const int o = warp * 32 + lane;
+    float* P = parts + (size_t)blockIdx.x * 128 * 128 + (size_t)o * 128;
+#pragma unroll 1
+    for (int sl = 0; sl < 4; ++sl) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + sl * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(P + sl * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+  } else if (warp == kMmaWarp) {
+    // ===== MMA issuer ==========================================================================================
+    constexpr uint32_t idesc = umma_idesc_tf32(128, 128, 1, 1);  // both operands MN-major
+    uint32_t it = 0;
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
+      const uint32_t rs = it % kRaw;
+      const uint32_t ls = it % kLo, lphase = (it / kLo) & 1u;
+      mbar_wait_a(bar_lo_full + ls * 8, lphase);  // the split warps wrote hi (in place) and lo of this block
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t g_hi = sm + rs * kBlockBytes, x_hi = g_hi + kOpBytes;
+        const uint32_t g_lo = sm + kOffLo + ls * kBlockBytes, x_lo = g_lo + kOpBytes;
+#pragma unroll
+        for (int kg = 0; kg < kRows / 8; ++kg) {
+          const uint32_t o = kg * 1024;
+          umma_tf32(tmem_base, umma_desc_mn128(g_lo + o, kLbo, 1024), umma_desc_mn128(x_hi + o, kLbo, 1024), idesc,
+                    (it | (uint32_t)kg) != 0);
+          umma_tf32(tmem_base, umma_desc_mn128(g_hi + o, kLbo, 1024), umma_desc_mn128(x_lo + o, kLbo, 1024), idesc, 1u);
+          umma_tf32(tmem_base, umma_desc_mn128(g_hi + o, kLbo, 1024), umma_desc_mn128(x_hi + o, kLbo, 1024), idesc, 1u);
+        }
+        umma_commit(bars + kRaw + rs);            // raw_empty
+        umma_commit(bars + 2 * kRaw + kLo + ls);  // lo_empty
+      }
+      __syncwarp();
+    }
+    if (lane == 0) umma_commit(bars + 2 * kRaw + 2 * kLo);
+    __syncwarp();
+  } else {
+    // ===== split warps: raw -> tf32 hi (in place) + lo; column sums of G ========================================
+    const int t = tid - kSplitWarp0 * 32;
+    const int c = t & 31, r0 = (t >> 5) * (kRows / kSplitWarps);
+    uint32_t off[kRows / kSplitWarps];
+#pragma unroll
+    for (int m = 0; m < kRows / kSplitWarps; ++m) off[m] = op_off(r0 + m, c);
+    double cs[4] = {0.0, 0.0, 0.0, 0.0};
+    uint32_t it = 0;
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
+      const uint32_t rs = it % kRaw, rphase = (it / kRaw) & 1u;
+      const uint32_t ls = it % kLo, lphase = (it / kLo) & 1u;
+      mbar_wait_a(bar_raw_full + rs * 8, rphase);
+      mbar_wait_a(bar_lo_empty + ls * 8, lphase ^ 1u);
+      const uint32_t raw = sm + rs * kBlockBytes, lo_t = sm + kOffLo + ls * kBlockBytes;
+      float4 sg = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int m = 0; m < kRows / kSplitWarps; ++m) {
+        const float4 g = lds4(raw + off[m]);
+        const float4 x = lds4(raw + kOpBytes + off[m]);
+        uint4 hi, lo;
+        split4(g, hi, lo);
+        sts4(raw + off[m], hi);
+        sts4(lo_t + off[m], lo);
+        split4(x, hi, lo);
+        sts4(raw + kOpBytes + off[m], hi);
+        sts4(lo_t + kOpBytes + off[m], lo);
+        sg.x += g.x, sg.y += g.y, sg.z += g.z, sg.w += g.w;
+      }
+      cs[0] += (double)sg.x, cs[1] += (double)sg.y, cs[2] += (double)sg.z, cs[3] += (double)sg.w;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(bar_lo_full + ls * 8);
+    }
+    if (colsum_parts) {  // [cta][split warp][128]; thread owns features 4c..4c+3 of its warp's rows
+      double* dst = colsum_parts + ((size_t)blockIdx.x * kSplitWarps + (t >> 5)) * 128 + c * 4;
+      dst[0] = cs[0], dst[1] = cs[1], dst[2] = cs[2], dst[3] = cs[3];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+// fixed-order second stage: dW = sum of the per-CTA partials, dbias = sum of the per-warp column sums (double)
+__global__ void wgrad_tc_reduce_kernel(int nparts, const float* __restrict__ parts,
+                                       const double* __restrict__ colsum_parts, float* __restrict__ dW,
+                                       float* __restrict__ dbias) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 128 * 128) {
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += (double)parts[(size_t)p * 128 * 128 + i];
+    dW[i] = (float)s;
+  }
+  if (dbias && i < 128) {
+    double s = 0.0;
+    for (int p = 0; p < nparts * kSplitWarps; ++p) s += colsum_parts[(size_t)p * 128 + i];
+    dbias[i] = (float)s;
+  }
+}
+
+}  // namespace
+
+namespace eg {
+
+int launch_wgrad_tc(long long rows, const float* G, const float* X, float* dW, float* dbias, void* ws,
+                    size_t ws_bytes, cudaStream_t s) {
+  static_assert((size_t)kNumSMs * kSplitWarps * 128 * sizeof(double) <= kStatsBytes, "column-sum partials fit the stats area");
+  if (!ws || ws_bytes < kWorkspaceBytes) {
+    set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
+    return EG_ERR_WORKSPACE;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    EG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr_done = true;
+  }
+  const long long nblocks = (rows + kRows - 1) / kRows;
+  const int grid = (int)(nblocks < kNumSMs ? nblocks : kNumSMs);
+  double* colsum = reinterpret_cast<double*>(ws);
+  float* parts = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);
+  ProfileScope prof("wgrad_tc", s);
+  wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(rows, G, X, parts, dbias ? colsum : nullptr);
+  EG_LAUNCH_CHECK();
+  wgrad_tc_reduce_kernel<<<(128 * 128 + 255) / 256, 256, 0, s>>>(grid, parts, dbias ? colsum : nullptr, dW, dbias);
+  EG_LAUNCH_CHECK();
+  return EG_OK;
+}
+
+}  // namespace eg
