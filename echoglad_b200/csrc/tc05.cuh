@@ -104,11 +104,14 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-// MN-major SWIZZLE_128B: atoms of 128 B (32 tf32 along M/N) x 8 K-rows; LBO = byte stride between atoms
-// along M/N, SBO = byte stride between 8-row groups along K.
-__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// MN-major operands of kind::tf32 (32-bit elements) must use the SWIZZLE_128B_BASE32B layout (layout type 1;
+// CUTLASS: "for mn-major tf32 operands, SW128_32B is the only available smem layout"): rows of 128 B = 32 tf32
+// along M/N, one row per K index, swizzle atom = 4 K-rows (512 B) in which the 32-byte unit u of row r sits at
+// unit position u ^ (r & 3) (Swizzle<2,5,2> on byte addresses).  LBO = byte stride between 32-element atoms
+// along M/N, SBO = byte stride between 4-row groups along K; one K = 8 MMA spans two groups.
+__device__ __forceinline__ uint64_t umma_desc_mn128_b32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
-         ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+         ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
 // kind::tf32 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
 // a_major / b_major (bits 15 / 16: 0 = K-major, 1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28.

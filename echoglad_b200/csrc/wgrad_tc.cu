@@ -9,8 +9,8 @@
 //
 // The reduction runs over the ROWS, so both operands are "MN-major" for the MMA (the 128 features of a row
 // are contiguous, the K index is the row): a block of 16 rows of G and of X travels global -> shared with
-// cp.async straight into the canonical MN-major SWIZZLE_128B layout (4 atoms of 32 features x 8 rows x 2
-// row groups), no transpose anywhere.  3xTF32: split warps rewrite the raw block in place as its tf32 hi part
+// cp.async straight into the canonical MN-major layout of 32-bit operands (SWIZZLE_128B_BASE32B: 4 atoms of
+// 32 features x 4 row groups of 4 rows), no transpose anywhere.  3xTF32: split warps rewrite the raw block in place as its tf32 hi part
 // and write the lo part to a second ring; one elected thread issues, per 8-row group,
 //     D += G_lo^T X_hi,  D += G_hi^T X_lo,  D += G_hi^T X_hi        (tcgen05.mma kind::tf32, M = N = 128, K = 8)
 // into ONE 128-column TMEM accumulator that lives for the whole kernel.  Each CTA drains its accumulator once
@@ -39,13 +39,15 @@ constexpr uint32_t kBlockBytes = 2 * kOpBytes; // G + X
 constexpr uint32_t kOffLo = kRaw * kBlockBytes;
 constexpr uint32_t kOffBars = kOffLo + kLo * kBlockBytes;
 constexpr uint32_t kSmemBytes = kOffBars + 8 * (2 * kRaw + 2 * kLo + 1) + 16 + 1024;
-constexpr uint32_t kLbo = (kRows / 8) * 1024;  // byte stride between the 32-feature atoms of an operand
+constexpr uint32_t kLbo = (kRows / 4) * 512;   // byte stride between the 32-feature atoms of an operand
+constexpr uint32_t kSbo = 512;                 // byte stride between 4-row groups
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // byte offset of 16-byte chunk c (0..31: features 4c..4c+3) of row r (0..kRows-1) inside an operand block:
-// atom a = c / 8 (32 features), row group kg = r / 8; inside the 1 KB atom the chunk position is XOR-swizzled.
+// [atom a = c / 8 (32 features)][row group r / 4][4 rows x 128 B]; inside the 512-byte swizzle atom the 32-byte
+// unit (c & 7) >> 1 of row r sits at unit position ((c & 7) >> 1) ^ (r & 3)  (SWIZZLE_128B_BASE32B).
 __device__ __forceinline__ uint32_t op_off(int r, int c) {
-  return (uint32_t)((((c >> 3) * (kRows / 8) + (r >> 3)) << 10) + ((r & 7) << 7) + (((c & 7) ^ (r & 7)) << 4));
+  return (uint32_t)(((c >> 3) * (kRows / 4) + (r >> 2)) * 512 + (r & 3) * 128 + (((((c & 7) >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4)));
 }
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool ok) {
@@ -147,10 +149,10 @@ wgrad_tc_kernel(long long rows, const float* __restrict__ G, const float* __rest
 #pragma unroll
         for (int kg = 0; kg < kRows / 8; ++kg) {
           const uint32_t o = kg * 1024;
-          umma_tf32(tmem_base, umma_desc_mn128(g_lo + o, kLbo, 1024), umma_desc_mn128(x_hi + o, kLbo, 1024), idesc,
+          umma_tf32(tmem_base, umma_desc_mn128_b32(g_lo + o, kLbo, kSbo), umma_desc_mn128_b32(x_hi + o, kLbo, kSbo), idesc,
                     (it | (uint32_t)kg) != 0);
-          umma_tf32(tmem_base, umma_desc_mn128(g_hi + o, kLbo, 1024), umma_desc_mn128(x_lo + o, kLbo, 1024), idesc, 1u);
-          umma_tf32(tmem_base, umma_desc_mn128(g_hi + o, kLbo, 1024), umma_desc_mn128(x_hi + o, kLbo, 1024), idesc, 1u);
+          umma_tf32(tmem_base, umma_desc_mn128_b32(g_hi + o, kLbo, kSbo), umma_desc_mn128_b32(x_lo + o, kLbo, kSbo), idesc, 1u);
+          umma_tf32(tmem_base, umma_desc_mn128_b32(g_hi + o, kLbo, kSbo), umma_desc_mn128_b32(x_hi + o, kLbo, kSbo), idesc, 1u);
         }
         umma_commit(bars + kRaw + rs);            // raw_empty
         umma_commit(bars + 2 * kRaw + kLo + ls);  // lo_empty
