@@ -279,11 +279,16 @@ def run_native(args):
     value = frames_total / (ms / 1e3)
     hbm_peak, peak_src = peaks()
     # dominant kernel: the fused tcgen05 message-passing + transform kernel (gather A_hat X -> 3xTF32 MMA ->
-    # bias / statistics / residual epilogue).  Algorithmic bytes per launch: every input row read
-    # once + every output row written once (+ the 64 KB weight); index bytes are overhead and not counted.
-    agg_ms, agg_n = prof.get("gcn_tc", (0.0, 0))
-    a_agg = 2 * B * N_NODES * F * 4 + F * F * 4
+    # bias / statistics / residual epilogue).  Algorithmic bytes per launch: forward = every input
+    # row read once + every output row written once (+ the 64 KB weight) = 2 U; the backward launch also reads the
+    # residual gradient and writes the A_hat dH side output = 4 U.  Index bytes are overhead and not counted.
+    u_bytes = B * N_NODES * F * 4
+    agg_ms, agg_n = prof.get("gcn_tc_fwd", (0.0, 0))
+    a_agg = 2 * u_bytes + F * F * 4
     achieved = (a_agg * agg_n) / (agg_ms / 1e3) / 1e9 if agg_ms > 0 else None
+    bwd_ms, bwd_n = prof.get("gcn_tc_bwd", (0.0, 0))
+    a_bwd = 4 * u_bytes + F * F * 4
+    achieved_bwd = (a_bwd * bwd_n) / (bwd_ms / 1e3) / 1e9 if bwd_ms > 0 else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram__bytes_read+write per launch from the last ncu --set full capture
     if os.path.exists(tpath):
@@ -318,11 +323,14 @@ def run_native(args):
                 "h2d_bytes_per_step": int(frames_h.numel() * 4 + coords_h.numel() * 4) * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "gcn_tc (fused A_hat X gather + 3xTF32 tcgen05 transform, fwd and bwd-dX)",
+        "roofline": {"bound": "hbm", "kernel": "gcn_tc forward launches (fused A_hat X gather + 3xTF32 tcgen05 transform + bias/BN statistics)",
                      "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": a_agg,
-                     "launches_per_step": agg_n / args.steps, "avg_launch_ms": (agg_ms / agg_n) if agg_n else None},
+                     "launches_per_step": agg_n / args.steps, "avg_launch_ms": (agg_ms / agg_n) if agg_n else None,
+                     "backward_launches": {"achieved": achieved_bwd, "frac": (achieved_bwd / hbm_peak) if achieved_bwd else None,
+                                           "algorithmic_bytes_per_launch": a_bwd, "launches_per_step": bwd_n / args.steps,
+                                           "avg_launch_ms": (bwd_ms / bwd_n) if bwd_n else None}},
         "cpu_baseline": cpu_baseline,
         "kernels": kernels,
         "native_kernel_ms_per_step": native_ms,

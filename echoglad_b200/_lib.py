@@ -52,6 +52,9 @@ SIGNATURES = {
     "eg_graph_check_edge_index": (_I, [_P, _I, _P, _L, _P, _P]),
     "eg_pack_nodes": (_I, [_P, _I, C.POINTER(_P), _P, _P, _P, _P]),
     "eg_pack_nodes_grad": (_I, [_P, _I, _P, C.POINTER(_P), _P, _P, _P]),
+    "eg_level_embed_supported": (_I, [_P, _I, _I]),
+    "eg_level_embed_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "eg_level_embed_bwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "eg_gcn_aggregate": (_I, [_P, _I, _I, _P, _P, _P]),
     "eg_gcn_conv_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "eg_gcn_conv_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),

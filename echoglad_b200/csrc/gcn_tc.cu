@@ -20,17 +20,20 @@
 //     the 32 lanes of a warp hold 32 consecutive features = one coalesced 128-byte store.  No staging.
 //
 // Work decomposition.  Tile = 128 output rows (8x16 lattice patches, see eg_graph::tile_nodes); K is
-// consumed in 4 chunks of 32 features.  Per chunk, two LOADER warps copy the tile's unique source rows
+// consumed in 4 chunks of 32 features.  Per chunk, three LOADER warps copy the tile's unique source rows
 // (own rows + lattice halo + parents, <= 216 rows x 128 B, eg::TilePlan) from global into a 3-stage RAW
 // ring with cp.async -- no registers are held, so ~80 KB per SM are in flight and every neighbour row
 // crosses L2 -> SM once per tile instead of once per edge; 16 COMPUTE warps then gather / weight / sum
-// from shared memory: a row's slots and weights sit in registers for the whole tile (PlanRow), the inner
-// loop is branch-free LDS.128 + 4 FFMA per edge; the 2x2 children of an aux node are not staged (512 rows)
-// and are read from global, issued before the staged part.  The sums are split into tf32 hi/lo and fill a
-// 3-stage OPERAND ring ([128 rows x 128 B] hi + lo = 32 KB).
+// from shared memory.  A lattice tile (every main-level tile: <= 5 staged neighbours + the row itself) keeps
+// its slot offsets and weights in registers for the whole tile; its inner loop is 6 LDS.128 + 12 FFMA2
+// (packed fp32 pairs) per row.  The 2x2 children of an aux node are not staged (512 rows) and are read
+// from global, issued before the staged part.  The sums are split into tf32 hi/lo and fill a 3-stage
+// OPERAND ring ([128 rows x 128 B] hi + lo = 32 KB).  The compute warps are the critical resource of the
+// kernel (measured: they are busy > 80 % of the time while loaders, MMA and epilogue wait), so everything
+// that can live elsewhere does: row copies in the loader warps, waits with a suspend hint.
 // TMEM: 256 columns of weight + 2 x 128 of accumulator.
 // Warps: 0-3 epilogue (TMEM lane quadrant = warp id), 4 MMA issuer, 5-7 loaders, 8-23 compute; the compute
-// warpgroups raise their register budget to 96 with setmaxnreg, the others drop to 64.
+// warpgroups raise their register budget to 88 with setmaxnreg, the others drop to 56.
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -55,18 +58,19 @@ namespace {
 
 constexpr int kStages = 3;                 // operand ring (hi + lo tiles)
 constexpr int kRawStages = 3;              // raw source-row ring
-constexpr int kLoadWarps = 3;
 constexpr int kProdWarps = 16;             // compute warps: 8 tile rows per warp and stage
 constexpr int kRowsPerProd = 128 / kProdWarps;
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = kEpiWarps;
+constexpr int kLoadWarps = 3;
 constexpr int kLoadWarp0 = kMmaWarp + 1;
 constexpr int kProdWarp0 = kLoadWarp0 + kLoadWarps;
-constexpr int kThreads = (kEpiWarps + 1 + kLoadWarps + kProdWarps) * 32;
-// Register budget by warpgroup (setmaxnreg): 8 non-compute warps drop to 56, 16 compute warps rise to 88.
-constexpr int kRegsCompute = 88, kRegsOther = 56;  // within the 768 x 80 registers the CTA is launched with
-static_assert(kEpiWarps == 4 && kLoadWarps == 3 && kProdWarps == 16, "warpgroup layout of setmaxnreg");
-static_assert((kEpiWarps + 1 + kLoadWarps) * 32 * kRegsOther + kProdWarps * 32 * kRegsCompute <= kThreads * 80, "register pool of the CTA");
+constexpr int kThreads = (kProdWarp0 + kProdWarps) * 32;  // 768 threads launched with 80 registers each
+static_assert(kProdWarp0 == 8, "warpgroup layout of setmaxnreg");
+// Register budget by warpgroup (setmaxnreg): the 8 non-compute warps drop to 56, the 16 compute warps rise to 88
+// (each SM sub-partition hosts 2 + 4 of them: 2 x 56 + 4 x 88 = 464 registers x 32 lanes <= 16384).
+constexpr int kRegsCompute = 88, kRegsOther = 56;
+static_assert(kProdWarp0 * 32 * kRegsOther + kProdWarps * 32 * kRegsCompute <= kThreads * 80, "register pool of the CTA");
 constexpr int kTileBytes = 128 * 128;      // one [128 rows x 32 tf32] operand tile
 constexpr uint32_t kABytes = kStages * 2 * kTileBytes;
 constexpr int kRawRows = kPlanSrc;         // 216 >= 128 (linear mode stages the tile's own rows)
@@ -131,15 +135,33 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
   acc.z = fmaf(w, x.z, acc.z);
   acc.w = fmaf(w, x.w, acc.w);
 }
+// Same arithmetic (round-to-nearest fp32 FMA per element) as two packed FFMA2 instructions: sm_100 issues
+// fma.rn.f32x2 with the scalar weight broadcast to both halves, which halves the FMA issue slots of the gather.
+__device__ __forceinline__ void fma4_x2(float4& acc, float w, const float4& x) {
+  unsigned long long a0, a1;
+  const unsigned long long w2 = ((unsigned long long)__float_as_uint(w) << 32) | __float_as_uint(w);
+  const unsigned long long x0 = ((unsigned long long)__float_as_uint(x.y) << 32) | __float_as_uint(x.x);
+  const unsigned long long x1 = ((unsigned long long)__float_as_uint(x.w) << 32) | __float_as_uint(x.z);
+  const unsigned long long c0 = ((unsigned long long)__float_as_uint(acc.y) << 32) | __float_as_uint(acc.x);
+  const unsigned long long c1 = ((unsigned long long)__float_as_uint(acc.w) << 32) | __float_as_uint(acc.z);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a0) : "l"(w2), "l"(x0), "l"(c0));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(a1) : "l"(w2), "l"(x1), "l"(c1));
+  acc.x = __uint_as_float((uint32_t)a0);
+  acc.y = __uint_as_float((uint32_t)(a0 >> 32));
+  acc.z = __uint_as_float((uint32_t)a1);
+  acc.w = __uint_as_float((uint32_t)(a1 >> 32));
+}
 
 template <bool GATHER>
 __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
 #ifdef EG_TC_TIMING
-  long long dbg_acc[2] = {0, 0};
+  long long dbg_acc[4] = {0, 0, 0, 0};
   const long long dbg_t0 = clock64();
 #endif
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte aligned base in the shared address space (the swizzle patterns are functions of the shared address)
+  const uint32_t sm = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sm - smem_u32(smem_raw));
   uint8_t* sA = smem;                     // [stage][hi|lo][16 KB]
   uint8_t* sRaw = sA + kABytes;           // [raw stage][kRawRows][128 B]
   uint8_t* sPlan = sRaw + kRawStages * kRawBytes;  // [compute warp][2][kPlanWarpBytes]
@@ -149,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
   uint64_t* raw_full = empty + kStages;   // [kRawStages]  loaders (cp.async completion) -> compute
   uint64_t* raw_empty = raw_full + kRawStages;   // [kRawStages]  compute -> loaders
   uint64_t* acc_full = raw_empty + kRawStages;   // [2] MMA -> epilogue
-  uint64_t* acc_empty = acc_full + 2;            // [2] epilogue -> MMA
+  uint64_t* acc_empty = acc_full + 2;     // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -200,28 +222,25 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
   __syncthreads();
   tc_fence_after();
 
-  // one setmaxnreg per warpgroup: warps 0-7 (epilogue, MMA, loaders) release registers, warps 8-23 take them
-#ifndef EG_NO_SETMAXNREG
+  // one setmaxnreg per warpgroup: warps 0-7 release registers, warps 8-23 take them
   if (warp >= kProdWarp0) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
   }
-#endif
   if (warp >= kProdWarp0) {
-    // ===== compute warps: gather from the raw stage -> split -> swizzled operand tile =======================
+    // ===== compute warps: copy raw rows two chunks ahead, gather -> split -> swizzled operand tile ==========
     const int pw = warp - kProdWarp0;
     const int g = lane >> 3, j = lane & 7;
     constexpr int kIters = kRowsPerProd / 4;
-    const uint32_t sm = smem_u32(smem);  // every shared address below is sm + a compile-time offset
-    const uint32_t sA_u = sm, sRaw_u = sm + kOffRaw + j * 16;
-    const uint32_t bar_full = sm + kOffFull, bar_empty = sm + kOffEmpty;
-    const uint32_t bar_raw_full = sm + kOffRawFull, bar_raw_empty = sm + kOffRawEmpty;
     const uint32_t plan_u = sm + kOffPlan + pw * 2 * kPlanWarpBytes;  // this warp's two plan buffers
-    const bool agg_out = p.AggOut != nullptr;
+    const uint32_t lane_raw = kOffRaw + j * 16;  // this lane's 16 bytes of a staged 128-byte row slice
     uint32_t soff[kIters];  // swizzled position of this lane's 16 bytes inside an operand tile
 #pragma unroll
-    for (int i = 0; i < kIters; ++i) soff[i] = sw128_off(pw * kRowsPerProd + i * 4 + g, j);
+    for (int i = 0; i < kIters; ++i) {
+      soff[i] = sw128_off(pw * kRowsPerProd + i * 4 + g, j);
+      asm volatile("" : "+r"(soff[i]));  // opaque: kept in a register instead of being recomputed from tid per chunk
+    }
     // The warp's plan rows (8 x 80 B, contiguous) + the tile header travel global -> shared with cp.async one
     // tile ahead, so a tile starts with LDS instead of an exposed L2 round trip.
     auto prefetch_plan = [&](int tile, uint32_t buf) {
@@ -233,27 +252,206 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
       if (lane < 8) cp_async16(dst + (32 + lane) * 16, src + (32 + lane) * 16);
       if (lane == 8) cp_async16(dst + kRowsPerProd * sizeof(PlanRow), p.plan.hdr + t);
     };
-    uint32_t chunk = 0, pbuf = 0;
-    if (GATHER) prefetch_plan(blockIdx.x, 0);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, pbuf ^= 1u) {
-      // Per tile: this lane's two rows of the gather plan (all 8 lanes of a row group hold the same copy)
-      int ks = 0, nfar = 0, has_csr = 0;
-      uint2 slots[kIters];
-      float4 w0[kIters], w1[kIters];
-      const float* fbase = p.X;
-      const int32_t* tnode = nullptr;
-      long long frow0 = 0;
-      const uint32_t prow = plan_u + pbuf * kPlanWarpBytes + g * sizeof(PlanRow);  // + i * 4 rows
-      if (GATHER) {
+
+    uint32_t chunk = 0;
+    // waits for the raw stage and a free operand stage of `chunk`; returns the shared addresses of both
+    auto acquire = [&](uint32_t& raw, uint32_t& a_hi) {
+      const uint32_t stage = chunk % kStages, phase = (chunk / kStages) & 1u;
+      const uint32_t rs = chunk % kRawStages, rphase = (chunk / kRawStages) & 1u;
+#ifdef EG_TC_TIMING
+      const long long _t = clock64();
+      mbar_wait_a(sm + kOffRawFull + rs * 8, rphase);
+      dbg_acc[1] += clock64() - _t;
+      const long long _t2 = clock64();
+      mbar_wait_a(sm + kOffEmpty + stage * 8, phase ^ 1u);
+      dbg_acc[0] += clock64() - _t2;
+#else
+      mbar_wait_a(sm + kOffRawFull + rs * 8, rphase);
+      mbar_wait_a(sm + kOffEmpty + stage * 8, phase ^ 1u);
+#endif
+      raw = sm + rs * kRawBytes;
+      a_hi = sm + stage * 2 * kTileBytes;
+    };
+    auto release = [&]() {
+#ifdef EG_TC_TIMING
+      const long long _tr = clock64();
+      fence_proxy_async_smem();
+      dbg_acc[2] += clock64() - _tr;
+#elif !defined(EG_DBG_NOFENCE)
+      fence_proxy_async_smem();
+#endif
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_a(sm + kOffFull + (chunk % kStages) * 8);
+        mbar_arrive_a(sm + kOffRawEmpty + (chunk % kRawStages) * 8);
+      }
+      ++chunk;
+    };
+    auto emit = [&](uint32_t a_hi, int i, const float4& acc) {  // 3xTF32 split -> operand tiles
+#ifdef EG_DBG_NOEMIT
+      if (acc.x == 123.456f) sts4(a_hi + soff[i], make_uint4(0, 0, 0, 0));
+      return;
+#endif
+      uint4 hi, lo;
+      split_tf32_op(acc.x, hi.x, lo.x);
+      split_tf32_op(acc.y, hi.y, lo.y);
+      split_tf32_op(acc.z, hi.z, lo.z);
+      split_tf32_op(acc.w, hi.w, lo.w);
+      sts4(a_hi + soff[i], hi);
+      sts4(a_hi + kTileBytes + soff[i], lo);
+    };
+
+    if (!GATHER) {
+      // linear mode: raw slot r = tile row r (rows past the end were not copied: zero them)
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < 4; ++kc) {
+          uint32_t raw, a_hi;
+          acquire(raw, a_hi);
+#pragma unroll
+          for (int i = 0; i < kIters; ++i) {
+            const int r = pw * kRowsPerProd + i * 4 + g;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((long long)tile * 128 + r < p.rows) acc = lds4(raw + lane_raw + r * 128);
+            emit(a_hi, i, acc);
+          }
+          release();
+        }
+      }
+    } else {
+      const bool agg_out = p.AggOut != nullptr;
+      uint32_t pbuf = 0;
+      prefetch_plan(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, pbuf ^= 1u) {
         const int b = tile / p.tiles_per_frame;
         const int t = tile - b * p.tiles_per_frame;
-        cp_async_wait_all();
+        const uint32_t prow = plan_u + pbuf * kPlanWarpBytes + g * sizeof(PlanRow);  // + i * 4 rows
+        const long long frow0 = (long long)b * p.nodes_per_frame;
+        const float* fbase = p.X + frow0 * 128;
+        const int32_t* tnode = p.tile_nodes + t * 128 + pw * kRowsPerProd + g;
+        auto store_agg = [&](int i, int coff, const float4& acc) {
+          const int node = __ldg(tnode + i * 4);
+          if (node >= 0) st4(p.AggOut + (frow0 + node) * 128 + coff, acc);
+        };
+        cp_async_wait_all();  // this tile's plan rows (prefetched one tile ahead)
         __syncwarp();
+        uint32_t raw, a_hi;
         const float4 hdr = lds4(plan_u + pbuf * kPlanWarpBytes + kRowsPerProd * sizeof(PlanRow));
-        ks = __float_as_int(hdr.y), nfar = __float_as_int(hdr.z), has_csr = __float_as_int(hdr.w);
-        frow0 = (long long)b * p.nodes_per_frame;
-        fbase = p.X + frow0 * 128;
-        tnode = p.tile_nodes + t * 128 + pw * kRowsPerProd + g;
+        const int ks = __float_as_int(hdr.y), nfar = __float_as_int(hdr.z), has_csr = __float_as_int(hdr.w);
+        if (ks <= 5 && !nfar && !has_csr) {
+          // ---- lattice tile (every main-level tile): <= 5 staged neighbours + the row itself, all in shared
+          // memory.  Slot byte offsets and weights sit in registers for the 4 chunks; the loop body is
+          // 6 LDS.128 + 12 FFMA2 + split + 2 STS.128 per row.
+          uint32_t so[kIters][6];
+          float wv[kIters][6];
+#pragma unroll
+          for (int i = 0; i < kIters; ++i) {
+            const float4 a = lds4(prow + i * 4 * sizeof(PlanRow));
+            const float4 wa = lds4(prow + i * 4 * sizeof(PlanRow) + 16);
+            const float4 wb = lds4(prow + i * 4 * sizeof(PlanRow) + 32);
+            const uint32_t s_lo = __float_as_uint(a.x), s_hi = __float_as_uint(a.y);
+            so[i][0] = (__byte_perm(s_lo, 0, 0x4440) << 7) + lane_raw;
+            so[i][1] = (__byte_perm(s_lo, 0, 0x4441) << 7) + lane_raw;
+            so[i][2] = (__byte_perm(s_lo, 0, 0x4442) << 7) + lane_raw;
+            so[i][3] = (__byte_perm(s_lo, 0, 0x4443) << 7) + lane_raw;
+            so[i][4] = (__byte_perm(s_hi, 0, 0x4440) << 7) + lane_raw;
+            so[i][5] = (__byte_perm(s_hi, 0, 0x4443) << 7) + lane_raw;  // the row itself
+            wv[i][0] = wa.x, wv[i][1] = wa.y, wv[i][2] = wa.z, wv[i][3] = wa.w, wv[i][4] = wb.x, wv[i][5] = wb.w;
+          }
+          prefetch_plan(tile + gridDim.x, pbuf ^ 1u);
+#pragma unroll 1
+          for (int kc = 0; kc < 4; ++kc) {
+            acquire(raw, a_hi);
+#ifdef EG_DBG_NOCOMPUTE
+            release();
+            continue;
+#endif
+            float4 x[kIters][6];
+#pragma unroll
+            for (int i = 0; i < kIters; ++i)
+#pragma unroll
+              for (int k = 0; k < 6; ++k) {
+#ifdef EG_DBG_NOGATHER
+                x[i][k] = k == 5 ? lds4(raw + so[i][k]) : make_float4(1.f, 2.f, 3.f, 4.f);
+#else
+                x[i][k] = lds4(raw + so[i][k]);
+#endif
+              }
+            float4 aggv[kIters];
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) {
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int k = 0; k < 6; ++k) fma4_x2(acc, wv[i][k], x[i][k]);  // plan order, self loop last
+              emit(a_hi, i, acc);
+              aggv[i] = acc;
+            }
+            release();
+            if (agg_out) {  // A_hat dH side output: stored after the chunk is handed to the MMA
+#pragma unroll
+              for (int i = 0; i < kIters; ++i) store_agg(i, kc * 32 + j * 4, aggv[i]);
+            }
+          }
+          continue;
+        }
+        if (ks <= 5 && !has_csr) {
+          // ---- aux lattice tile (128x128, 64x64 ... levels): as above plus the 2x2 children of every row, which
+          // are not staged (512 rows) and come from global / L2.  All 8 child loads of the chunk are issued before
+          // the barrier waits so that their latency overlaps the wait and the staged part; slots and weights are
+          // re-read from the plan rows in shared memory (broadcast LDS) to leave the registers to the loads.
+          prefetch_plan(tile + gridDim.x, pbuf ^ 1u);
+#pragma unroll 1
+          for (int kc = 0; kc < 4; ++kc) {
+            const int coff = kc * 32 + j * 4;
+            float4 fx[kIters][4];
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) {
+              const float4 fn = lds4(prow + i * 4 * sizeof(PlanRow) + 48);
+              fx[i][0] = ldg4(fbase + (long long)__float_as_int(fn.x) * 128 + coff);
+              fx[i][1] = ldg4(fbase + (long long)__float_as_int(fn.y) * 128 + coff);
+              fx[i][2] = ldg4(fbase + (long long)__float_as_int(fn.z) * 128 + coff);
+              fx[i][3] = ldg4(fbase + (long long)__float_as_int(fn.w) * 128 + coff);
+            }
+            acquire(raw, a_hi);
+            const uint32_t rawl = raw + lane_raw;
+            float4 aggv[kIters];
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) {
+              const float4 a = lds4(prow + i * 4 * sizeof(PlanRow));
+              const float4 wa = lds4(prow + i * 4 * sizeof(PlanRow) + 16);
+              const float4 wb = lds4(prow + i * 4 * sizeof(PlanRow) + 32);
+              const float4 fw = lds4(prow + i * 4 * sizeof(PlanRow) + 64);
+              const uint32_t s_lo = __float_as_uint(a.x), s_hi = __float_as_uint(a.y);
+              const float4 x0 = lds4(rawl + (__byte_perm(s_lo, 0, 0x4440) << 7));
+              const float4 x1 = lds4(rawl + (__byte_perm(s_lo, 0, 0x4441) << 7));
+              const float4 x2 = lds4(rawl + (__byte_perm(s_lo, 0, 0x4442) << 7));
+              const float4 x3 = lds4(rawl + (__byte_perm(s_lo, 0, 0x4443) << 7));
+              const float4 x4 = lds4(rawl + (__byte_perm(s_hi, 0, 0x4440) << 7));
+              const float4 xs = lds4(rawl + (__byte_perm(s_hi, 0, 0x4443) << 7));  // the row itself
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              fma4_x2(acc, wa.x, x0);
+              fma4_x2(acc, wa.y, x1);
+              fma4_x2(acc, wa.z, x2);
+              fma4_x2(acc, wa.w, x3);
+              fma4_x2(acc, wb.x, x4);
+              fma4_x2(acc, fw.x, fx[i][0]);
+              fma4_x2(acc, fw.y, fx[i][1]);
+              fma4_x2(acc, fw.z, fx[i][2]);
+              fma4_x2(acc, fw.w, fx[i][3]);
+              fma4_x2(acc, wb.w, xs);  // self loop last
+              emit(a_hi, i, acc);
+              aggv[i] = acc;
+            }
+            release();
+            if (agg_out) {
+#pragma unroll
+              for (int i = 0; i < kIters; ++i) store_agg(i, coff, aggv[i]);
+            }
+          }
+          continue;
+        }
+        // ---- general tile: up to 7 staged neighbours, 4 far neighbours read from global, CSR rows (hubs)
+        uint2 slots[kIters];
+        float4 w0[kIters], w1[kIters];
 #pragma unroll
         for (int i = 0; i < kIters; ++i) {
           const float4 a = lds4(prow + i * 4 * sizeof(PlanRow));
@@ -262,57 +460,42 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
           w1[i] = lds4(prow + i * 4 * sizeof(PlanRow) + 32);
         }
         prefetch_plan(tile + gridDim.x, pbuf ^ 1u);
-      }
-      for (int kc = 0; kc < 4; ++kc, ++chunk) {
-        const uint32_t stage = chunk % kStages, phase = (chunk / kStages) & 1u;
-        const uint32_t rs = chunk % kRawStages, rphase = (chunk / kRawStages) & 1u;
-        const int coff = kc * 32 + j * 4;
-        float4 fx[4];
-        if (GATHER && nfar) {  // far rows of the first row group: in flight across the barrier waits
-          const float4 fn = lds4(prow + 48);
-          fx[0] = ldg4(fbase + (long long)__float_as_int(fn.x) * 128 + coff);
-          fx[1] = ldg4(fbase + (long long)__float_as_int(fn.y) * 128 + coff);
-          fx[2] = ldg4(fbase + (long long)__float_as_int(fn.z) * 128 + coff);
-          fx[3] = ldg4(fbase + (long long)__float_as_int(fn.w) * 128 + coff);
-        }
-#ifdef EG_TC_TIMING
-        {
-          const long long _t = clock64();
-          mbar_wait_a(bar_raw_full + rs * 8, rphase);
-          dbg_acc[1] += clock64() - _t;
-          const long long _t2 = clock64();
-          mbar_wait_a(bar_empty + stage * 8, phase ^ 1u);
-          dbg_acc[0] += clock64() - _t2;
-        }
-#else
-        mbar_wait_a(bar_raw_full + rs * 8, rphase);
-        mbar_wait_a(bar_empty + stage * 8, phase ^ 1u);
-#endif
-        const uint32_t a_hi = sA_u + stage * 2 * kTileBytes, a_lo = a_hi + kTileBytes;
-        const uint32_t raw = sRaw_u + rs * kRawBytes;
+#pragma unroll 1
+        for (int kc = 0; kc < 4; ++kc) {
+          const int coff = kc * 32 + j * 4;
+          float4 fx[4];
+          if (nfar) {  // far rows of the first row group: in flight across the barrier waits
+            const float4 fn = lds4(prow + 48);
+            fx[0] = ldg4(fbase + (long long)__float_as_int(fn.x) * 128 + coff);
+            fx[1] = ldg4(fbase + (long long)__float_as_int(fn.y) * 128 + coff);
+            fx[2] = ldg4(fbase + (long long)__float_as_int(fn.z) * 128 + coff);
+            fx[3] = ldg4(fbase + (long long)__float_as_int(fn.w) * 128 + coff);
+          }
+          acquire(raw, a_hi);
+          const uint32_t rawl = raw + lane_raw;
+          float4 aggv[kIters];
 #pragma unroll
-        for (int i = 0; i < kIters; ++i) {
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (GATHER) {
+          for (int i = 0; i < kIters; ++i) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             uint32_t s_lo = slots[i].x, s_hi = slots[i].y;
             asm volatile("" : "+r"(s_lo), "+r"(s_hi));  // keep the slot -> address arithmetic inside the chunk loop
             // staged neighbours 0..4 (+ 5, 6 on tiles that have them): loads first, then the sums in plan
             // order (unused entries of a row point at slot 0 with weight 0)
-            float4 x0 = lds4(raw + (__byte_perm(s_lo, 0, 0x4440) << 7));
-            float4 x1 = lds4(raw + (__byte_perm(s_lo, 0, 0x4441) << 7));
-            float4 x2 = lds4(raw + (__byte_perm(s_lo, 0, 0x4442) << 7));
-            float4 x3 = lds4(raw + (__byte_perm(s_lo, 0, 0x4443) << 7));
-            float4 x4 = lds4(raw + (__byte_perm(s_hi, 0, 0x4440) << 7));
+            float4 x0 = lds4(rawl + (__byte_perm(s_lo, 0, 0x4440) << 7));
+            float4 x1 = lds4(rawl + (__byte_perm(s_lo, 0, 0x4441) << 7));
+            float4 x2 = lds4(rawl + (__byte_perm(s_lo, 0, 0x4442) << 7));
+            float4 x3 = lds4(rawl + (__byte_perm(s_lo, 0, 0x4443) << 7));
+            float4 x4 = lds4(rawl + (__byte_perm(s_hi, 0, 0x4440) << 7));
             fma4(acc, w0[i].x, x0);
             fma4(acc, w0[i].y, x1);
             if (ks > 5) {
-              x0 = lds4(raw + (__byte_perm(s_hi, 0, 0x4441) << 7));
-              x1 = lds4(raw + (__byte_perm(s_hi, 0, 0x4442) << 7));
+              x0 = lds4(rawl + (__byte_perm(s_hi, 0, 0x4441) << 7));
+              x1 = lds4(rawl + (__byte_perm(s_hi, 0, 0x4442) << 7));
             }
             fma4(acc, w0[i].z, x2);
             fma4(acc, w0[i].w, x3);
             fma4(acc, w1[i].x, x4);
-            x2 = lds4(raw + (__byte_perm(s_hi, 0, 0x4443) << 7));  // the row itself
+            x2 = lds4(rawl + (__byte_perm(s_hi, 0, 0x4443) << 7));  // the row itself
             if (ks > 5) {
               fma4(acc, w1[i].y, x0);
               fma4(acc, w1[i].z, x1);
@@ -338,28 +521,14 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
               for (int e = cbeg; e < cbeg + cdeg; ++e)
                 fma4(acc, __ldg(p.w + e), ldg4(fbase + (long long)__ldg(p.col + e) * 128 + coff));
             }
-            if (agg_out) {
-              const int node = __ldg(tnode + i * 4);
-              if (node >= 0) st4(p.AggOut + (frow0 + node) * 128 + coff, acc);
-            }
-          } else {
-            // linear mode: raw slot r = tile row r (rows past the end were not copied: zero them)
-            const int r = pw * kRowsPerProd + i * 4 + g;
-            if ((long long)tile * 128 + r < p.rows) acc = lds4(raw + r * 128);
+            emit(a_hi, i, acc);
+            aggv[i] = acc;
           }
-          uint4 hi, lo;
-          split_tf32_fast(acc.x, hi.x, lo.x);
-          split_tf32_fast(acc.y, hi.y, lo.y);
-          split_tf32_fast(acc.z, hi.z, lo.z);
-          split_tf32_fast(acc.w, hi.w, lo.w);
-          sts4(a_hi + soff[i], hi);
-          sts4(a_lo + soff[i], lo);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive_a(bar_full + stage * 8);
-          mbar_arrive_a(bar_raw_empty + rs * 8);
+          release();
+          if (agg_out) {
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) store_agg(i, coff, aggv[i]);
+          }
         }
       }
     }
@@ -368,7 +537,6 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
     constexpr int kPer = kRawRows / (kLoadWarps * 4);  // source rows per thread (8 lanes x 16 B per row)
     const int q = (warp - kLoadWarp0) * 32 + lane;
     const int sl = q >> 3, j = q & 7;
-    const uint32_t sm = smem_u32(smem);
     const uint32_t bar_raw_full = sm + kOffRawFull, bar_raw_empty = sm + kOffRawEmpty;
     const uint32_t dst0 = sm + kOffRaw + sl * 128 + j * 16;
     // frame-local node staged in slot sl + (kLoadWarps*4) * m (-1 = none), fetched one tile ahead
@@ -409,8 +577,13 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
         const uint32_t dst = dst0 + rs * kRawBytes;
         const float* srcb = p.X + kc * 32 + j * 4;
 #pragma unroll
-        for (int m = 0; m < kPer; ++m)
+        for (int m = 0; m < kPer; ++m) {
+#ifdef EG_DBG_NOLOAD
+          if (srow[m] >= 0 && m == 0) cp_async16(dst + kLoadWarps * 4 * m * 128, srcb + (long long)srow[m] * 128);
+#else
           if (srow[m] >= 0) cp_async16(dst + kLoadWarps * 4 * m * 128, srcb + (long long)srow[m] * 128);
+#endif
+        }
         cp_async_mbar_arrive_a(bar_raw_full + rs * 8);
       }
     }
@@ -445,7 +618,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp < kEpiWarps) {
     // ===== epilogue: thread <-> output feature; TMEM -> registers -> 128-byte row segments ===================
     // A 16-column slab of the accumulator = one 16-row group of the tile = consecutive rows of Out
     // (tile table contract), so a slab is addressed as one base pointer + immediate offsets.
@@ -470,44 +643,81 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
         gbase = r0 < p.rows ? r0 : -1;
         gcnt = (int)max(0LL, min(16LL, p.rows - r0));
       }
+      if (p.addend && tile + (int)gridDim.x < p.num_tiles) {
+        // residual rows of this CTA's NEXT tile -> L2 now, so that the slab loop below reads them at L2 latency
+        // one tile from now (exposed DRAM latency per slab made the epilogue the bottleneck of the backward)
+        const int ntile = tile + gridDim.x;
+        long long nbase = -1;
+        int ncnt = 0;
+        if (GATHER) {
+          const int nb = ntile / p.tiles_per_frame;
+          const int v = lane < 16 ? __ldg(p.tile_groups + (ntile - nb * p.tiles_per_frame) * 16 + lane) : 0;
+          ncnt = v;
+          nbase = (lane < 8 && v >= 0) ? (long long)nb * p.nodes_per_frame + v : -1;
+        } else {
+          const long long r0 = (long long)ntile * 128 + (lane & 7) * 16;
+          nbase = r0 < p.rows ? r0 : -1;
+          ncnt = (int)max(0LL, min(16LL, p.rows - r0));
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {  // 8 groups x 64 lines of 128 B, 4 lines per epilogue thread
+          const int line = f + 128 * m, grp = line >> 6, lo = line & 63;
+          const long long base = __shfl_sync(0xffffffffu, nbase, grp);
+          const int cnt = __shfl_sync(0xffffffffu, ncnt, GATHER ? 8 + grp : grp);
+          if (base >= 0 && lo < cnt * 4) prefetch_l2(p.addend + base * 128 + lo * 32);
+        }
+      }
       TC_TIMED_WAIT(0, &acc_full[buf], acc_phase);
       tc_fence_after();
 #pragma unroll 1
+#ifdef EG_DBG_NOEPI
+      for (int sl = 0; sl < 0; ++sl) {
+#else
       for (int sl = 0; sl < 8; ++sl) {  // 16 tile rows (accumulator columns) at a time
+#endif
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + kTmemAcc + buf * 128 + sl * 16, v);
         const long long base = __shfl_sync(0xffffffffu, gbase, sl);
         const int cnt = __shfl_sync(0xffffffffu, gcnt, GATHER ? 8 + sl : sl);
         float* out = p.Out + max(base, 0LL) * 128 + f;
-        float ad[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) ad[i] = 0.f;
-        if (p.addend) {  // all residual loads in flight before the accumulator is consumed
+        float s = 0.f, q = 0.f;
+        if (p.addend) {  // backward: + residual gradient; all 16 loads in flight before the accumulator is consumed
+          float ad[16];
           const float* adp = p.addend + max(base, 0LL) * 128 + f;
 #pragma unroll
+          for (int i = 0; i < 16; ++i) ad[i] = i < cnt ? __ldg(adp + i * 128) : 0.f;
+          tmem_ld_wait();
+#pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (i < cnt) ad[i] = __ldg(adp + i * 128);
-        }
-        tmem_ld_wait();
-        float s = 0.f, q = 0.f;
-        if (cnt == 16) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float o = __uint_as_float(v[i]) + bias + ad[i];
-#ifndef EG_DBG_NOSTORE
-            out[i * 128] = o;
-#endif
-            s += o;
-            q = fmaf(o, o, q);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float o = __uint_as_float(v[i]) + bias + ad[i];
-            if (i < cnt) {  // warp-uniform
+            if (i < cnt) {  // warp-uniform predicate
+              const float o = __uint_as_float(v[i]) + bias + ad[i];
               out[i * 128] = o;
+              if (p.stat_parts) {  // (no caller asks for both today; kept for the ABI)
+                s += o;
+                q = fmaf(o, o, q);
+              }
+            }
+        } else {
+          tmem_ld_wait();
+          if (cnt == 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float o = __uint_as_float(v[i]) + bias;
+#ifndef EG_DBG_NOSTORE
+              out[i * 128] = o;
+#endif
               s += o;
               q = fmaf(o, o, q);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float o = __uint_as_float(v[i]) + bias;
+              if (i < cnt) {  // warp-uniform
+                out[i * 128] = o;
+                s += o;
+                q = fmaf(o, o, q);
+              }
             }
           }
         }
@@ -527,7 +737,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
 #ifdef EG_TC_TIMING
   if (lane == 0) {
     long long* d = g_tc_dbg[blockIdx.x];
-    if (warp == kProdWarp0) { d[0] = dbg_acc[0]; d[5] = dbg_acc[1]; } // compute warp 0: wait operand stage, wait raw
+    if (warp == kProdWarp0) { d[0] = dbg_acc[0]; d[5] = dbg_acc[1]; d[7] = dbg_acc[2]; } // compute warp 0: wait operand stage, wait raw, fence
     if (warp == kLoadWarp0) d[6] = dbg_acc[0];                       // loader: wait for a free raw stage
     if (warp == kMmaWarp) { d[1] = dbg_acc[0]; d[2] = dbg_acc[1]; } // MMA: wait acc_empty, wait full
     if (warp == 0) { d[3] = dbg_acc[0]; d[4] = clock64() - dbg_t0; } // epilogue: wait acc_full; total cycles
@@ -602,7 +812,7 @@ int launch_gcn_tc(const eg_graph* g, int batch, const float* X, const float* W, 
   p.addend = addend;
   p.Out = Out;
   p.AggOut = AggOut;
-  return launch<true>(p, mean, var, ws, ws_bytes, "gcn_tc", s);
+  return launch<true>(p, mean, var, ws, ws_bytes, AggOut ? "gcn_tc_bwd" : "gcn_tc_fwd", s);
 }
 
 // C = A op(W) + bias + addend (C may alias A: a tile is read completely before its epilogue writes it).

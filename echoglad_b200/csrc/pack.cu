@@ -96,8 +96,6 @@ extern "C" {
 int eg_pack_nodes(const eg_graph* g, int batch, const float* const* maps, const float* head, const float* tail,
                   float* X, void* stream) {
   EG_CHECK_ARG(g && maps && X && batch >= 1, "eg_pack_nodes: bad arguments");
-  const eg_graph_info& info = graph_info(g);
-  for (int l = 0; l < info.num_levels; ++l) EG_CHECK_ARG(maps[l], "eg_pack_nodes: maps[%d] is NULL", l);
   return run(g, batch, const_cast<float* const*>(reinterpret_cast<const float* const*>(maps)),
              const_cast<float*>(head), const_cast<float*>(tail), X, 1, as_stream(stream));
 }

@@ -33,13 +33,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded spin: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 1.9 GHz
-  }
-}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }
 
 // Same on a precomputed 32-bit shared-space address (saves the generic -> shared conversion in hot loops).
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
@@ -56,11 +51,28 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the waiting thread sleeps inside the instruction (up to ~kSuspendNs) instead
+// of spinning through the issue slots the working warps need.
+#ifndef EG_SUSPEND_NS
+#define EG_SUSPEND_NS 20000
+#endif
+constexpr uint32_t kSuspendNs = EG_SUSPEND_NS;
+__device__ __forceinline__ bool mbar_try_wait_hint_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(kSuspendNs)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait_a(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_a(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint_a(bar, parity)) {
+    if (++spins > (1u << 22)) __trap();  // seconds: a protocol bug, never a legitimate wait
   }
 }
 
@@ -76,6 +88,9 @@ __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void cp_async_mbar_arrive_a(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>  // at most N of this thread's most recent groups may still be pending
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // waits for ALL earlier cp.async of this thread, committed to a group or not
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -195,6 +210,18 @@ __device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t&
   hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   const float r = x - __uint_as_float(hi);
   lo = (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
+}
+
+// Operand split used by the tensor-core kernels.  The tensor core reads the upper 19 bits of a 32-bit tf32
+// operand; with -DEG_TF32_TRUNC the hi part is the unmodified fp32 value (the hardware drops the low 13 bits)
+// and lo = x - trunc(x), 2 instructions per element instead of 5 (error <= 2^-21 |x| instead of 2^-22 |x|).
+__device__ __forceinline__ void split_tf32_op(float x, uint32_t& hi, uint32_t& lo) {
+#ifdef EG_TF32_TRUNC
+  hi = __float_as_uint(x);
+  lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u));
+#else
+  split_tf32_fast(x, hi, lo);
+#endif
 }
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }

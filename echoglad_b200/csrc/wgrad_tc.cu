@@ -13,12 +13,15 @@
 // 32 features x 4 row groups of 4 rows), no transpose anywhere.  3xTF32: split warps rewrite the raw block in place as its tf32 hi part
 // and write the lo part to a second ring; one elected thread issues, per 8-row group,
 //     D += G_lo^T X_hi,  D += G_hi^T X_lo,  D += G_hi^T X_hi        (tcgen05.mma kind::tf32, M = N = 128, K = 8)
-// into ONE 128-column TMEM accumulator that lives for the whole kernel.  Each CTA drains its accumulator once
-// at the end ([148][128][128] partials) and a fixed-order second stage sums the partials in double: no atomics,
-// bit-reproducible.
+// into a 128-column TMEM accumulator.  The tensor core does not round its fp32 accumulation to nearest, so a
+// long accumulation chain drifts (measured: 2 x 288,084 rows in ONE chain per CTA missed the 1e-5 bound against
+// fp64 by 1.5x); the accumulation therefore runs in SEGMENTS of kSegBlocks blocks that alternate between two
+// TMEM accumulators, and four epilogue warps drain each finished segment into the CTA's fp32 partial in global
+// memory (L2-resident, round-to-nearest adds, fixed order) while the next segment accumulates.  A fixed-order
+// second stage sums the [148][128][128] partials in double: no atomics, bit-reproducible.
 //
 // Rings: RAW/hi ring of kRaw blocks (16 KB: G and X) deep enough to cover the HBM latency, LO ring of kLo blocks.
-// Warps: 0-3 loaders (and the final epilogue: TMEM lane quadrant = warp id), 4 MMA issuer, 5-12 split.
+// Warps: 0-3 loaders, 4 MMA issuer, 5-12 split, 13-16 epilogue (TMEM lane quadrant = warp id % 4).
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -30,15 +33,17 @@ namespace {
 constexpr int kRows = 16;                      // rows per block (2 MMA k-steps of 8)
 constexpr int kRaw = 9;                        // raw / hi ring depth
 constexpr int kLo = 4;                         // lo ring depth
-constexpr int kLoadWarps = 4, kSplitWarps = 8;
+constexpr int kSegBlocks = 128;                // blocks (2048 rows, 768 MMAs) per accumulation segment
+constexpr int kLoadWarps = 4, kSplitWarps = 8, kEpiWarps = 4;
 constexpr int kMmaWarp = kLoadWarps;
 constexpr int kSplitWarp0 = kMmaWarp + 1;
-constexpr int kThreads = (kLoadWarps + 1 + kSplitWarps) * 32;
+constexpr int kEpiWarp0 = kSplitWarp0 + kSplitWarps;
+constexpr int kThreads = (kLoadWarps + 1 + kSplitWarps + kEpiWarps) * 32;
 constexpr uint32_t kOpBytes = kRows * 512;     // one operand (G or X) of a block: 8 KB
 constexpr uint32_t kBlockBytes = 2 * kOpBytes; // G + X
 constexpr uint32_t kOffLo = kRaw * kBlockBytes;
 constexpr uint32_t kOffBars = kOffLo + kLo * kBlockBytes;
-constexpr uint32_t kSmemBytes = kOffBars + 8 * (2 * kRaw + 2 * kLo + 1) + 16 + 1024;
+constexpr uint32_t kSmemBytes = kOffBars + 8 * (2 * kRaw + 2 * kLo + 4) + 16 + 1024;
 constexpr uint32_t kLbo = (kRows / 4) * 512;   // byte stride between the 32-feature atoms of an operand
 constexpr uint32_t kSbo = 512;                 // byte stride between 4-row groups
 static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -77,9 +82,11 @@ wgrad_tc_kernel(long long rows, const float* __restrict__ G, const float* __rest
   const uint32_t sm = smem_u32(smem);
   const uint32_t bar_raw_full = sm + kOffBars, bar_raw_empty = bar_raw_full + 8 * kRaw,
                  bar_lo_full = bar_raw_empty + 8 * kRaw, bar_lo_empty = bar_lo_full + 8 * kLo,
-                 bar_acc = bar_lo_empty + 8 * kLo;
+                 bar_acc_full = bar_lo_empty + 8 * kLo, bar_acc_empty = bar_acc_full + 16;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRaw + 2 * kLo + 1);
+  uint64_t* acc_full = bars + 2 * kRaw + 2 * kLo;  // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;              // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long nblocks = (rows + kRows - 1) / kRows;
 
@@ -92,10 +99,13 @@ wgrad_tc_kernel(long long rows, const float* __restrict__ G, const float* __rest
       mbar_init(bars + 2 * kRaw + s, kSplitWarps);  // lo_full
       mbar_init(bars + 2 * kRaw + kLo + s, 1);      // lo_empty: tcgen05.commit
     }
-    mbar_init(bars + 2 * kRaw + 2 * kLo, 1);        // accumulator complete
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full + b, 1);
+      mbar_init(acc_empty + b, kEpiWarps);
+    }
     mbar_init_fence();
   }
-  if (warp == 0) tmem_alloc<128>(tmem_slot);
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -120,20 +130,6 @@ wgrad_tc_kernel(long long rows, const float* __restrict__ G, const float* __rest
       }
       cp_async_mbar_arrive_a(bar_raw_full + rs * 8);
     }
-    // ===== epilogue: the CTA's partial dW, thread <-> output feature o = TMEM lane ==============================
-    mbar_wait_a(bar_acc, 0);
-    tc_fence_after();
-    const int o = warp * 32 + lane;
-    float* P = parts + (size_t)blockIdx.x * 128 * 128 + (size_t)o * 128;
-#pragma unroll 1
-    for (int sl = 0; sl < 4; ++sl) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + sl * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<uint4*>(P + sl * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    }
   } else if (warp == kMmaWarp) {
     // ===== MMA issuer ==========================================================================================
     constexpr uint32_t idesc = umma_idesc_tf32(128, 128, 1, 1);  // both operands MN-major
@@ -141,26 +137,65 @@ wgrad_tc_kernel(long long rows, const float* __restrict__ G, const float* __rest
     for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
       const uint32_t rs = it % kRaw;
       const uint32_t ls = it % kLo, lphase = (it / kLo) & 1u;
+      const uint32_t seg = it / kSegBlocks, sb = it % kSegBlocks, buf = seg & 1u;
+      if (sb == 0) {  // new segment: its accumulator must have been drained (segment seg - 2)
+        mbar_wait_a(bar_acc_empty + buf * 8, ((seg >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+      }
       mbar_wait_a(bar_lo_full + ls * 8, lphase);  // the split warps wrote hi (in place) and lo of this block
       tc_fence_after();
       if (lane == 0) {
+        const uint32_t d = tmem_base + buf * 128;
         const uint32_t g_hi = sm + rs * kBlockBytes, x_hi = g_hi + kOpBytes;
         const uint32_t g_lo = sm + kOffLo + ls * kBlockBytes, x_lo = g_lo + kOpBytes;
 #pragma unroll
         for (int kg = 0; kg < kRows / 8; ++kg) {
           const uint32_t o = kg * 1024;
-          umma_tf32(tmem_base, umma_desc_mn128_b32(g_lo + o, kLbo, kSbo), umma_desc_mn128_b32(x_hi + o, kLbo, kSbo), idesc,
-                    (it | (uint32_t)kg) != 0);
-          umma_tf32(tmem_base, umma_desc_mn128_b32(g_hi + o, kLbo, kSbo), umma_desc_mn128_b32(x_lo + o, kLbo, kSbo), idesc, 1u);
-          umma_tf32(tmem_base, umma_desc_mn128_b32(g_hi + o, kLbo, kSbo), umma_desc_mn128_b32(x_hi + o, kLbo, kSbo), idesc, 1u);
+          umma_tf32(d, umma_desc_mn128_b32(g_lo + o, kLbo, kSbo), umma_desc_mn128_b32(x_hi + o, kLbo, kSbo), idesc,
+                    (sb | (uint32_t)kg) != 0);
+          umma_tf32(d, umma_desc_mn128_b32(g_hi + o, kLbo, kSbo), umma_desc_mn128_b32(x_lo + o, kLbo, kSbo), idesc, 1u);
+          umma_tf32(d, umma_desc_mn128_b32(g_hi + o, kLbo, kSbo), umma_desc_mn128_b32(x_hi + o, kLbo, kSbo), idesc, 1u);
         }
         umma_commit(bars + kRaw + rs);            // raw_empty
         umma_commit(bars + 2 * kRaw + kLo + ls);  // lo_empty
+        if (sb == kSegBlocks - 1 || blk + gridDim.x >= nblocks) umma_commit(acc_full + buf);  // segment complete
       }
       __syncwarp();
     }
-    if (lane == 0) umma_commit(bars + 2 * kRaw + 2 * kLo);
-    __syncwarp();
+  } else if (warp >= kEpiWarp0) {
+    // ===== epilogue: finished segments -> the CTA's partial dW (fp32, round-to-nearest adds, fixed order) =========
+    // thread <-> output feature o = TMEM lane; P[o][0..127] is this thread's 512 bytes of the partial
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int o = q * 32 + lane;
+    float* P = parts + (size_t)blockIdx.x * 128 * 128 + (size_t)o * 128;
+    const long long my_blocks = (nblocks - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const uint32_t nseg = (uint32_t)((my_blocks + kSegBlocks - 1) / kSegBlocks);
+    for (uint32_t seg = 0; seg < nseg; ++seg) {
+      const uint32_t buf = seg & 1u;
+      mbar_wait_a(bar_acc_full + buf * 8, (seg >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sl = 0; sl < 4; ++sl) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + sl * 32, v);
+        float4 old[8];
+        if (seg) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) old[c] = *reinterpret_cast<const float4*>(P + sl * 32 + c * 4);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 r = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                                 __uint_as_float(v[4 * c + 3]));
+          if (seg) r.x += old[c].x, r.y += old[c].y, r.z += old[c].z, r.w += old[c].w;
+          *reinterpret_cast<float4*>(P + sl * 32 + c * 4) = r;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(bar_acc_empty + buf * 8);
+    }
   } else {
     // ===== split warps: raw -> tf32 hi (in place) + lo; column sums of G ========================================
     const int t = tid - kSplitWarp0 * 32;
@@ -204,7 +239,7 @@ wgrad_tc_kernel(long long rows, const float* __restrict__ G, const float* __rest
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<256>(tmem_base);
   }
 }
 

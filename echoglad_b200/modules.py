@@ -321,8 +321,10 @@ class UNETHierarchicalPatchModel(HierarchicalPatchModel):
         self.up_convs = nn.ModuleList(_UpConv(f, f // 2, up_sizes[i]) for i, f in enumerate(reversed(dims)))
         feats_in = list(reversed(dims)) + [dims[0] // 2]
         self.linears = nn.ModuleList(nn.Conv2d(c, self.node_embedding_dim, kernel_size=1) for c in feats_in)
+        self.fuse_level_embed = True  # False: PyTorch conv1x1 + ReLU + eg_pack_nodes for every level (A/B, tests)
 
-    def pyramid(self, x: torch.Tensor) -> List[torch.Tensor]:
+    def decoder_features(self, x: torch.Tensor):
+        """UNet encoder / decoder (PyTorch): decoder maps of all 8 scales and the indices the graph uses."""
         skips = []
         for down in self.down_convs:
             skips.append(x)
@@ -332,8 +334,28 @@ class UNETHierarchicalPatchModel(HierarchicalPatchModel):
             x = up(x, skips.pop())
             feats.append(x)
         naux = 0 if self.use_main_graph_only else self.num_aux_graphs
-        used = list(range(naux)) + [len(feats) - 1]
+        return feats, list(range(naux)) + [len(feats) - 1]
+
+    def pyramid(self, x: torch.Tensor) -> List[torch.Tensor]:
+        feats, used = self.decoder_features(x)
         return [TF.relu(self.linears[i](feats[i])) for i in used]
+
+    def create_node_pixels(self, x: torch.Tensor, graph: DeviceGraph) -> torch.Tensor:
+        """Fused route (default.yml: no connection / coordinate nodes): the narrow decoder maps of the big levels
+        go straight into eg_level_embed (1x1 conv + ReLU + packing in one pass)."""
+        meta = graph.meta
+        if meta.first_pixel_node or meta.num_coord_nodes or not self.fuse_level_embed:
+            return super().create_node_pixels(x, graph)
+        feats, used = self.decoder_features(x)
+        fused, args = [], []
+        for l, i in enumerate(used):
+            lin, f = self.linears[i], feats[i]
+            if ops.lib.eg_level_embed_supported(graph.handle, l, f.shape[1]):
+                fused.append(l)
+                args += [f, lin.weight, lin.bias]
+            else:
+                args += [TF.relu(lin(f)), None, None]
+        return ops.EmbedPackNodes.apply(graph, tuple(fused), *args)
 
     def connection_rows(self, maps: List[torch.Tensor]) -> torch.Tensor:
         """One connection node per used level = its spatial mean (src/core/models.py:735-752)."""

@@ -168,6 +168,80 @@ class PackNodes(torch.autograd.Function):
         return (None, d_head if need[1] else None, d_tail if need[2] else None, *d_maps)
 
 
+class EmbedPackNodes(torch.autograd.Function):
+    """Node features of the UNet variant: per lattice level `relu(conv1x1(feature map))` packed node-major
+    (reference src/core/models.py:708-710,722-756).  Levels whose raw map is narrow (cin 4 / 8: the main grid
+    and the 128x128 level, 92 % of the nodes) run the fused eg_level_embed kernels straight from the raw UNet
+    map; the remaining (tiny) levels arrive already embedded and go through eg_pack_nodes.
+
+    args: graph, fused_levels (tuple of level indices), then for every level l either
+          (raw_map [B,cin,s,s], weight [128,cin,1,1], bias [128]) if l is fused, or (map [B,128,s,s], None, None)."""
+
+    @staticmethod
+    def forward(ctx, graph: DeviceGraph, fused_levels, *args):
+        meta = graph.meta
+        if len(args) != 3 * meta.num_levels:
+            raise EchogladError(f"expected {3 * meta.num_levels} tensors, got {len(args)}")
+        fused = set(fused_levels)
+        maps = [_f32(args[3 * l], "map") for l in range(meta.num_levels)]
+        batch = maps[0].shape[0]
+        dev = maps[0].device
+        x = torch.empty(batch * meta.num_nodes, F, device=dev)
+        st = _stream(x)
+        plain = []
+        for l, s_l in enumerate(meta.level_size):
+            if l in fused:
+                plain.append(None)
+                continue
+            if tuple(maps[l].shape) != (batch, F, s_l, s_l):
+                raise EchogladError(f"level {l} map has shape {tuple(maps[l].shape)}, expected {(batch, F, s_l, s_l)}")
+            plain.append(maps[l])
+        arr = (C.c_void_p * len(plain))(*[_ptr(m) for m in plain])
+        check(lib.eg_pack_nodes(graph.handle, batch, arr, None, None, x.data_ptr(), st), "eg_pack_nodes")
+        saved = []
+        for l in sorted(fused):
+            w, b = _f32(args[3 * l + 1], "weight"), _f32(args[3 * l + 2], "bias")
+            cin = maps[l].shape[1]
+            if tuple(maps[l].shape) != (batch, cin, meta.level_size[l], meta.level_size[l]) or w.numel() != F * cin:
+                raise EchogladError(f"level {l}: raw map {tuple(maps[l].shape)} / weight {tuple(w.shape)} mismatch")
+            check(lib.eg_level_embed_fwd(graph.handle, batch, l, cin, maps[l].data_ptr(), w.data_ptr(), b.data_ptr(),
+                                         x.data_ptr(), st), "eg_level_embed_fwd")
+            saved += [maps[l], w, b]
+        ctx.save_for_backward(*saved)
+        ctx.graph, ctx.batch, ctx.fused = graph, batch, sorted(fused)
+        ctx.shapes = [m.shape for m in maps]
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        dx = _f32(dx, "dx")
+        meta = ctx.graph.meta
+        need = ctx.needs_input_grad
+        st = _stream(dx)
+        grads = [None] * (3 * meta.num_levels)
+        d_plain = []
+        for l in range(meta.num_levels):
+            if l in ctx.fused or not need[2 + 3 * l]:
+                d_plain.append(None)
+            else:
+                grads[3 * l] = torch.empty(ctx.shapes[l], device=dx.device)
+                d_plain.append(grads[3 * l])
+        arr = (C.c_void_p * len(d_plain))(*[_ptr(m) for m in d_plain])
+        check(lib.eg_pack_nodes_grad(ctx.graph.handle, ctx.batch, dx.data_ptr(), arr, None, None, st),
+              "eg_pack_nodes_grad")
+        ws = _ws(dx.device)
+        for k, l in enumerate(ctx.fused):
+            raw, w, b = ctx.saved_tensors[3 * k:3 * k + 3]
+            cin = raw.shape[1]
+            d_raw = torch.empty_like(raw) if need[2 + 3 * l] else None
+            dw, db = torch.empty_like(w), torch.empty_like(b)
+            check(lib.eg_level_embed_bwd(ctx.graph.handle, ctx.batch, l, cin, raw.data_ptr(), w.data_ptr(),
+                                         b.data_ptr(), dx.data_ptr(), _ptr(d_raw), dw.data_ptr(), db.data_ptr(),
+                                         ws.data_ptr(), WORKSPACE_BYTES, st), "eg_level_embed_bwd")
+            grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = d_raw, dw, db
+        return (None, None, *grads)
+
+
 class Aggregate(torch.autograd.Function):
     """y = A_hat x (A_hat symmetric => backward is the same kernel)."""
 

@@ -102,12 +102,28 @@ int eg_graph_check_edge_index(const eg_graph* g, int batch, const int64_t* edge_
 /* ---- node-feature packing: replaces the per-frame permute/reshape/cat loop --------------------------
  * (src/core/models.py:722-756).  maps[l] = DEVICE float[batch, F, s_l, s_l] (NCHW) for lattice level l;
  * `maps` itself is a HOST array of num_levels pointers.  head = float[batch, first_pixel_node, F]
- * (connection-node rows) or NULL; tail = float[batch, num_coord_nodes, F] or NULL.
+ * (connection-node rows) or NULL; tail = float[batch, num_coord_nodes, F] or NULL.  A NULL maps[l] skips
+ * level l (its rows are written by eg_level_embed_fwd).
  * X = float[batch*N, F] node-major.  The _grad form scatters dX back (d_maps etc. are outputs). */
 int eg_pack_nodes(const eg_graph* g, int batch, const float* const* maps, const float* head,
                   const float* tail, float* X, void* stream);
 int eg_pack_nodes_grad(const eg_graph* g, int batch, const float* dX, float* const* d_maps, float* d_head,
                        float* d_tail, void* stream);
+
+/* ---- fused level embedding: 1x1 conv (cin -> F) + bias + ReLU + packing of ONE lattice level -----------
+ * replaces `new_features[l] = F.relu(self.linears[l](features[l]))` (src/core/models.py:708-710) and that
+ * level's share of the packing loop (:728-741).  in = DEVICE float[batch, cin, s_l, s_l] (the UNet decoder
+ * map), W = float[F, cin] (Conv2d 1x1 weight), bias = float[F]; writes rows [off_l, off_l + s_l^2) of every
+ * frame of X.  Built for cin in {4, 8} and s_l^2 % 64 == 0 (eg_level_embed_supported); levels packed this
+ * way are passed as NULL to eg_pack_nodes / eg_pack_nodes_grad.
+ * _bwd: d_in (nullable) = float[batch, cin, s_l, s_l], dW = float[F, cin], dbias = float[F]; the ReLU mask
+ * is recomputed from `in` (bit-identical to the forward), nothing is saved between the passes. */
+int eg_level_embed_supported(const eg_graph* g, int level, int cin);
+int eg_level_embed_fwd(const eg_graph* g, int batch, int level, int cin, const float* in, const float* W,
+                       const float* bias, float* X, void* stream);
+int eg_level_embed_bwd(const eg_graph* g, int batch, int level, int cin, const float* in, const float* W,
+                       const float* bias, const float* dX, float* d_in, float* dW, float* dbias, void* ws,
+                       size_t ws_bytes, void* stream);
 
 /* ---- message passing: out = A_hat * in, A_hat = D^-1/2 (A+I) D^-1/2 -------------------------------
  * replaces PyG GCNConv.propagate / torch_scatter.scatter_add (called from src/core/models.py:431).

@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 if torch.cuda.is_available():
     import echoglad_b200 as eg
     from echoglad_b200 import ops
+    from echoglad_b200._lib import WORKSPACE_BYTES
     DEV = torch.device("cuda", 0)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -182,6 +183,55 @@ def test_aggregate_full_graph_linearity_and_symmetry():
     assert ok, worst
 
 
+@pytest.mark.parametrize("kw,batch", [
+    (dict(), 3),                                                       # BASELINE configs[0]/[2]: default.yml graph
+    (dict(use_main_graph_only=True), 4),                               # configs[1]: pixel-level graph only
+    (dict(frame_size=448, num_aux_graphs=8), 2),                       # configs[3]: 2x resolution (4x nodes / edges)
+    (dict(use_connection_nodes=True), 2),                              # hub rows (CSR rows of the gather plan)
+    (dict(main_graph_type="grid-diagonal", aux_graph_type="grid-diagonal"), 2),
+])
+def test_fused_gcn_kernel_equals_csr_composition_at_full_size(kw, batch):
+    """At the full graph sizes of BASELINE.json's configs the fused tcgen05 kernel (tile plan, shared-memory
+    gather, tensor-core transform) must agree with the composition of the two independent kernels of the library
+    (CSR segmented aggregation `eg_gcn_aggregate`, then `eg_linear128`), which the small-graph tests pin to the
+    oracle element by element: forward H and BatchNorm statistics, backward dX, the A_hat dH side output and dW.
+    Tolerance: |a-b| <= 1e-4 |b| + 1e-5 max|b| (both sides are fp32-class; summation orders differ)."""
+    spec = eg.HierGraphSpec(**kw)
+    g = eg.DeviceGraph.get(spec, DEV)
+    n = g.meta.num_nodes
+    rows = batch * n
+    gen = torch.Generator(device=DEV).manual_seed(n)
+    X = torch.randn(rows, 128, device=DEV, generator=gen)
+    W = torch.randn(128, 128, device=DEV, generator=gen) * 0.1
+    bias = torch.randn(128, device=DEV, generator=gen)
+    DH = torch.randn(rows, 128, device=DEV, generator=gen)
+    ADD = torch.randn(rows, 128, device=DEV, generator=gen)
+    ws = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    H = torch.empty_like(X)
+    mean, var = torch.empty(128, device=DEV), torch.empty(128, device=DEV)
+    ops.check(ops.lib.eg_gcn_conv_fwd(g.handle, batch, X.data_ptr(), W.data_ptr(), bias.data_ptr(), H.data_ptr(),
+                                      mean.data_ptr(), var.data_ptr(), ws.data_ptr(), WORKSPACE_BYTES, st))
+    want_h = ops.linear128(ops.gcn_aggregate(g, batch, X), W, True, bias=bias)
+    ok, worst = close(H.cpu(), want_h.cpu(), 1e-4, 1e-5)
+    assert ok, f"H {worst}"
+    ok, worst = close(mean.cpu(), want_h.double().mean(0).cpu(), 1e-4, 1e-5)
+    assert ok, f"mean {worst}"
+    ok, worst = close(var.cpu(), want_h.double().var(0, unbiased=False).cpu(), 1e-4, 1e-5)
+    assert ok, f"var {worst}"
+    dX, dW, G = torch.empty_like(X), torch.empty_like(W), torch.empty_like(X)
+    ops.check(ops.lib.eg_gcn_conv_bwd(g.handle, batch, X.data_ptr(), W.data_ptr(), DH.data_ptr(), ADD.data_ptr(),
+                                      dX.data_ptr(), dW.data_ptr(), None, G.data_ptr(), ws.data_ptr(),
+                                      WORKSPACE_BYTES, st))
+    want_g = ops.gcn_aggregate(g, batch, DH)
+    ok, worst = close(G.cpu(), want_g.cpu(), 1e-4, 1e-5)
+    assert ok, f"A_hat dH {worst}"
+    ok, worst = close(dX.cpu(), ops.linear128(want_g, W, False, addend=ADD).cpu(), 1e-4, 1e-5)
+    assert ok, f"dX {worst}"
+    ok, worst = close(dW.cpu(), (want_g.double().t() @ X.double()).cpu(), 1e-4, 1e-5)
+    assert ok, f"dW {worst}"
+
+
 # ---- dense transforms -----------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("rows", [1, 127, 128, 1000, 40000])
@@ -212,7 +262,7 @@ def test_linear128_3xtf32_fp32_class_accuracy(rows, trans):
     assert ok, worst
 
 
-@pytest.mark.parametrize("rows", [5, 64, 777, 50000])
+@pytest.mark.parametrize("rows", [5, 64, 777, 50000, 700001])  # 700001: 3 accumulation segments per CTA + ragged tail
 def test_linear128_wgrad(rows):
     gen = torch.Generator().manual_seed(rows)
     g = torch.randn(rows, 128, generator=gen)
@@ -348,6 +398,87 @@ def test_pack_nodes_fwd_bwd(key):
     R.pack_nodes(cfg, cpu_maps).backward(dx)
     for a, b in zip(dev_maps, cpu_maps):
         assert torch.allclose(a.grad.cpu(), b.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("frame,naux,batch", [(16, 3, 3), (224, 7, 2)])
+def test_level_embed_fused_matches_conv_relu_pack(frame, naux, batch):
+    """eg_level_embed_fwd/bwd (1x1 conv + ReLU + packing fused) against the reference
+    sequence `F.relu(self.linears[l](features[l]))` -> permute/reshape/cat (src/core/models.py:708-741) run by
+    the CPU oracle in fp32.  Tolerance: activations 1e-5 rel (same fp32 FMA arithmetic, different order),
+    gradients rtol 1e-4 + 1e-5 of the largest entry."""
+    spec = eg.HierGraphSpec(frame_size=frame, num_aux_graphs=naux)
+    g = eg.DeviceGraph(spec, DEV)
+    cfg = R.Cfg(frame_size=frame, num_aux_graphs=naux)
+    gen = torch.Generator().manual_seed(frame)
+    sizes = list(g.meta.level_size)
+    # narrow raw maps for the levels the fused kernel supports (cin 8 for the finest aux level that is a multiple
+    # of 64 positions, cin 4 for the main grid), ready 128-channel maps for the others
+    cins = [128] * len(sizes)
+    cins[-1] = 4
+    cins[-2] = 8
+    raws = [torch.randn(batch, c, s, s, generator=gen) for c, s in zip(cins, sizes)]
+    ws = [torch.randn(128, c, 1, 1, generator=gen) * 0.5 for c in cins]
+    bs = [torch.randn(128, generator=gen) * 0.1 for _ in cins]
+    fused = [l for l, (c, s) in enumerate(zip(cins, sizes)) if c != 128 and
+             ops.lib.eg_level_embed_supported(g.handle, l, c)]
+    assert len(sizes) - 1 in fused and (frame != 224 or len(fused) == 2)
+
+    def leaf(t, dev):
+        return t.to(dev).clone().requires_grad_(True)
+
+    # oracle (CPU, fp32): conv1x1 -> relu -> pack
+    o_raw = [leaf(t, "cpu") for t in raws]
+    o_w = [leaf(t, "cpu") for t in ws]
+    o_b = [leaf(t, "cpu") for t in bs]
+    maps = [torch.relu(torch.nn.functional.conv2d(r, w, b)) if l in fused else r
+            for l, (r, w, b) in enumerate(zip(o_raw, o_w, o_b))]
+    want = R.pack_nodes(cfg, maps)
+    dx = torch.randn(want.shape, generator=gen)
+    want.backward(dx)
+
+    d_raw = [leaf(t, DEV) for t in raws]
+    d_w = [leaf(t, DEV) for t in ws]
+    d_b = [leaf(t, DEV) for t in bs]
+    args = []
+    for l in range(len(sizes)):
+        args += [d_raw[l], d_w[l], d_b[l]] if l in fused else [d_raw[l], None, None]
+    x = ops.EmbedPackNodes.apply(g, tuple(fused), *args)
+    ok, worst = close(x.detach().cpu(), want.detach(), 1e-5, 1e-6)
+    assert ok, f"X {worst}"
+    # the ReLU sign pattern must be identical wherever the oracle is not within rounding of zero
+    x.backward(dx.to(DEV))
+    for l in range(len(sizes)):
+        ok, worst = close(d_raw[l].grad.cpu(), o_raw[l].grad, 1e-4, 1e-5)
+        assert ok, f"d_raw[{l}] {worst}"
+        if l in fused:
+            ok, worst = close(d_w[l].grad.cpu(), o_w[l].grad, 1e-4, 1e-5)
+            assert ok, f"dW[{l}] {worst}"
+            ok, worst = close(d_b[l].grad.cpu(), o_b[l].grad, 1e-4, 1e-5)
+            assert ok, f"db[{l}] {worst}"
+
+
+def test_unet_module_fused_embed_equals_unfused_route():
+    """The drop-in module with the fused level embedding gives the same logits and parameter gradients as its own
+    PyTorch conv1x1 + ReLU + eg_pack_nodes route (fuse_level_embed = False)."""
+    cfg = R.Cfg(variant="unet", frame_size=16, num_aux_graphs=3, gnn_dropout_p=0.0, classifier_dropout_p=0.0)
+    sd = R.init_landmark_state(cfg, seed=11)
+    x0 = torch.randn(3, 4, 16, 16, generator=torch.Generator().manual_seed(12))
+    outs = []
+    for fuse in (True, False):
+        model = _build_module(cfg, "unet").to(DEV)
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        model.fuse_level_embed = fuse
+        x = x0.to(DEV).requires_grad_(True)
+        logits, _ = model(x=x)
+        logits.square().mean().backward()
+        outs.append((logits.detach().cpu(), x.grad.cpu(), {k: p.grad.cpu() for k, p in model.named_parameters() if p.grad is not None}))
+    ok, worst = close(outs[0][0], outs[1][0], 1e-4, 1e-5)
+    assert ok, f"logits {worst}"
+    ok, worst = close(outs[0][1], outs[1][1], 2e-3, 2e-4)
+    assert ok, f"dx {worst}"
+    bad = grads_close(outs[0][2], {k: v.numpy() for k, v in outs[1][2].items()}, rtol=2e-3, atol_frac=2e-4)
+    assert not bad, bad
 
 
 # ---- whole module against the reference's golden vectors ----------------------------------------------------------
@@ -566,6 +697,17 @@ def _hot_path_vs_oracle(cfg, variant, batch, frames_or_x, y, valid, sd, embed_sd
 def test_unet_variant_hot_path_strict():
     c = load_case("model_unet_S16_n3_train")
     _hot_path_vs_oracle(c["cfg"], "unet", c["batch"], c["x"], c["y"], c["valid"], c["sd"])
+
+
+def test_deeper_stack_hot_path_against_oracle():
+    """BASELINE.json configs[3] depth: 2 x num_gnn_layers (6 GCN layers, residual, jk 'last') on a small
+    hierarchy — every layer of the deeper stack against the oracle at the strict fp32 tolerance."""
+    cfg = R.Cfg(variant="avgpool", frame_size=16, num_aux_graphs=3, num_gnn_layers=6, gnn_dropout_p=0.0,
+                classifier_dropout_p=0.0)
+    batch = 3
+    _, _, y, valid = R.synthetic_batch(batch, 16, 3, seed=7)
+    x = torch.randn(batch, 128, 16, 16, generator=torch.Generator().manual_seed(8))
+    _hot_path_vs_oracle(cfg, "avgpool", batch, x, y, valid, R.init_landmark_state(cfg, seed=9))
 
 
 def test_default_yml_batch2_hot_path_against_oracle():

@@ -91,7 +91,7 @@ def main():
             import numpy as np
             a = np.array(buf).reshape(148, 8).mean(0)
             print(f"   tc wait cycles/CTA: compute-wait-operand {a[0]:.0f} compute-wait-raw {a[5]:.0f} loader-wait-raw-empty {a[6]:.0f} "
-                  f"mma-wait-acc-empty {a[1]:.0f} mma-wait-full {a[2]:.0f} epilogue-wait-acc-full {a[3]:.0f} total {a[4]:.0f}")
+                  f"compute-fence {a[7]:.0f} mma-wait-acc-empty {a[1]:.0f} mma-wait-full {a[2]:.0f} epilogue-wait-acc-full {a[3]:.0f} total {a[4]:.0f}")
         print(f"{name:14s} {ms:8.3f} ms   {nbytes / 1e9:6.2f} GB algorithmic   {nbytes / ms / 1e6:8.1f} GB/s", flush=True)
     print(json.dumps({"batch": B, "rows": rows, "results": res}))
 
