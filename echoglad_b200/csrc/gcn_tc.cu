@@ -33,7 +33,7 @@
 // that can live elsewhere does: row copies in the loader warps, waits with a suspend hint.
 // TMEM: 256 columns of weight + 2 x 128 of accumulator.
 // Warps: 0-3 epilogue (TMEM lane quadrant = warp id), 4 MMA issuer, 5-7 loaders, 8-23 compute; the compute
-// warpgroups raise their register budget to 88 with setmaxnreg, the others drop to 56.
+// warpgroups raise their register budget to 88 with setmaxnreg, the epilogue drops to 72, MMA + loaders to 56.
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -67,10 +67,10 @@ constexpr int kLoadWarp0 = kMmaWarp + 1;
 constexpr int kProdWarp0 = kLoadWarp0 + kLoadWarps;
 constexpr int kThreads = (kProdWarp0 + kProdWarps) * 32;  // 768 threads launched with 80 registers each
 static_assert(kProdWarp0 == 8, "warpgroup layout of setmaxnreg");
-// Register budget by warpgroup (setmaxnreg): the 8 non-compute warps drop to 56, the 16 compute warps rise to 88
-// (each SM sub-partition hosts 2 + 4 of them: 2 x 56 + 4 x 88 = 464 registers x 32 lanes <= 16384).
-constexpr int kRegsCompute = 88, kRegsOther = 56;
-static_assert(kProdWarp0 * 32 * kRegsOther + kProdWarps * 32 * kRegsCompute <= kThreads * 80, "register pool of the CTA");
+// Register budget by warpgroup (setmaxnreg): epilogue 72, MMA + loaders 56, the 16 compute warps 88
+// (each SM sub-partition hosts 1 + 1 + 4 of them: (72 + 56 + 4 x 88) x 32 lanes = 15360 <= 16384 registers).
+constexpr int kRegsCompute = 88, kRegsEpi = 72, kRegsLoad = 56;
+static_assert(4 * 32 * (kRegsEpi + kRegsLoad) + kProdWarps * 32 * kRegsCompute <= kThreads * 80, "register pool of the CTA");
 constexpr int kTileBytes = 128 * 128;      // one [128 rows x 32 tf32] operand tile
 constexpr uint32_t kABytes = kStages * 2 * kTileBytes;
 constexpr int kRawRows = kPlanSrc;         // 216 >= 128 (linear mode stages the tile's own rows)
@@ -225,8 +225,10 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
   // one setmaxnreg per warpgroup: warps 0-7 release registers, warps 8-23 take them
   if (warp >= kProdWarp0) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
+  } else if (warp < kEpiWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLoad));
   }
   if (warp >= kProdWarp0) {
     // ===== compute warps: copy raw rows two chunks ahead, gather -> split -> swizzled operand tile ==========
@@ -669,24 +671,32 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
       }
       TC_TIMED_WAIT(0, &acc_full[buf], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-#ifdef EG_DBG_NOEPI
-      for (int sl = 0; sl < 0; ++sl) {
-#else
-      for (int sl = 0; sl < 8; ++sl) {  // 16 tile rows (accumulator columns) at a time
-#endif
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(ew * 32) << 16) + kTmemAcc + buf * 128 + sl * 16, v);
-        const long long base = __shfl_sync(0xffffffffu, gbase, sl);
-        const int cnt = __shfl_sync(0xffffffffu, gcnt, GATHER ? 8 + sl : sl);
-        float* out = p.Out + max(base, 0LL) * 128 + f;
-        float s = 0.f, q = 0.f;
-        if (p.addend) {  // backward: + residual gradient; all 16 loads in flight before the accumulator is consumed
-          float ad[16];
+      const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + kTmemAcc + buf * 128;
+      if (p.addend) {
+        // backward: Out = acc + bias + residual gradient.  The 16 residual loads of a slab are issued one slab
+        // AHEAD (two register sets, ping-pong), so their L2 latency overlaps the previous slab's TMEM load and
+        // stores instead of stalling the epilogue 8 times per tile (it was the bottleneck of the backward).
+        auto slab_rows = [&](int sl, long long& base, int& cnt) {
+          base = __shfl_sync(0xffffffffu, gbase, sl);
+          cnt = __shfl_sync(0xffffffffu, gcnt, GATHER ? 8 + sl : sl);
+        };
+        auto load_res = [&](int sl, float (&ad)[16]) {
+          long long base;
+          int cnt;
+          slab_rows(sl, base, cnt);
           const float* adp = p.addend + max(base, 0LL) * 128 + f;
 #pragma unroll
           for (int i = 0; i < 16; ++i) ad[i] = i < cnt ? __ldg(adp + i * 128) : 0.f;
+        };
+        auto finish = [&](int sl, const float (&ad)[16]) {
+          uint32_t v[16];
+          tmem_ld16(tacc + sl * 16, v);
+          long long base;
+          int cnt;
+          slab_rows(sl, base, cnt);
+          float* out = p.Out + max(base, 0LL) * 128 + f;
           tmem_ld_wait();
+          float s = 0.f, q = 0.f;
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             if (i < cnt) {  // warp-uniform predicate
@@ -697,7 +707,31 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
                 q = fmaf(o, o, q);
               }
             }
-        } else {
+          s_sum += (double)s;
+          s_sq += (double)q;
+        };
+        float adA[16], adB[16];
+        load_res(0, adA);
+#pragma unroll 1
+        for (int sl = 0; sl < 8; sl += 2) {
+          load_res(sl + 1, adB);
+          finish(sl, adA);
+          if (sl + 2 < 8) load_res(sl + 2, adA);
+          finish(sl + 1, adB);
+        }
+      } else {
+#pragma unroll 1
+#ifdef EG_DBG_NOEPI
+        for (int sl = 0; sl < 0; ++sl) {
+#else
+        for (int sl = 0; sl < 8; ++sl) {  // 16 tile rows (accumulator columns) at a time
+#endif
+          uint32_t v[16];
+          tmem_ld16(tacc + sl * 16, v);
+          const long long base = __shfl_sync(0xffffffffu, gbase, sl);
+          const int cnt = __shfl_sync(0xffffffffu, gcnt, GATHER ? 8 + sl : sl);
+          float* out = p.Out + max(base, 0LL) * 128 + f;
+          float s = 0.f, q = 0.f;
           tmem_ld_wait();
           if (cnt == 16) {
 #pragma unroll
@@ -720,9 +754,9 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
               }
             }
           }
+          s_sum += (double)s;
+          s_sq += (double)q;
         }
-        s_sum += (double)s;
-        s_sq += (double)q;
       }
       tc_fence_before();
       __syncwarp();
