@@ -9,12 +9,14 @@ using namespace eg;
 namespace {
 
 constexpr int kMidThreads = 128;  // warp k <-> head k, lane <-> row of the 32-row tile
+constexpr int kMidGrid = kNumSMs * 6;  // 6 resident blocks per SM (34 KB of shared memory each)
+static_assert((size_t)kMidGrid * 128 * sizeof(double) <= kStatsBytes, "clf_mid_fwd partials fit the stats area");
 constexpr int TR = 32;
 constexpr int LDA = 132;          // A1 tile stride
 constexpr int LDO = 68;           // Z2 tile stride
 
 // Z2[r][16k+j] = b2[k][j] + sum_i A1[r][32k+i] * W2[k][j][i]
-__global__ void __launch_bounds__(kMidThreads)
+__global__ void __launch_bounds__(kMidThreads, 6)
 clf_mid_fwd_kernel(long long rows, const float* __restrict__ A1, const float* __restrict__ W2,
                    const float* __restrict__ b2, float* __restrict__ Z2, double* __restrict__ parts) {
   __shared__ __align__(16) float As[TR * LDA];
@@ -79,7 +81,7 @@ clf_mid_fwd_kernel(long long rows, const float* __restrict__ A1, const float* __
 
 // dA1[r][32k+i] = sum_j dZ2[r][16k+j] W2[k][j][i];  per-block partials of dW2[k][j][i], db2[k][j].
 constexpr int kMidPart = 2048 + 64;
-__global__ void __launch_bounds__(kMidThreads)
+__global__ void __launch_bounds__(kMidThreads, 6)
 clf_mid_bwd_kernel(long long rows, const float* __restrict__ A1, const float* __restrict__ W2,
                    const float* __restrict__ dZ2, float* __restrict__ dA1, float* __restrict__ parts) {
   __shared__ __align__(16) float As[TR * LDA];   // A1 tile, then reused for the dA1 tile
@@ -255,7 +257,7 @@ int eg_clf_mid_fwd(int64_t rows, const float* A1, const float* W2, const float* 
     return EG_ERR_WORKSPACE;
   }
   long long ntiles = (rows + TR - 1) / TR;
-  int grid = (int)(ntiles < kMaxParts ? ntiles : kMaxParts);
+  int grid = (int)(ntiles < kMidGrid ? ntiles : kMidGrid);
   double* parts = stats ? reinterpret_cast<double*>(ws) : nullptr;
   ProfileScope prof("clf_mid_fwd", as_stream(stream));
   clf_mid_fwd_kernel<<<grid, kMidThreads, 0, as_stream(stream)>>>(rows, A1, W2, b2, Z2, parts);
@@ -271,8 +273,9 @@ int eg_clf_mid_bwd(int64_t rows, const float* A1, const float* W2, const float* 
     set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
     return EG_ERR_WORKSPACE;
   }
+  static_assert((size_t)kMidGrid * kMidPart * sizeof(float) <= kWgradBytes, "clf_mid_bwd partials fit the workspace");
   long long ntiles = (rows + TR - 1) / TR;
-  int grid = (int)(ntiles < kMaxParts ? ntiles : kMaxParts);
+  int grid = (int)(ntiles < kMidGrid ? ntiles : kMidGrid);
   float* parts = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);
   ProfileScope prof("clf_mid_bwd", as_stream(stream));
   clf_mid_bwd_kernel<<<grid, kMidThreads, 0, as_stream(stream)>>>(rows, A1, W2, dZ2, dA1, parts);

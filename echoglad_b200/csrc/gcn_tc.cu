@@ -628,47 +628,45 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
     const int f = ew * 32 + lane;    // output feature owned by this thread
     const float bias = p.bias ? __ldg(p.bias + f) : 0.f;
     double s_sum = 0.0, s_sq = 0.0;
+    // row groups of a tile: lane l < 8 holds the first global row of group l (or -1), lane 8 + l its row count.
+    // They are fetched ONE TILE AHEAD (the table read is a dependent global load that would otherwise be exposed
+    // at the top of every tile).
+    auto tile_rows = [&](int tile, long long& base, int& cnt) {
+      base = -1;
+      cnt = 0;
+      if (tile >= p.num_tiles) return;
+      if (GATHER) {
+        const int b = tile / p.tiles_per_frame;
+        const int v = lane < 16 ? __ldg(p.tile_groups + (tile - b * p.tiles_per_frame) * 16 + lane) : 0;
+        cnt = v;
+        base = (lane < 8 && v >= 0) ? (long long)b * p.nodes_per_frame + v : -1;
+      } else {
+        const long long r0 = (long long)tile * 128 + (lane & 7) * 16;
+        base = r0 < p.rows ? r0 : -1;
+        cnt = (int)max(0LL, min(16LL, p.rows - r0));
+      }
+    };
+    long long gbase, nbase;
+    int gcnt, ncnt;
+    tile_rows(blockIdx.x, gbase, gcnt);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, acc_phase = (it >> 1) & 1u;
-      // lane l < 8: first global row of group l (or -1); lane 8 + l: rows in group l
-      long long gbase = -1;
-      int gcnt = 0;
-      if (GATHER) {
-        const int b = tile / p.tiles_per_frame;
-        const int t = tile - b * p.tiles_per_frame;
-        const int v = lane < 16 ? __ldg(p.tile_groups + t * 16 + lane) : 0;
-        gcnt = v;
-        gbase = (lane < 8 && v >= 0) ? (long long)b * p.nodes_per_frame + v : -1;
-      } else {
-        const long long r0 = (long long)tile * 128 + (lane & 7) * 16;
-        gbase = r0 < p.rows ? r0 : -1;
-        gcnt = (int)max(0LL, min(16LL, p.rows - r0));
-      }
-      if (p.addend && tile + (int)gridDim.x < p.num_tiles) {
-        // residual rows of this CTA's NEXT tile -> L2 now, so that the slab loop below reads them at L2 latency
-        // one tile from now (exposed DRAM latency per slab made the epilogue the bottleneck of the backward)
-        const int ntile = tile + gridDim.x;
-        long long nbase = -1;
-        int ncnt = 0;
-        if (GATHER) {
-          const int nb = ntile / p.tiles_per_frame;
-          const int v = lane < 16 ? __ldg(p.tile_groups + (ntile - nb * p.tiles_per_frame) * 16 + lane) : 0;
-          ncnt = v;
-          nbase = (lane < 8 && v >= 0) ? (long long)nb * p.nodes_per_frame + v : -1;
-        } else {
-          const long long r0 = (long long)ntile * 128 + (lane & 7) * 16;
-          nbase = r0 < p.rows ? r0 : -1;
-          ncnt = (int)max(0LL, min(16LL, p.rows - r0));
-        }
+      tile_rows(tile + gridDim.x, nbase, ncnt);  // consumed after the slab loop
+      float adA[16], adB[16];
+      auto slab_rows = [&](int sl, long long& base, int& cnt) {
+        base = __shfl_sync(0xffffffffu, gbase, sl);
+        cnt = __shfl_sync(0xffffffffu, gcnt, GATHER ? 8 + sl : sl);
+      };
+      auto load_res = [&](int sl, float (&ad)[16]) {
+        long long base;
+        int cnt;
+        slab_rows(sl, base, cnt);
+        const float* adp = p.addend + max(base, 0LL) * 128 + f;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {  // 8 groups x 64 lines of 128 B, 4 lines per epilogue thread
-          const int line = f + 128 * m, grp = line >> 6, lo = line & 63;
-          const long long base = __shfl_sync(0xffffffffu, nbase, grp);
-          const int cnt = __shfl_sync(0xffffffffu, ncnt, GATHER ? 8 + grp : grp);
-          if (base >= 0 && lo < cnt * 4) prefetch_l2(p.addend + base * 128 + lo * 32);
-        }
-      }
+        for (int i = 0; i < 16; ++i) ad[i] = i < cnt ? __ldg(adp + i * 128) : 0.f;
+      };
+      if (p.addend) load_res(0, adA);  // in flight across the wait for the accumulator
       TC_TIMED_WAIT(0, &acc_full[buf], acc_phase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + kTmemAcc + buf * 128;
@@ -676,18 +674,6 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
         // backward: Out = acc + bias + residual gradient.  The 16 residual loads of a slab are issued one slab
         // AHEAD (two register sets, ping-pong), so their L2 latency overlaps the previous slab's TMEM load and
         // stores instead of stalling the epilogue 8 times per tile (it was the bottleneck of the backward).
-        auto slab_rows = [&](int sl, long long& base, int& cnt) {
-          base = __shfl_sync(0xffffffffu, gbase, sl);
-          cnt = __shfl_sync(0xffffffffu, gcnt, GATHER ? 8 + sl : sl);
-        };
-        auto load_res = [&](int sl, float (&ad)[16]) {
-          long long base;
-          int cnt;
-          slab_rows(sl, base, cnt);
-          const float* adp = p.addend + max(base, 0LL) * 128 + f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) ad[i] = i < cnt ? __ldg(adp + i * 128) : 0.f;
-        };
         auto finish = [&](int sl, const float (&ad)[16]) {
           uint32_t v[16];
           tmem_ld16(tacc + sl * 16, v);
@@ -710,8 +696,6 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
           s_sum += (double)s;
           s_sq += (double)q;
         };
-        float adA[16], adB[16];
-        load_res(0, adA);
 #pragma unroll 1
         for (int sl = 0; sl < 8; sl += 2) {
           load_res(sl + 1, adB);
@@ -761,6 +745,18 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (p.addend) {
+        // residual rows of this CTA's NEXT tile -> L2 now, so that its slab loop reads them at L2 latency
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {  // 8 groups x 64 lines of 128 B, 4 lines per epilogue thread
+          const int line = f + 128 * m, grp = line >> 6, lo = line & 63;
+          const long long base = __shfl_sync(0xffffffffu, nbase, grp);
+          const int cnt = __shfl_sync(0xffffffffu, ncnt, GATHER ? 8 + grp : grp);
+          if (base >= 0 && lo < cnt * 4) prefetch_l2(p.addend + base * 128 + lo * 32);
+        }
+      }
+      gbase = nbase;
+      gcnt = ncnt;
     }
     if (p.stat_parts) {
       p.stat_parts[(size_t)blockIdx.x * 256 + f] = s_sum;
