@@ -37,9 +37,10 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="")
+    ap.add_argument("--main-only", action="store_true", help="use_main_graph_only graph (all tiles are lattice tiles)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
-    g = eg.DeviceGraph.get(eg.HierGraphSpec(), dev)
+    g = eg.DeviceGraph.get(eg.HierGraphSpec(use_main_graph_only=args.main_only), dev)
     B, N = args.batch, g.meta.num_nodes
     rows = B * N
     U = rows * 128 * 4
