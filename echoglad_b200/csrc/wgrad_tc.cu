@@ -8,7 +8,7 @@
 // are read exactly once (2 U), the result is 64 KB.
 //
 // The reduction runs over the ROWS, so both operands are "MN-major" for the MMA (the 128 features of a row
-// are contiguous, the K index is the row): a block of 16 rows of G and of X travels global -> shared with
+// are contiguous, the K index is the row): a block of 32 rows of G and of X travels global -> shared with
 // cp.async straight into the canonical MN-major layout of 32-bit operands (SWIZZLE_128B_BASE32B: 4 atoms of
 // 32 features x 4 row groups of 4 rows), no transpose anywhere.  3xTF32: split warps rewrite the raw block in place as its tf32 hi part
 // and write the lo part to a second ring; one elected thread issues, per 8-row group,
@@ -20,7 +20,7 @@
 // memory (L2-resident, round-to-nearest adds, fixed order) while the next segment accumulates.  A fixed-order
 // second stage sums the [148][128][128] partials in double: no atomics, bit-reproducible.
 //
-// Rings: RAW/hi ring of kRaw blocks (16 KB: G and X) deep enough to cover the HBM latency, LO ring of kLo blocks.
+// Rings: RAW/hi ring of kRaw = 5 blocks (32 KB: 32 rows of G and X), LO ring of kLo = 2 blocks (224 KB in all).
 // Warps: 0-3 loaders, 4 MMA issuer, 5-12 split, 13-16 epilogue (TMEM lane quadrant = warp id % 4).
 #include "common.cuh"
 #include "tc05.cuh"
@@ -30,11 +30,20 @@ using namespace eg::tc;
 
 namespace {
 
-constexpr int kRows = 16;                      // rows per block (2 MMA k-steps of 8)
-constexpr int kRaw = 9;                        // raw / hi ring depth
-constexpr int kLo = 4;                         // lo ring depth
-constexpr int kSegBlocks = 128;                // blocks (2048 rows, 768 MMAs) per accumulation segment
-constexpr int kLoadWarps = 4, kSplitWarps = 8, kEpiWarps = 4;
+#ifndef EG_WG_ROWS
+#define EG_WG_ROWS 32  // measured at batch 64: 8 rows 1.65 ms, 16 rows 1.18 ms, 32 rows 1.07 ms (per-block handshakes)
+#define EG_WG_RAW 5
+#define EG_WG_LO 2
+#endif
+#ifndef EG_WG_SPLIT
+#define EG_WG_SPLIT 8
+#endif
+constexpr int kRows = EG_WG_ROWS;              // rows per block (kRows / 8 MMA k-steps)
+constexpr int kRaw = EG_WG_RAW;                // raw / hi ring depth
+constexpr int kLo = EG_WG_LO;                  // lo ring depth
+constexpr int kSegBlocks = 2048 / kRows;       // blocks (2048 rows, 768 MMAs) per accumulation segment
+constexpr int kLoadWarps = 4, kSplitWarps = EG_WG_SPLIT, kEpiWarps = 4;
+static_assert(kRows % kSplitWarps == 0 && kRows % kLoadWarps == 0 && kRows % 8 == 0, "block shape");
 constexpr int kMmaWarp = kLoadWarps;
 constexpr int kSplitWarp0 = kMmaWarp + 1;
 constexpr int kEpiWarp0 = kSplitWarp0 + kSplitWarps;
