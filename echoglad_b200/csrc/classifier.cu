@@ -15,67 +15,97 @@ constexpr int TR = 32;
 constexpr int LDA = 132;          // A1 tile stride
 constexpr int LDO = 68;           // Z2 tile stride
 
-// Z2[r][16k+j] = b2[k][j] + sum_i A1[r][32k+i] * W2[k][j][i]
-__global__ void __launch_bounds__(kMidThreads, 6)
-clf_mid_fwd_kernel(long long rows, const float* __restrict__ A1, const float* __restrict__ W2,
-                   const float* __restrict__ b2, float* __restrict__ Z2, double* __restrict__ parts) {
-  __shared__ __align__(16) float As[TR * LDA];
-  __shared__ __align__(16) float Ws[4 * 16 * 32];
-  __shared__ __align__(16) float Os[TR * LDO];
-  __shared__ float bs[64];
-  const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
-  for (int i = tid; i < 2048; i += kMidThreads) Ws[i] = __ldg(W2 + i);
-  if (tid < 64) bs[tid] = __ldg(b2 + tid);
-  double run_sum = 0.0, run_sq = 0.0;  // thread c < 64 owns column c
-  const long long ntiles = (rows + TR - 1) / TR;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long row0 = tile * TR;
-    const int nvalid = (int)min((long long)TR, rows - row0);
-    __syncthreads();  // previous tile fully consumed (also orders the Ws/bs fill)
-    for (int i = tid; i < TR * 32; i += kMidThreads) {
-      int r = i >> 5, c4 = i & 31;
-      float4 v = r < nvalid ? ldg4(A1 + (row0 + r) * 128 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(As + r * LDA + c4 * 4) = v;
-    }
-    __syncthreads();
-    float acc[16];
+// sum over the 32 lanes of v[i] for i = 0..31; on return lane l holds the total of v[l] (31 shuffles)
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = bs[k * 16 + j];
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
 #pragma unroll
-    for (int i4 = 0; i4 < 8; ++i4) {
-      const float4 a = *reinterpret_cast<const float4*>(As + lane * LDA + k * 32 + i4 * 4);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float4 w = *reinterpret_cast<const float4*>(Ws + (k * 16 + j) * 32 + i4 * 4);
-        acc[j] = fmaf(a.x, w.x, acc[j]);
-        acc[j] = fmaf(a.y, w.y, acc[j]);
-        acc[j] = fmaf(a.z, w.z, acc[j]);
-        acc[j] = fmaf(a.w, w.w, acc[j]);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      *reinterpret_cast<float4*>(Os + lane * LDO + k * 16 + q * 4) =
-          make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-    __syncthreads();
-    for (int i = tid; i < TR * 16; i += kMidThreads) {
-      int r = i >> 4, c4 = i & 15;
-      if (r < nvalid) st4(Z2 + (row0 + r) * 64 + c4 * 4, *reinterpret_cast<const float4*>(Os + r * LDO + c4 * 4));
-    }
-    if (parts && tid < 64) {
-      float s = 0.f, q = 0.f;
-      for (int r = 0; r < nvalid; ++r) {
-        float v = Os[r * LDO + tid];
-        s += v;
-        q = fmaf(v, v, q);
-      }
-      run_sum += (double)s;
-      run_sq += (double)q;
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
     }
   }
-  if (parts && tid < 64) {
-    parts[(size_t)blockIdx.x * 128 + tid] = run_sum;
-    parts[(size_t)blockIdx.x * 128 + 64 + tid] = run_sq;
+  return v[0];
+}
+// (x, y) += a * (w.x, w.y): one packed FFMA2
+__device__ __forceinline__ void fma2(float& x, float& y, float a, float wx, float wy) {
+  unsigned long long c = ((unsigned long long)__float_as_uint(y) << 32) | __float_as_uint(x);
+  const unsigned long long a2 = ((unsigned long long)__float_as_uint(a) << 32) | __float_as_uint(a);
+  const unsigned long long w2 = ((unsigned long long)__float_as_uint(wy) << 32) | __float_as_uint(wx);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a2), "l"(w2));
+  x = __uint_as_float((uint32_t)c);
+  y = __uint_as_float((uint32_t)(c >> 32));
+}
+
+// Z2[r][16k+j] = b2[k][j] + sum_i A1[r][32k+i] * W2[k][j][i]
+// Warp k <-> head k; a thread owns TWO rows (lane, lane + 32 of a 64-row tile) and reads its 128-byte slices of
+// A1 straight from global (16 independent 128-bit loads in flight per thread, no shared-memory staging, no block
+// barrier in the loop); the transposed weight Wt[k][i][0..15] is read as 4 broadcast LDS.128 per input feature and
+// shared by both rows; packed FFMA2.  Column statistics: 31-shuffle transpose-reduce per tile, double per thread.
+constexpr int TR2 = 64;
+__global__ void __launch_bounds__(kMidThreads)
+clf_mid_fwd_kernel(long long rows, const float* __restrict__ A1, const float* __restrict__ W2,
+                   const float* __restrict__ b2, float* __restrict__ Z2, double* __restrict__ parts) {
+  __shared__ __align__(16) float Wt[4 * 32 * 16];  // Wt[k][i][j] = W2[k][j][i]
+  __shared__ float bs[64];
+  const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
+  for (int i = tid; i < 2048; i += kMidThreads) {
+    const int kk = i >> 9, j = (i >> 5) & 15, ii = i & 31;
+    Wt[(kk * 32 + ii) * 16 + j] = __ldg(W2 + i);
+  }
+  if (tid < 64) bs[tid] = __ldg(b2 + tid);
+  __syncthreads();
+  double run = 0.0;  // lane l < 16: sum of column 16k + l; lane 16 + l: sum of squares of that column
+  const long long ntiles = (rows + TR2 - 1) / TR2;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long r0 = tile * TR2 + lane, r1 = r0 + 32;
+    const bool ok0 = r0 < rows, ok1 = r1 < rows;
+    float4 a0[8], a1[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      a0[q] = ok0 ? ldg4(A1 + r0 * 128 + k * 32 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      a1[q] = ok1 ? ldg4(A1 + r1 * 128 + k * 32 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float z0[16], z1[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z0[j] = z1[j] = bs[k * 16 + j];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float av0[4] = {a0[q].x, a0[q].y, a0[q].z, a0[q].w}, av1[4] = {a1[q].x, a1[q].y, a1[q].z, a1[q].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float* wrow = Wt + (k * 32 + q * 4 + e) * 16;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 w = *reinterpret_cast<const float4*>(wrow + j4 * 4);
+          fma2(z0[4 * j4], z0[4 * j4 + 1], av0[e], w.x, w.y);
+          fma2(z0[4 * j4 + 2], z0[4 * j4 + 3], av0[e], w.z, w.w);
+          fma2(z1[4 * j4], z1[4 * j4 + 1], av1[e], w.x, w.y);
+          fma2(z1[4 * j4 + 2], z1[4 * j4 + 3], av1[e], w.z, w.w);
+        }
+      }
+    }
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      if (ok0) st4(Z2 + r0 * 64 + k * 16 + j4 * 4, make_float4(z0[4 * j4], z0[4 * j4 + 1], z0[4 * j4 + 2], z0[4 * j4 + 3]));
+      if (ok1) st4(Z2 + r1 * 64 + k * 16 + j4 * 4, make_float4(z1[4 * j4], z1[4 * j4 + 1], z1[4 * j4 + 2], z1[4 * j4 + 3]));
+    }
+    if (parts) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float x0 = ok0 ? z0[j] : 0.f, x1 = ok1 ? z1[j] : 0.f;
+        v[j] = x0 + x1;
+        v[16 + j] = fmaf(x0, x0, x1 * x1);
+      }
+      run += (double)transpose_reduce32(v, lane);
+    }
+  }
+  if (parts) {  // parts[block][0..63] sums, [64..127] sums of squares
+    const int col = k * 16 + (lane & 15);
+    parts[(size_t)blockIdx.x * 128 + (lane < 16 ? col : 64 + col)] = run;
   }
 }
 
@@ -256,7 +286,7 @@ int eg_clf_mid_fwd(int64_t rows, const float* A1, const float* W2, const float* 
     set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
     return EG_ERR_WORKSPACE;
   }
-  long long ntiles = (rows + TR - 1) / TR;
+  long long ntiles = (rows + TR2 - 1) / TR2;
   int grid = (int)(ntiles < kMidGrid ? ntiles : kMidGrid);
   double* parts = stats ? reinterpret_cast<double*>(ws) : nullptr;
   ProfileScope prof("clf_mid_fwd", as_stream(stream));
