@@ -687,7 +687,11 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
           long long base;
           int cnt;
           slab_rows(sl, base, cnt);
+          #ifdef EG_DBG_SMALLOUT
+          float* out = p.Out + (max(base, 0LL) & 1023) * 128 + f;  // timing experiment: all stores hit the same 512 KB
+#else
           float* out = p.Out + max(base, 0LL) * 128 + f;
+#endif
           tmem_ld_wait();
           float s = 0.f, q = 0.f;
 #pragma unroll
@@ -721,7 +725,11 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
           tmem_ld16(tacc + sl * 16, v);
           const long long base = __shfl_sync(0xffffffffu, gbase, sl);
           const int cnt = __shfl_sync(0xffffffffu, gcnt, GATHER ? 8 + sl : sl);
+          #ifdef EG_DBG_SMALLOUT
+          float* out = p.Out + (max(base, 0LL) & 1023) * 128 + f;  // timing experiment: all stores hit the same 512 KB
+#else
           float* out = p.Out + max(base, 0LL) * 128 + f;
+#endif
           float s = 0.f, q = 0.f;
           tmem_ld_wait();
           if (cnt == 16) {

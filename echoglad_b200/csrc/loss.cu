@@ -271,6 +271,86 @@ int make_levels(int num_levels, const int32_t* level_size, Levels& lv) {
 
 }  // namespace
 
+
+namespace {
+// Expected landmark coordinates of the main level (post-path metric, src/core/evaluators.py:310-348): one block per
+// frame, all four channels at once (one float4 per node).  Pass 1: channel maxima of the logits and of the label
+// heat map; pass 2: softmax normaliser and first moments in h and w, smallest row / column holding the label
+// maximum (torch.max returns the first maximum), sum of `valid`.  Block-wide reductions in a fixed order.
+constexpr int kEcThreads = 512;
+struct Ec4 { float v[4]; };
+__device__ __forceinline__ float ec_red(float x, float* red, bool is_max, bool is_min) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float y = __shfl_xor_sync(0xffffffffu, x, o);
+    x = is_max ? fmaxf(x, y) : (is_min ? fminf(x, y) : x + y);
+  }
+  __syncthreads();
+  if (lane == 0) red[warp] = x;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < kEcThreads / 32; ++w) r = is_max ? fmaxf(r, red[w]) : (is_min ? fminf(r, red[w]) : r + red[w]);
+  return r;
+}
+__global__ void __launch_bounds__(kEcThreads)
+expected_coords_kernel(int n0, int frame, const float* __restrict__ logits, const float* __restrict__ y,
+                       const float* __restrict__ valid, float* __restrict__ pred_hw, int* __restrict__ gt_hw,
+                       float* __restrict__ valid_mean) {
+  __shared__ float red[kEcThreads / 32];
+  const int b = blockIdx.x, P = frame * frame;
+  const float4* L = reinterpret_cast<const float4*>(logits) + (size_t)b * n0 + (n0 - P);
+  const float4* Y = reinterpret_cast<const float4*>(y) + (size_t)b * n0 + (n0 - P);
+  const float4* V = valid ? reinterpret_cast<const float4*>(valid) + (size_t)b * n0 + (n0 - P) : nullptr;
+  float ml[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, my[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  for (int i = threadIdx.x; i < P; i += kEcThreads) {
+    const float4 l = __ldg(L + i), t = __ldg(Y + i);
+    ml[0] = fmaxf(ml[0], l.x); ml[1] = fmaxf(ml[1], l.y); ml[2] = fmaxf(ml[2], l.z); ml[3] = fmaxf(ml[3], l.w);
+    my[0] = fmaxf(my[0], t.x); my[1] = fmaxf(my[1], t.y); my[2] = fmaxf(my[2], t.z); my[3] = fmaxf(my[3], t.w);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    ml[c] = ec_red(ml[c], red, true, false);
+    my[c] = ec_red(my[c], red, true, false);
+  }
+  float se[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0}, sw[4] = {0, 0, 0, 0}, sv[4] = {0, 0, 0, 0};
+  float gh[4], gw[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) gh[c] = gw[c] = (float)frame;
+  for (int i = threadIdx.x; i < P; i += kEcThreads) {
+    const float4 l4 = __ldg(L + i), t4 = __ldg(Y + i);
+    const float4 v4 = V ? __ldg(V + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float l[4] = {l4.x, l4.y, l4.z, l4.w}, t[4] = {t4.x, t4.y, t4.z, t4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+    const float h = (float)(i / frame), w = (float)(i % frame);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float e = expf(l[c] - ml[c]);
+      se[c] += e;
+      sh[c] = fmaf(e, h, sh[c]);
+      sw[c] = fmaf(e, w, sw[c]);
+      sv[c] += v[c];
+      if (t[c] == my[c]) {
+        gh[c] = fminf(gh[c], h);
+        gw[c] = fminf(gw[c], w);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float e = ec_red(se[c], red, false, false), a = ec_red(sh[c], red, false, false),
+                bw = ec_red(sw[c], red, false, false), vv = ec_red(sv[c], red, false, false),
+                h0 = ec_red(gh[c], red, false, true), w0 = ec_red(gw[c], red, false, true);
+    if (threadIdx.x == 0) {
+      pred_hw[(b * 4 + c) * 2] = a / e;
+      pred_hw[(b * 4 + c) * 2 + 1] = bw / e;
+      gt_hw[(b * 4 + c) * 2] = (int)h0;
+      gt_hw[(b * 4 + c) * 2 + 1] = (int)w0;
+      valid_mean[b * 4 + c] = vv / (float)P;
+    }
+  }
+}
+}  // namespace
+
 extern "C" {
 
 int eg_bce_multilevel(int64_t n, const float* logits, const float* y, const float* valid, float ones_weight,
@@ -337,6 +417,20 @@ int eg_node_labels(int batch, int channels, int frame_size, int num_levels, cons
   EG_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)batch * lv.total * channels, s));
   const int total = batch * channels * num_levels;
   labels_kernel<<<(total + 127) / 128, 128, 0, s>>>(batch, channels, frame_size, lv, coords, y);
+  EG_LAUNCH_CHECK();
+  return EG_OK;
+}
+
+int eg_expected_coords(int batch, int channels, int nodes_per_frame, int frame_size, const float* logits,
+                       const float* y, const float* valid, float* pred_hw, int32_t* gt_hw, float* valid_mean,
+                       void* stream) {
+  EG_CHECK_ARG(batch >= 1 && logits && y && pred_hw && gt_hw && valid_mean, "eg_expected_coords: NULL argument");
+  EG_CHECK_ARG(channels == 4, "eg_expected_coords: built for 4 landmark channels (got %d)", channels);
+  EG_CHECK_ARG(frame_size >= 1 && (long long)frame_size * frame_size <= nodes_per_frame,
+               "eg_expected_coords: frame_size^2 exceeds nodes_per_frame");
+  ProfileScope prof("expected_coords", as_stream(stream));
+  expected_coords_kernel<<<batch, kEcThreads, 0, as_stream(stream)>>>(nodes_per_frame, frame_size, logits, y, valid,
+                                                                      pred_hw, gt_hw, valid_mean);
   EG_LAUNCH_CHECK();
   return EG_OK;
 }

@@ -1,0 +1,145 @@
+"""Drop-in for the reference's `LandmarkExpectedCoordiantesEvaluator` (sic; `EVALUATORS['landmarkcoorderror']`,
+src/builders/evaluator_builder.py:6-12, src/core/evaluators.py:239-483): same constructor, `update / compute /
+reset / get_last / get_predictions / get_sum_of_width_*` contract, but the per-node work — softmax over the
+224 x 224 main-level logits of every frame and channel, its expected (h, w), the arg-max of the label heat map —
+runs in ONE device kernel (`eg_expected_coords`) on the logits the model just produced, so a step transfers
+3 x [B,4,2] numbers instead of the `[B*N,4]` logits the reference moves to the host (`src/engine.py:466-492`).
+The remaining arithmetic is on [B,4] tensors and follows the reference line by line."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._lib import EchogladError, check, lib
+
+_NAMES = ('lvid_top', 'lvid_bot', 'lvpw', 'ivs')
+
+
+def expected_coords(y_pred: torch.Tensor, y_true: torch.Tensor, valid, batch_size: int, frame_size: int):
+    """-> preds float[B,4,2], gt int32[B,4,2], valid_subset float[B,4] (device tensors)."""
+    if not y_pred.is_cuda:
+        raise EchogladError("expected_coords needs CUDA tensors: echoglad_b200 has no CPU fallback")
+    lg = y_pred.detach().to(torch.float32).contiguous().view(-1, 4)
+    yt = y_true.detach().to(torch.float32).contiguous().view(-1, 4)
+    vd = None if valid is None else valid.detach().to(torch.float32).contiguous().view(-1, 4)
+    if lg.shape[0] % batch_size or yt.shape != lg.shape or (vd is not None and vd.shape != lg.shape):
+        raise EchogladError(f"expected_coords: logits {tuple(lg.shape)} / labels {tuple(yt.shape)} do not match "
+                            f"batch_size={batch_size}")
+    n0 = lg.shape[0] // batch_size
+    dev = lg.device
+    preds = torch.empty(batch_size, 4, 2, device=dev)
+    gt = torch.empty(batch_size, 4, 2, device=dev, dtype=torch.int32)
+    vs = torch.empty(batch_size, 4, device=dev)
+    check(lib.eg_expected_coords(batch_size, 4, n0, frame_size, lg.data_ptr(), yt.data_ptr(),
+                                 None if vd is None else vd.data_ptr(), preds.data_ptr(), gt.data_ptr(),
+                                 vs.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "eg_expected_coords")
+    return preds, gt, vs
+
+
+class LandmarkExpectedCoordiantesEvaluator(object):
+    """Locates the landmarks as the expected value of the soft-maxed heat map and measures how far they are from the
+    ground truth (src/core/evaluators.py:239-483)."""
+
+    def __init__(self, logger=None, batch_size=2, frame_size=224, use_coord_graph=False):
+        if use_coord_graph:
+            raise NotImplementedError("use_coordinate_graph=True is not built (SURVEY.md §8(f) row 3)")
+        self.batch_size = batch_size
+        self.frame_size = frame_size
+        self.use_coord_graph = use_coord_graph
+        self.detailed_performance = {}
+        self.reset()
+
+    def reset(self):
+        self.coordinate_errors = {k: [] for k in ('ivs', 'lvid_top', 'lvid_bot', 'lvpw')}
+        self.valid_errors = {k: [] for k in ('ivs', 'lvid_top', 'lvid_bot', 'lvpw')}
+        self.width_MAE = {k: [] for k in ('lvid', 'ivs', 'lvpw')}
+        self.width_MPE = {k: [] for k in ('lvid', 'ivs', 'lvpw')}
+        self.detailed_performance.clear()
+
+    @staticmethod
+    def get_pixel_length(x0, y0, x1, y1, pix2mm_x, pix2mm_y):
+        return torch.sqrt(((x0 - x1) * pix2mm_x) ** 2 + ((y0 - y1) * pix2mm_y) ** 2)
+
+    def update(self, y_pred, y_true, pix2mm_x, pix2mm_y, valid):
+        self.detailed_performance.clear()
+        preds, gt, valid_subset = expected_coords(y_pred, y_true, valid, self.batch_size, self.frame_size)
+        # everything below works on [B,4] numbers; one small D2H transfer, then the reference's arithmetic
+        preds, gt, valid_subset = preds.cpu(), gt.cpu().to(torch.int64), valid_subset.cpu()
+        pix2mm_x, pix2mm_y = pix2mm_x.detach().cpu().float(), pix2mm_y.detach().cpu().float()
+        num_valid = torch.sum(valid_subset, dim=0, keepdim=True)
+        for k, name in enumerate(_NAMES):
+            self.valid_errors[name].append((num_valid[0, k] > 0).item())
+        num_valid[num_valid == 0] = 1
+        gt_h, gt_w = gt[:, :, 0], gt[:, :, 1]
+        preds_h, preds_w = preds[:, :, 0], preds[:, :, 1]
+        err = self.get_pixel_length(gt_w, gt_h, preds_w, preds_h, pix2mm_x.unsqueeze(1), pix2mm_y.unsqueeze(1)).numpy()
+        err *= valid_subset.numpy()
+        err = np.squeeze(np.sum(err, axis=0) / num_valid.numpy())
+        for k, name in enumerate(_NAMES):
+            self.coordinate_errors[name].append(err[k])
+        widths = self.calculate_widths(preds, gt, pix2mm_x, pix2mm_y)
+        scale = {'lvid': valid_subset[:, 0] * valid_subset[:, 1] / torch.min(num_valid[0, 0], num_valid[0, 1]),
+                 'ivs': valid_subset[:, 3] / num_valid[0, 3], 'lvpw': valid_subset[:, 2] / num_valid[0, 2]}
+        ivs, lvid, lvpw = self.calculate_width_MAE(widths)
+        for k, e in (('ivs', ivs), ('lvid', lvid), ('lvpw', lvpw)):
+            self.width_MAE[k].append((e * scale[k]).sum().item())
+        ivs, lvid, lvpw = self.calculate_width_MPE(widths)
+        for k, e in (('ivs', ivs), ('lvid', lvid), ('lvpw', lvpw)):
+            self.width_MPE[k].append((e * scale[k]).sum().item())
+        coordinates = {'pred_ivs': preds[:, 3], 'pred_lvid_top': preds[:, 0], 'pred_lvid_bot': preds[:, 1],
+                       'pred_lvpw': preds[:, 2], 'gt_ivs': gt[:, 3], 'gt_lvid_top': gt[:, 0],
+                       'gt_lvid_bot': gt[:, 1], 'gt_lvpw': gt[:, 2]}
+        self.detailed_performance = {'widths': widths, 'coordinates': coordinates}
+
+    def calculate_widths(self, preds, gt, pix2mm_x, pix2mm_y):
+        gt = gt.to(preds.dtype)
+        pl = self.get_pixel_length
+        return {"pred_ivs_mm": pl(preds[:, 3, 1], preds[:, 3, 0], preds[:, 0, 1], preds[:, 0, 0], pix2mm_x, pix2mm_y),
+                "pred_lvid_mm": pl(preds[:, 0, 1], preds[:, 0, 0], preds[:, 1, 1], preds[:, 1, 0], pix2mm_x, pix2mm_y),
+                "pred_lvpw_mm": pl(preds[:, 1, 1], preds[:, 1, 0], preds[:, 2, 1], preds[:, 2, 0], pix2mm_x, pix2mm_y),
+                "gt_ivs_mm": pl(gt[:, 3, 1], gt[:, 3, 0], gt[:, 0, 1], gt[:, 0, 0], pix2mm_x, pix2mm_y),
+                "gt_lvid_mm": pl(gt[:, 0, 1], gt[:, 0, 0], gt[:, 1, 1], gt[:, 1, 0], pix2mm_x, pix2mm_y),
+                "gt_lvpw_mm": pl(gt[:, 1, 1], gt[:, 1, 0], gt[:, 2, 1], gt[:, 2, 0], pix2mm_x, pix2mm_y)}
+
+    @staticmethod
+    def calculate_width_MAE(widths):
+        return (torch.abs(widths['pred_ivs_mm'] - widths['gt_ivs_mm']),
+                torch.abs(widths['pred_lvid_mm'] - widths['gt_lvid_mm']),
+                torch.abs(widths['pred_lvpw_mm'] - widths['gt_lvpw_mm']))
+
+    @staticmethod
+    def calculate_width_MPE(widths):
+        return (100 * torch.abs(widths['pred_ivs_mm'] - widths['gt_ivs_mm']) / widths['gt_ivs_mm'],
+                100 * torch.abs(widths['pred_lvid_mm'] - widths['gt_lvid_mm']) / widths['gt_lvid_mm'],
+                100 * torch.abs(widths['pred_lvpw_mm'] - widths['gt_lvpw_mm']) / widths['gt_lvpw_mm'])
+
+    def compute(self):
+        v = {k: np.asarray(self.valid_errors[k]) for k in self.valid_errors}
+        both = np.logical_and(v['lvid_top'], v['lvid_bot'])
+        temp = {k: np.asarray(self.coordinate_errors[k]).sum() / np.count_nonzero(v[k]) for k in _NAMES}
+        temp['ivs_w'] = np.asarray(self.width_MAE['ivs']).sum() / np.count_nonzero(v['ivs'])
+        temp['lvid_w'] = np.asarray(self.width_MAE['lvid']).sum() / np.count_nonzero(both)
+        temp['lvpw_w'] = np.asarray(self.width_MAE['lvpw']).sum() / np.count_nonzero(v['lvpw'])
+        temp['ivs_mpe'] = np.asarray(self.width_MPE['ivs']).sum() / np.count_nonzero(v['ivs'])
+        temp['lvid_mpe'] = np.asarray(self.width_MPE['lvid']).sum() / np.count_nonzero(both)
+        temp['lvpw_mpe'] = np.asarray(self.width_MPE['lvpw']).sum() / np.count_nonzero(v['lvpw'])
+        return temp
+
+    def get_sum_of_width_MAE(self):
+        temp = self.compute()
+        return sum(value for k, value in temp.items() if k in ['ivs_w', 'lvid_w', 'lvpw_w'])
+
+    def get_sum_of_width_MPE(self):
+        temp = self.compute()
+        return sum(value for k, value in temp.items() if k in ['ivs_mpe', 'lvid_mpe', 'lvpw_mpe'])
+
+    def get_last(self):
+        temp = {k: self.coordinate_errors[k][-1] for k in _NAMES}
+        for k in ('ivs', 'lvid', 'lvpw'):
+            temp[k + '_w'] = self.width_MAE[k][-1]
+        for k in ('ivs', 'lvid', 'lvpw'):
+            temp[k + '_mpe'] = self.width_MPE[k][-1]
+        return temp
+
+    def get_predictions(self):
+        return self.detailed_performance

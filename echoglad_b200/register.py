@@ -9,6 +9,7 @@ src/builders/criterion_builder.py:6-35) construct them from an unmodified config
 from __future__ import annotations
 
 from .criterion import ExpectedLandmarkMSE, WeightedBCEWithLogitsLoss
+from .evaluator import LandmarkExpectedCoordiantesEvaluator
 from .modules import HierarchicalPatchModel, UNETHierarchicalPatchModel
 
 MODEL_KEYS = {
@@ -19,9 +20,14 @@ CRITERION_KEYS = {
     'WeightedBceWithLogits': WeightedBCEWithLogitsLoss,
     'ExpectedLandmarkMse': ExpectedLandmarkMSE,
 }
+EVALUATOR_KEYS = {
+    'landmarkcoorderror': LandmarkExpectedCoordiantesEvaluator,  # src/builders/evaluator_builder.py:9
+}
 
 
-def patch(models: dict, criteria: dict) -> None:
+def patch(models: dict, criteria: dict, evaluators: dict = None) -> None:
     """Overwrites the hot-path entries of the reference registries in place; everything else is untouched."""
     models.update(MODEL_KEYS)
     criteria.update(CRITERION_KEYS)
+    if evaluators is not None:
+        evaluators.update(EVALUATOR_KEYS)

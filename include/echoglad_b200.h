@@ -210,6 +210,15 @@ int eg_expected_landmark_mse(int batch, int channels, int num_levels, const int3
 int eg_node_labels(int batch, int channels, int frame_size, int num_levels, const int32_t* level_size,
                    const int32_t* coords, float* y, void* stream);
 
+/* ---- post-path metric: expected landmark coordinates (src/core/evaluators.py:310-348) ----------------
+ * On the main level (the last frame_size^2 of the nodes_per_frame pixel nodes of every frame): softmax over the
+ * nodes of each of the 4 channels and its expected (h, w) -> pred_hw float[batch,4,2]; position of the label heat
+ * map maximum (first maximum along each axis, as torch.max) -> gt_hw int32[batch,4,2]; mean of `valid` (NULL =
+ * all valid) -> valid_mean float[batch,4].  logits / y / valid: DEVICE float[batch*nodes_per_frame, 4]. */
+int eg_expected_coords(int batch, int channels, int nodes_per_frame, int frame_size, const float* logits,
+                       const float* y, const float* valid, float* pred_hw, int32_t* gt_hw, float* valid_mean,
+                       void* stream);
+
 /* ---- measurement hooks (no reference counterpart) ---------------------------------------------------
  * eg_profile_enable(1) clears and starts recording CUDA-event spans around every launch helper on the
  * caller's stream; eg_profile_read sums the device time and span count recorded under `name`

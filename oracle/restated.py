@@ -568,3 +568,57 @@ def clone_state(sd: Dict[str, Tensor], requires_grad: bool = False) -> Dict[str,
             t.requires_grad_(True)
         out[k] = t
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# post-path metric: LandmarkExpectedCoordiantesEvaluator (src/core/evaluators.py:239-483), SURVEY.md §8(f) row 4
+# ---------------------------------------------------------------------------------------------------------
+
+def expected_coords(logits: Tensor, y: Tensor, valid: Tensor, batch: int, frame: int):
+    """src/core/evaluators.py:310-348: on the main level (the last frame^2 nodes of every frame) the softmax over
+    the nodes of each channel, its expected (h, w), the arg-max position of the label heat map (first maximum
+    along each axis) and the mean of `valid`.  Returns preds[B,4,2], gt[B,4,2] (int64), valid_subset[B,4]."""
+    c = logits.shape[-1]
+    yp = logits.view(batch, -1, c).detach()[:, -frame * frame:, :]
+    yt = y.view(batch, -1, c).detach()[:, -frame * frame:, :].view(batch, frame, frame, c)
+    vs = valid.view(batch, -1, c)[:, -frame * frame:, :].permute(0, 2, 1).mean(dim=-1)
+    max_along_w, _ = torch.max(yt, dim=-2)
+    max_along_h, _ = torch.max(yt, dim=-3)
+    _, gt_h = torch.max(max_along_w, dim=-2)
+    _, gt_w = torch.max(max_along_h, dim=-2)
+    gt = torch.cat((gt_h.unsqueeze(2), gt_w.unsqueeze(2)), dim=2)
+    heat = torch.softmax(yp, dim=1).view(batch, frame, frame, c)
+    line = torch.linspace(0, frame - 1, frame)
+    ph = torch.sum(heat * line.view(1, -1, 1, 1), dim=(1, 2))
+    pw = torch.sum(heat * line.view(1, 1, -1, 1), dim=(1, 2))
+    return torch.cat((ph.unsqueeze(2), pw.unsqueeze(2)), dim=2), gt, vs
+
+
+def expected_coord_metrics(preds: Tensor, gt: Tensor, valid_subset: Tensor, pix2mm_x: Tensor, pix2mm_y: Tensor) -> dict:
+    """src/core/evaluators.py:350-391,395-428: per-landmark errors in mm and width MAE / MPE of one batch, from the
+    [B,4,2] coordinates.  Landmark order lvid_top, lvid_bot, lvpw, ivs.  Returns the values `get_last()` reports
+    plus 'valid' (4 bools) and the width dictionary."""
+    def plen(x0, y0, x1, y1, mx, my):
+        return torch.sqrt(((x0 - x1) * mx) ** 2 + ((y0 - y1) * my) ** 2)
+
+    gt = gt.to(preds.dtype)
+    nvs = valid_subset.sum(dim=0, keepdim=True)
+    valid_flags = [(nvs[0, k] > 0).item() for k in range(4)]
+    nvs = nvs.clone()
+    nvs[nvs == 0] = 1
+    err = plen(gt[:, :, 1], gt[:, :, 0], preds[:, :, 1], preds[:, :, 0], pix2mm_x.unsqueeze(1), pix2mm_y.unsqueeze(1))
+    err = (err * valid_subset).sum(dim=0) / nvs[0]
+    w = {}
+    for tag, t in (("pred", preds), ("gt", gt)):
+        w[f"{tag}_ivs_mm"] = plen(t[:, 3, 1], t[:, 3, 0], t[:, 0, 1], t[:, 0, 0], pix2mm_x, pix2mm_y)
+        w[f"{tag}_lvid_mm"] = plen(t[:, 0, 1], t[:, 0, 0], t[:, 1, 1], t[:, 1, 0], pix2mm_x, pix2mm_y)
+        w[f"{tag}_lvpw_mm"] = plen(t[:, 1, 1], t[:, 1, 0], t[:, 2, 1], t[:, 2, 0], pix2mm_x, pix2mm_y)
+    out = {"lvid_top": err[0].item(), "lvid_bot": err[1].item(), "lvpw": err[2].item(), "ivs": err[3].item(),
+           "valid": valid_flags, "widths": w}
+    scale = {"lvid": valid_subset[:, 0] * valid_subset[:, 1] / torch.min(nvs[0, 0], nvs[0, 1]),
+             "ivs": valid_subset[:, 3] / nvs[0, 3], "lvpw": valid_subset[:, 2] / nvs[0, 2]}
+    for k in ("ivs", "lvid", "lvpw"):
+        d = torch.abs(w[f"pred_{k}_mm"] - w[f"gt_{k}_mm"])
+        out[f"{k}_w"] = (d * scale[k]).sum().item()
+        out[f"{k}_mpe"] = (100 * d / w[f"gt_{k}_mm"] * scale[k]).sum().item()
+    return out

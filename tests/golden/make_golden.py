@@ -219,6 +219,52 @@ def make_models(skip_big: bool):
     print("default.yml B=1", float(o["loss_bce"]), float(o["loss_elmse"]), f"{time.time() - t:.1f}s", flush=True)
 
 
+def make_evaluator():
+    """LandmarkExpectedCoordiantesEvaluator.update / compute (src/core/evaluators.py:291-391,430-449) run by the
+    reference's own class on seeded logits / labels / valid masks: two batches per case, the second with one
+    landmark invalid in one frame and one landmark invalid in all frames."""
+    import importlib
+    from oracle import ref_shim
+    ref_shim.load()
+    ev_mod = importlib.import_module("src.core.evaluators")
+    out = {}
+    for name, (frame, naux, batch) in {"S16_n3_B3": (16, 3, 3), "S28_n4_B2": (28, 4, 2)}.items():
+        ev = ev_mod.LandmarkExpectedCoordiantesEvaluator(logger=None, batch_size=batch, frame_size=frame,
+                                                         use_coord_graph=False)
+        n0 = sum(4 ** k for k in range(1, naux + 1)) + frame * frame
+        gen = torch.Generator().manual_seed(frame)
+        for step in range(2):
+            rng = np.random.default_rng(100 * frame + step)
+            coords = rng.integers(0, frame, size=(batch, 4, 2))
+            y = torch.cat([R.node_labels(c, frame, naux) for c in coords], dim=0)
+            logits = torch.randn(batch * n0, 4, generator=gen) * 3.0
+            valid = torch.ones(batch, n0, 4)
+            if step == 1:
+                valid[0, :, 1] = 0.0
+                valid[:, :, 2] = 0.0
+            valid = valid.view(batch * n0, 4)
+            px = torch.rand(batch, generator=gen) + 0.5
+            py = torch.rand(batch, generator=gen) + 0.5
+            ev.update(logits, y, px, py, valid)
+            pre = f"{name}/step{step}/"
+            out[pre + "logits"] = logits.numpy()
+            out[pre + "coords"] = coords
+            out[pre + "valid"] = valid.numpy()
+            out[pre + "pix2mm_x"] = px.numpy()
+            out[pre + "pix2mm_y"] = py.numpy()
+            last = ev.get_last()
+            for k, v in last.items():
+                out[pre + "last/" + k] = np.float64(v)
+            for k, v in ev.detailed_performance["coordinates"].items():
+                out[pre + "coord/" + k] = v.numpy()
+            for k, v in ev.detailed_performance["widths"].items():
+                out[pre + "width/" + k] = v.numpy()
+        for k, v in ev.compute().items():
+            out[f"{name}/compute/{k}"] = np.float64(v)
+    np.savez_compressed(os.path.join(HERE, "evaluator_expected_coords.npz"), **out)
+    print("evaluator", len(out), "arrays", flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-big", action="store_true")
@@ -232,3 +278,5 @@ if __name__ == "__main__":
         make_labels()
     if a.only in ("", "models"):
         make_models(a.skip_big)
+    if a.only in ("", "evaluator"):
+        make_evaluator()

@@ -481,6 +481,49 @@ def test_unet_module_fused_embed_equals_unfused_route():
     assert not bad, bad
 
 
+def test_expected_coordinate_evaluator_matches_reference_golden():
+    """Device evaluator (eg_expected_coords + the [B,4] arithmetic) against values minted by the reference's own
+    LandmarkExpectedCoordiantesEvaluator: per-batch `get_last()`, predicted coordinates, widths and the
+    accumulated `compute()`.  Tolerance 1e-4 relative (fp32 softmax over up to 784 nodes)."""
+    z = np.load(os.path.join(GOLDEN, "evaluator_expected_coords.npz"))
+    for name, (frame, naux, batch) in {"S16_n3_B3": (16, 3, 3), "S28_n4_B2": (28, 4, 2)}.items():
+        ev = eg.LandmarkExpectedCoordiantesEvaluator(logger=None, batch_size=batch, frame_size=frame, use_coord_graph=False)
+        for step in range(2):
+            pre = f"{name}/step{step}/"
+            y = torch.cat([R.node_labels(c, frame, naux) for c in z[pre + "coords"]], dim=0)
+            ev.update(torch.from_numpy(z[pre + "logits"]).to(DEV), y.to(DEV), torch.from_numpy(z[pre + "pix2mm_x"]).to(DEV),
+                      torch.from_numpy(z[pre + "pix2mm_y"]).to(DEV), torch.from_numpy(z[pre + "valid"]).to(DEV))
+            last = ev.get_last()
+            for k, v in last.items():
+                want = float(z[pre + "last/" + k])
+                assert abs(v - want) <= 1e-4 * max(abs(want), 1.0), (name, step, k, v, want)
+            perf = ev.get_predictions()
+            for k, v in perf["coordinates"].items():
+                assert np.allclose(v.numpy(), z[pre + "coord/" + k], rtol=1e-4, atol=1e-4), k
+            for k, v in perf["widths"].items():
+                assert np.allclose(v.numpy(), z[pre + "width/" + k], rtol=1e-4, atol=1e-4), k
+        for k, v in ev.compute().items():
+            want = float(z[f"{name}/compute/{k}"])
+            assert abs(v - want) <= 1e-4 * max(abs(want), 1.0), (name, k, v, want)
+
+
+def test_expected_coords_default_size_against_oracle():
+    """default.yml size (224 x 224 main level, batch 3): device softmax moments / arg-max / valid means vs the oracle."""
+    frame, naux, batch = 224, 7, 3
+    _, coords, y, valid = R.synthetic_batch(batch, frame, naux, seed=5)
+    valid = valid.clone().view(batch, -1, 4)
+    valid[1, :, 3] = 0.0
+    valid = valid.view(-1, 4)
+    logits = torch.randn(y.shape, generator=torch.Generator().manual_seed(6)) * 4.0
+    from echoglad_b200.evaluator import expected_coords
+    preds, gt, vs = expected_coords(logits.to(DEV), y.to(DEV), valid.to(DEV), batch, frame)
+    wp, wg, wv = R.expected_coords(logits, y, valid, batch, frame)
+    assert torch.equal(gt.cpu().to(torch.int64), wg)
+    assert torch.equal(wg, coords.to(torch.int64))
+    assert torch.allclose(preds.cpu(), wp, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(vs.cpu(), wv, rtol=0, atol=1e-6)
+
+
 # ---- whole module against the reference's golden vectors ----------------------------------------------------------
 
 def _build_module(cfg, variant):

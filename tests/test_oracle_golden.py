@@ -120,3 +120,29 @@ def test_default_yml_full_graph_matches_reference():
     want = {k[5:]: z[k] for k in z.files if k.startswith("grad/")}
     bad = grads_close({k: sd[k].grad for k in want}, want)
     assert not bad, bad
+
+
+def _evaluator_cases():
+    z = np.load(os.path.join(GOLDEN, "evaluator_expected_coords.npz"))
+    cases = {"S16_n3_B3": (16, 3, 3), "S28_n4_B2": (28, 4, 2)}
+    return z, cases
+
+
+def test_expected_coordinate_evaluator_restatement_matches_reference_golden():
+    """oracle `expected_coords` + `expected_coord_metrics` against values minted by the reference's own
+    LandmarkExpectedCoordiantesEvaluator (src/core/evaluators.py:291-391), incl. invalid landmarks."""
+    z, cases = _evaluator_cases()
+    for name, (frame, naux, batch) in cases.items():
+        for step in range(2):
+            pre = f"{name}/step{step}/"
+            logits = torch.from_numpy(z[pre + "logits"])
+            valid = torch.from_numpy(z[pre + "valid"])
+            y = torch.cat([R.node_labels(c, frame, naux) for c in z[pre + "coords"]], dim=0)
+            preds, gt, vs = R.expected_coords(logits, y, valid, batch, frame)
+            assert np.array_equal(gt.numpy(), z[pre + "coords"])  # arg-max of a one-hot map is the landmark pixel
+            got = R.expected_coord_metrics(preds, gt, vs, torch.from_numpy(z[pre + "pix2mm_x"]),
+                                           torch.from_numpy(z[pre + "pix2mm_y"]))
+            for k in ("lvid_top", "lvid_bot", "lvpw", "ivs", "ivs_w", "lvid_w", "lvpw_w", "ivs_mpe", "lvid_mpe", "lvpw_mpe"):
+                want = float(z[pre + "last/" + k])
+                assert abs(got[k] - want) <= 1e-5 * max(abs(want), 1.0), (name, step, k, got[k], want)
+            assert np.allclose(preds[:, 3].numpy(), z[pre + "coord/pred_ivs"], rtol=1e-5, atol=1e-5)
