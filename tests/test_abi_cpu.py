@@ -161,3 +161,28 @@ def test_registry_patch_replaces_only_hot_path_entries(eg):
     c = criteria['ExpectedLandmarkMse'](batch_size=2, frame_size=224, num_aux_graphs=7, use_main_graph_only=False,
                                         num_output_channels=4, loss_weight=10)
     assert c.grid_sizes == [2, 4, 8, 16, 32, 64, 128, 224]
+
+
+def test_argument_validation_happens_before_any_cuda_call(eg):
+    """Entry points reject malformed calls with EG_ERR_INVALID and a message from eg_last_error(), without
+    touching the (absent) GPU: NULL pointers, unsupported channel counts, evaluator shapes."""
+    lib = eg.lib
+    assert lib.eg_level_embed_fwd(None, 1, 0, 4, None, None, None, None, None) < 0
+    assert b"eg_level_embed_fwd" in lib.eg_last_error()
+    assert lib.eg_level_embed_supported(None, 0, 4) == 0
+    assert lib.eg_expected_coords(2, 3, 100, 4, 1, 1, None, 1, 1, 1, None) < 0  # 3 channels
+    assert b"4 landmark channels" in lib.eg_last_error()
+    assert lib.eg_expected_coords(2, 4, 10, 4, 1, 1, None, 1, 1, 1, None) < 0   # frame^2 > nodes per frame
+    assert lib.eg_linear128_wgrad(0, None, None, None, None, None, 0, None) < 0
+    assert lib.eg_gcn_conv_fwd(None, 1, None, None, None, None, None, None, None, 0, None) < 0
+
+
+def test_registry_patch_with_evaluators(eg):
+    from echoglad_b200 import register
+    models, criteria, evaluators = {}, {}, {'accuracy': object, 'landmarkcoorderror': object}
+    register.patch(models, criteria, evaluators)
+    assert evaluators['landmarkcoorderror'] is eg.LandmarkExpectedCoordiantesEvaluator and evaluators['accuracy'] is object
+    ev = evaluators['landmarkcoorderror'](logger=None, batch_size=2, frame_size=224, use_coord_graph=False)
+    assert set(ev.coordinate_errors) == {'ivs', 'lvid_top', 'lvid_bot', 'lvpw'} and ev.get_predictions() == {}
+    with pytest.raises(eg.EchogladError, match="no CPU fallback"):
+        ev.update(torch.zeros(8, 4), torch.zeros(8, 4), torch.ones(2), torch.ones(2), torch.ones(8, 4))
