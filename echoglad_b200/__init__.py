@@ -3,7 +3,7 @@
 Importing the package loads libechoglad_b200.so; there is no CPU or eager fallback.
 """
 from ._lib import EchogladError, lib  # noqa: F401  (fails loudly when the CUDA library is missing)
-from .criterion import ExpectedLandmarkMSE, WeightedBCEWithLogitsLoss  # noqa: F401
+from .criterion import MAE, ExpectedLandmarkMSE, WeightedBCEWithLogitsLoss  # noqa: F401
 from .evaluator import LandmarkExpectedCoordiantesEvaluator  # noqa: F401
 from .graph import DeviceGraph, GraphMeta, HierGraphSpec  # noqa: F401
 from .modules import CNN, HierarchicalPatchModel, UNETHierarchicalPatchModel  # noqa: F401

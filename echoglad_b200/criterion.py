@@ -41,3 +41,15 @@ class ExpectedLandmarkMSE(object):
     def compute(self, pred_y, y, valid):
         return ops.ExpectedLandmarkMSEFn.apply(pred_y, y, valid, int(self.batch_size), int(self.num_output_channels),
                                                tuple(self.grid_sizes), float(self.loss_weight))
+
+
+class MAE(object):
+    """CRITERIA['mae'] = the 'coordinate' loss of `use_coordinate_graph` (src/core/criterion.py:52-64,
+    src/builders/criterion_builder.py:40-41): loss_weight * mean |pred - y| over the [4B, 2] coordinates.  Eight
+    numbers per frame: plain torch on the device tensors (nothing to fuse)."""
+
+    def __init__(self, loss_weight=1):
+        self.loss_weight = loss_weight
+
+    def compute(self, pred_y, y):
+        return self.loss_weight * (pred_y - y.to(pred_y.dtype)).abs().mean()

@@ -42,7 +42,8 @@ class LandmarkExpectedCoordiantesEvaluator(object):
 
     def __init__(self, logger=None, batch_size=2, frame_size=224, use_coord_graph=False):
         if use_coord_graph:
-            raise NotImplementedError("use_coordinate_graph=True is not built (SURVEY.md §8(f) row 3)")
+            raise NotImplementedError("the reference evaluator itself raises NameError with use_coord_graph=True "
+                                      "(valid_subset undefined, src/core/evaluators.py:302-309,356); heat-map mode only")
         self.batch_size = batch_size
         self.frame_size = frame_size
         self.use_coord_graph = use_coord_graph

@@ -67,6 +67,23 @@ def _update_running(bn: nn.BatchNorm1d, mean: torch.Tensor, var: torch.Tensor, n
 # landmark model
 # ---------------------------------------------------------------------------------------------------------
 
+class _GatherRows(torch.autograd.Function):
+    """rows[idx] for a handful of rows of a large [R, C] tensor.  Unlike torch.gather / index_select it saves only
+    the indices, so the source may be updated in place afterwards (the coordinate rows of the same tensor are,
+    src/core/models.py:473)."""
+
+    @staticmethod
+    def forward(ctx, rows, idx):
+        ctx.save_for_backward(idx)
+        ctx.shape = rows.shape
+        return rows.index_select(0, idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        return torch.zeros(ctx.shape, dtype=g.dtype, device=g.device).index_add_(0, idx, g), None
+
+
 class HierarchicalPatchModel(nn.Module):
     """Base landmark model: average-pooled pyramid of the embedder output as node features."""
 
@@ -100,8 +117,6 @@ class HierarchicalPatchModel(nn.Module):
             raise NotImplementedError(
                 "echoglad_b200 classifier kernels are built for num_output_channels == 4 (src/engine.py:92) and "
                 f"classifier_hidden_dim == 32 (configs/default.yml:16); got {num_output_channels}/{classifier_hidden_dim}")
-        if use_coordinate_graph and not use_main_graph_only:
-            raise NotImplementedError("use_coordinate_graph=True is not built yet (SURVEY.md §8(f) row 3)")
         if gnn_jk_mode == 'cat':
             raise NotImplementedError("gnn_jk_mode='cat' feeds (L+1)*128 features into Linear(128, .) and fails in "
                                       "the reference as well (src/core/models.py:364,479-482)")
@@ -109,7 +124,15 @@ class HierarchicalPatchModel(nn.Module):
         self.gnn_layers = nn.ModuleList(
             _GNNBlock(node_embedding_dim if i == 0 else node_hidden_dim, node_hidden_dim, gnn_dropout_p,
                       relu=(i != num_gnn_layers - 1)) for i in range(num_gnn_layers))
+        # coordinate regressors, one per GNN layer (src/core/models.py:337-350); same Sequential indices -> same keys
         self.node_coordinate_mlp = nn.ModuleList()
+        if use_coordinate_graph:
+            ch = classifier_hidden_dim
+            for _ in range(num_gnn_layers):
+                self.node_coordinate_mlp.append(nn.Sequential(
+                    nn.Linear(node_hidden_dim + 8, ch), nn.BatchNorm1d(ch), nn.ReLU(inplace=True),
+                    nn.Dropout(p=classifier_dropout_p), nn.Linear(ch, ch // 2), nn.BatchNorm1d(ch // 2),
+                    nn.ReLU(inplace=True), nn.Dropout(p=classifier_dropout_p), nn.Linear(ch // 2, 2), nn.Identity()))
         self.output_activation = output_activation
         last = nn.Sigmoid() if output_activation == 'sigmoid' else nn.Identity()
         h = classifier_hidden_dim
@@ -150,10 +173,34 @@ class HierarchicalPatchModel(nn.Module):
         """[B, naux+1, 128]: the frame mean repeated (base variant, src/core/models.py:531-534)."""
         return maps[-1].mean(dim=(2, 3)).unsqueeze(1).repeat(1, self.num_aux_graphs + 1, 1)
 
-    def create_node_pixels(self, x: torch.Tensor, graph: DeviceGraph) -> torch.Tensor:
+    def bilinear_rows(self, coords: torch.Tensor, rows: torch.Tensor, frame_stride: int, offset: int) -> torch.Tensor:
+        """`bilinear_interpolation` (src/core/models.py:539-553) on node-major features: coords [B,4,2] (h, w);
+        rows [R, C] holds the row-major main grid of frame b at rows [b*frame_stride + offset, + S*S) -> [B,4,C].
+        The reference multiplies a dense [4,S,S] tent-weight map into the [C,S,S] frame; the tent
+        `relu(1 - |c - g|)` is non-zero on at most two grid lines per axis, so only those 4 taps are gathered (same
+        weights, same sub-gradient at the kinks: they come from the same formula through autograd)."""
+        s = self.frame_size
+        b = coords.shape[0]
+        base = torch.floor(coords.detach()).clamp_(0, s - 1)                  # [B,4,2] first grid line per axis
+        lines = torch.stack((base, (base + 1).clamp_(max=s - 1)), dim=-1)      # [B,4,2(axis),2(tap)]
+        w = TF.relu(1 - (coords.unsqueeze(-1) - lines).abs())                   # tent weights of the taps
+        # when the second tap was clamped onto the first (coordinate exactly S-1) it duplicates it: drop it
+        w = w * torch.stack((torch.ones_like(base), (base + 1 <= s - 1).to(w.dtype)), dim=-1)
+        idx = (lines[:, :, 0, :, None] * s + lines[:, :, 1, None, :]).long().view(b, 16)    # [B, 4 landmarks x 4 taps]
+        idx = idx + (torch.arange(b, device=idx.device) * frame_stride + offset).unsqueeze(1)
+        taps = _GatherRows.apply(rows, idx.reshape(-1)).view(b, 4, 4, -1)
+        wt = (w[:, :, 0, :, None] * w[:, :, 1, None, :]).view(b, 4, 4, 1)
+        return (taps * wt).sum(dim=2)
+
+    def create_node_pixels(self, x: torch.Tensor, graph: DeviceGraph, node_coords=None) -> torch.Tensor:
         maps = self.pyramid(x)
         head = self.connection_rows(maps) if graph.meta.first_pixel_node else None
-        return ops.PackNodes.apply(graph, head, None, *maps)
+        tail = None
+        if self.use_coordinate_graph:  # coordinate nodes start as the interpolated main-level features (:526-527)
+            m = maps[-1]
+            s2 = m.shape[2] * m.shape[3]
+            tail = self.bilinear_rows(node_coords, m.permute(0, 2, 3, 1).reshape(-1, m.shape[1]), s2, 0)
+        return ops.PackNodes.apply(graph, head, tail, *maps)
 
     # -- forward ---------------------------------------------------------------------------------------------
     def forward(self, data_batch=None, x: torch.Tensor = None, node_coords: torch.Tensor = None,
@@ -166,19 +213,45 @@ class HierarchicalPatchModel(nn.Module):
         graph = DeviceGraph.get(self.graph_spec, x.device)
         graph.validate_edge_index_once(edge_index, batch)
 
-        feats = self.create_node_pixels(x.float(), graph)
-        h = self.gnn_stack(feats, graph, batch)
+        coords = None
+        if self.use_coordinate_graph:
+            if node_coords is None and data_batch is not None:
+                node_coords = data_batch.node_coords
+            if node_coords is None:
+                raise EchogladError("use_coordinate_graph=True needs node_coords [4*B, 2]")
+            coords = node_coords.to(torch.float32).reshape(batch, 4, 2)  # not modified in place (the reference does)
+            feats = self.create_node_pixels(x.float(), graph, coords)
+            h, coords = self.gnn_stack(feats, graph, batch, coords)
+        else:
+            feats = self.create_node_pixels(x.float(), graph)
+            h = self.gnn_stack(feats, graph, batch)
         if graph.meta.num_pixel_nodes != graph.meta.num_nodes:  # drop connection / coordinate rows
             a = graph.meta.first_pixel_node
             h = h.view(batch, graph.meta.num_nodes, F)[:, a:a + graph.meta.num_pixel_nodes].reshape(-1, F)
         out = self.classify(h)
         self._step += 1
-        return out.squeeze(1), None
+        return out.squeeze(1), (None if coords is None else coords.reshape(batch * 4, 2))
 
     def _seed(self, salt: int) -> int:
         return (self.dropout_seed * 0x9E3779B1 + self._step * 1000003 + salt * 7919) & 0x7FFFFFFFFFFFFFFF
 
-    def gnn_stack(self, feats: torch.Tensor, graph: DeviceGraph, batch: int) -> torch.Tensor:
+    def update_coordinates(self, i: int, y: torch.Tensor, coords: torch.Tensor, graph: DeviceGraph, batch: int):
+        """Coordinate update after GNN layer i (src/core/models.py:438-473): relative-position features + the
+        coordinate nodes' embeddings -> MLP -> delta; clamp; the coordinate nodes' embeddings are re-sampled from the
+        main-level rows of `y` at the new coordinates and written back in place (4 rows per frame)."""
+        meta = graph.meta
+        s = self.frame_size
+        yv = y.view(batch, meta.num_nodes, F)
+        c0 = meta.num_nodes - meta.num_coord_nodes
+        m0 = meta.first_pixel_node + meta.num_pixel_nodes - s * s
+        rel = -(coords.unsqueeze(2) - coords.unsqueeze(1)).reshape(batch * 4, 8)
+        delta = self.node_coordinate_mlp[i](torch.cat((yv[:, c0:, :].reshape(batch * 4, F), rel), dim=1))
+        coords = torch.clamp(coords + delta.view(batch, 4, 2), min=0, max=s - 1)
+        new = self.bilinear_rows(coords, y, meta.num_nodes, m0)
+        yv[:, c0:, :] = new
+        return y, coords
+
+    def gnn_stack(self, feats: torch.Tensor, graph: DeviceGraph, batch: int, coords: torch.Tensor = None):
         hidden = [feats]
         rows = feats.shape[0]
         for i, blk in enumerate(self.gnn_layers):
@@ -190,13 +263,16 @@ class HierarchicalPatchModel(nn.Module):
                 blk.dropout_p if self.training else 0.0, self._seed(i), blk.relu, bool(self.residual))
             if self.training and bn.track_running_stats:
                 _update_running(bn, mean, var, rows)
+            if coords is not None:
+                y, coords = self.update_coordinates(i, y, coords, graph, batch)
             hidden.append(y)
         if self.gnn_jk_mode == 'max':
             out = hidden[0]
             for t in hidden[1:]:
                 out = torch.maximum(out, t)
-            return out
-        return hidden[-1]
+        else:
+            out = hidden[-1]
+        return out if coords is None else (out, coords)
 
     def classify(self, h: torch.Tensor) -> torch.Tensor:
         clf = self.node_classifiers

@@ -8,7 +8,7 @@ src/builders/criterion_builder.py:6-35) construct them from an unmodified config
 """
 from __future__ import annotations
 
-from .criterion import ExpectedLandmarkMSE, WeightedBCEWithLogitsLoss
+from .criterion import MAE, ExpectedLandmarkMSE, WeightedBCEWithLogitsLoss
 from .evaluator import LandmarkExpectedCoordiantesEvaluator
 from .modules import HierarchicalPatchModel, UNETHierarchicalPatchModel
 
@@ -19,6 +19,7 @@ MODEL_KEYS = {
 CRITERION_KEYS = {
     'WeightedBceWithLogits': WeightedBCEWithLogitsLoss,
     'ExpectedLandmarkMse': ExpectedLandmarkMSE,
+    'mae': MAE,  # the 'coordinate' loss (src/builders/criterion_builder.py:40-41)
 }
 EVALUATOR_KEYS = {
     'landmarkcoorderror': LandmarkExpectedCoordiantesEvaluator,  # src/builders/evaluator_builder.py:9

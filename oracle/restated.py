@@ -367,12 +367,32 @@ def pack_nodes(cfg: Cfg, maps: List[Tensor], node_coords: Optional[Tensor] = Non
     return torch.cat(rows, dim=0)
 
 
+def coordinate_mlp(sd, cfg: Cfg, i: int, feats: Tensor, training: bool) -> Tensor:
+    """node_coordinate_mlp[i] (src/core/models.py:337-350): Linear(136,32)-BN-ReLU-Drop-Linear(32,16)-BN-ReLU-Drop-
+    Linear(16,2)."""
+    p = f"node_coordinate_mlp.{i}."
+    z = F.linear(feats, sd[p + "0.weight"], sd[p + "0.bias"])
+    z = F.dropout(F.relu(_bn(sd, p + "1.", z, training)), cfg.classifier_dropout_p, training)
+    z = F.linear(z, sd[p + "4.weight"], sd[p + "4.bias"])
+    z = F.dropout(F.relu(_bn(sd, p + "5.", z, training)), cfg.classifier_dropout_p, training)
+    return F.linear(z, sd[p + "8.weight"], sd[p + "8.bias"])
+
+
 def gnn_stack(sd, cfg: Cfg, feats: Tensor, edge_index: Tensor, training: bool, masks=None,
-              return_hidden: bool = False):
-    """src/core/models.py:425-482 (coordinate branch excluded): L x [GCNConv -> BN -> Dropout ->
-    ReLU|Identity] + identity residual when widths match; JK last|max."""
+              return_hidden: bool = False, node_coords: Optional[Tensor] = None, node_type=None):
+    """src/core/models.py:425-482: L x [GCNConv -> BN -> Dropout -> ReLU|Identity] + identity residual when widths
+    match; with `use_coordinate_graph` the coordinate update of :438-473 after every layer (relative-position
+    features + the coordinate nodes' embeddings -> MLP -> coordinate delta, clamp, re-sample the coordinate
+    nodes' embeddings from the main-level rows of h); JK last|max.  node_coords: [B,4,2] (h, w), not modified;
+    with coordinates the result is (out, new_coords[B,4,2])."""
     hidden = [feats]
     L = cfg.num_gnn_layers
+    coords = node_coords
+    if cfg.use_coordinate_graph:
+        nt = torch.as_tensor(np.asarray(node_type))
+        coord_rows = torch.nonzero(nt == 1).squeeze(1)
+        pixel_rows = torch.nonzero(nt == 0).squeeze(1)
+        B, S = coords.shape[0], cfg.frame_size
     for i in range(L):
         p = f"gnn_layers.{i}."
         h = gcn_conv(hidden[i], edge_index, sd[p + "module_0.lin.weight"], sd[p + "module_0.bias"])
@@ -382,6 +402,14 @@ def gnn_stack(sd, cfg: Cfg, feats: Tensor, edge_index: Tensor, training: bool, m
             h = _relu(h, masks, f"gnn{i}")
         if cfg.residual and h.shape[1] == hidden[i].shape[1]:
             h = h + hidden[i]
+        if cfg.use_coordinate_graph:
+            rel = -(coords.unsqueeze(2) - coords.unsqueeze(1))          # [B,4,4,2]: -(c_j - c_k) per frame (:441-444)
+            shape_feats = rel.reshape(B * 4, 8)
+            delta = coordinate_mlp(sd, cfg, i, torch.cat((h[coord_rows], shape_feats), dim=1), training)
+            coords = torch.clamp(coords + delta.view(B, 4, 2), min=0, max=S - 1)
+            main = h[pixel_rows].view(B, -1, h.shape[1])[:, -S * S:, :].permute(0, 2, 1).reshape(B, -1, S, S)
+            new = torch.cat([bilinear_tent(coords[b], main[b]) for b in range(B)], dim=0)
+            h = h.index_copy(0, coord_rows, new)
         hidden.append(h)
     if cfg.gnn_jk_mode == "max":
         out = torch.stack(hidden, dim=-1).max(dim=-1)[0]
@@ -389,6 +417,8 @@ def gnn_stack(sd, cfg: Cfg, feats: Tensor, edge_index: Tensor, training: bool, m
         out = torch.cat(hidden, dim=-1)
     else:
         out = hidden[-1]
+    if cfg.use_coordinate_graph:
+        return out, coords
     return (out, hidden) if return_hidden else out
 
 
@@ -410,18 +440,31 @@ def classifiers(sd, cfg: Cfg, h: Tensor, training: bool, masks=None) -> Tensor:
 
 
 def landmark_forward(sd, cfg: Cfg, x: Tensor, edge_index: Tensor, node_type: np.ndarray,
-                     training: bool, masks=None, node_feats: Optional[Tensor] = None) -> Tensor:
-    """`HierarchicalPatchModel.forward` (src/core/models.py:394-496) without the coordinate branch.
-    x is the embedder output [B,C,S,S]; node_type is the batched per-node type vector; returns
-    logits [B*N0, num_output_channels]."""
+                     training: bool, masks=None, node_feats: Optional[Tensor] = None,
+                     node_coords: Optional[Tensor] = None):
+    """`HierarchicalPatchModel.forward` (src/core/models.py:394-496).  x is the embedder output [B,C,S,S];
+    node_type is the batched per-node type vector; returns logits [B*N0, num_output_channels], and with
+    `use_coordinate_graph` (node_coords [4B,2] or [B,4,2]) the pair (logits, coords [4B,2])."""
+    if cfg.use_coordinate_graph:
+        node_coords = node_coords.reshape(-1, 4, 2)
     if node_feats is None:
         maps = unet_pyramid(sd, cfg, x, training) if cfg.variant == "unet" else avgpool_pyramid(cfg, x)
-        node_feats = pack_nodes(cfg, maps)
-    h = gnn_stack(sd, cfg, node_feats, edge_index, training, masks)
+        node_feats = pack_nodes(cfg, maps, node_coords)
     keep = np.where(np.asarray(node_type) == 0)[0]
+    if cfg.use_coordinate_graph:
+        h, coords = gnn_stack(sd, cfg, node_feats, edge_index, training, masks, node_coords=node_coords,
+                              node_type=node_type)
+        h = h[torch.from_numpy(keep)]
+        return classifiers(sd, cfg, h, training, masks).squeeze(1), coords.reshape(-1, 2)
+    h = gnn_stack(sd, cfg, node_feats, edge_index, training, masks)
     if keep.shape[0] != h.shape[0]:
         h = h[torch.from_numpy(keep)]
     return classifiers(sd, cfg, h, training, masks).squeeze(1)
+
+
+def mae_loss(pred: Tensor, y: Tensor, loss_weight: float = 1.0) -> Tensor:
+    """criterion 'coordinate' = MAE (src/core/criterion.py:52-64, src/builders/criterion_builder.py:40-41)."""
+    return loss_weight * F.l1_loss(pred, y)
 
 
 # --------------------------------------------------------------------------------------------
@@ -540,6 +583,14 @@ def init_landmark_state(cfg: Cfg, seed: int = 200, embed_channels: int = 4) -> D
             bn(p + "BN2.", f // 2)
         for i, f in enumerate(list(reversed(dims)) + [dims[0] // 2]):
             linear(f"linears.{i}.", E, f, 1)
+    if cfg.use_coordinate_graph:  # src/core/models.py:337-350; drawn last so the other tensors keep their values
+        for i in range(cfg.num_gnn_layers):
+            p = f"node_coordinate_mlp.{i}."
+            linear(p + "0.", Ch, H + 8)
+            bn(p + "1.", Ch)
+            linear(p + "4.", Ch // 2, Ch)
+            bn(p + "5.", Ch // 2)
+            linear(p + "8.", 2, Ch // 2)
     return sd
 
 

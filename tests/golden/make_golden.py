@@ -114,7 +114,7 @@ def make_labels():
     np.savez_compressed(os.path.join(HERE, "labels.npz"), **out)
 
 
-GNN_PREFIXES = ("gnn_layers.", "node_classifiers.")
+GNN_PREFIXES = ("gnn_layers.", "node_classifiers.", "node_coordinate_mlp.")
 
 
 def run_reference_model(variant, cfg_kw, batch, seed, *, training, coords_seed=7):
@@ -128,7 +128,8 @@ def run_reference_model(variant, cfg_kw, batch, seed, *, training, coords_seed=7
                 node_hidden_dim=cfg.node_hidden_dim, num_output_channels=4,
                 num_gnn_layers=cfg.num_gnn_layers, num_aux_graphs=cfg.num_aux_graphs,
                 gnn_jk_mode=cfg.gnn_jk_mode, classifier_hidden_dim=cfg.classifier_hidden_dim,
-                residual=cfg.residual, use_coordinate_graph=False, output_activation=cfg.output_activation,
+                residual=cfg.residual, use_coordinate_graph=cfg.use_coordinate_graph,
+                output_activation=cfg.output_activation,
                 use_connection_nodes=cfg.use_connection_nodes, use_main_graph_only=cfg.use_main_graph_only)
     if variant == "unet":
         model = models.UNETHierarchicalPatchModel(encoder_embedding_widths=[128, 64, 32, 16, 8, 4, 2],
@@ -141,7 +142,7 @@ def run_reference_model(variant, cfg_kw, batch, seed, *, training, coords_seed=7
     model.train(training)
 
     ei1, nt1 = ref_shim.reference_graph(cfg.frame_size, cfg.num_aux_graphs, main_only=cfg.use_main_graph_only,
-                                        conn=cfg.use_connection_nodes)
+                                        conn=cfg.use_connection_nodes, coord=cfg.use_coordinate_graph)
     n = nt1.shape[0]
     ei = R.batch_edge_index(ei1, n, batch)
     node_type = torch.tensor(np.tile(nt1, batch))
@@ -158,7 +159,12 @@ def run_reference_model(variant, cfg_kw, batch, seed, *, training, coords_seed=7
         n0 = y.shape[0] // batch
         valid[n0:2 * n0, 2] = 0.0
 
-    logits, _ = model(x=x, node_coords=None, edge_index=ei, batch_idx=batch_idx, node_type=node_type)
+    node_coords = None
+    if cfg.use_coordinate_graph:  # initial coordinates as the data set provides them (src/core/datasets.py:99) + jitter
+        base = torch.tensor([[99.99, 112.57], [142.71, 90.67], [151.18, 86.25], [91.81, 117.91]]) * (cfg.frame_size / 224.0)
+        node_coords = (base.repeat(batch, 1) + torch.rand(4 * batch, 2, generator=g)).clamp(0, cfg.frame_size - 1)
+    logits, coord_pred = model(x=x, node_coords=None if node_coords is None else node_coords.clone(), edge_index=ei,
+                               batch_idx=batch_idx, node_type=node_type)
     bce = criterion.WeightedBCEWithLogitsLoss(reduction="none", ones_weight=9000, loss_weight=1)
     elm = criterion.ExpectedLandmarkMSE(loss_weight=10, batch_size=batch, frame_size=cfg.frame_size,
                                         num_aux_graphs=cfg.num_aux_graphs,
@@ -167,7 +173,13 @@ def run_reference_model(variant, cfg_kw, batch, seed, *, training, coords_seed=7
     l_bce = bce.compute(pv, yv, valid)
     l_elm = elm.compute(pv, yv, valid)
     total = l_bce + l_elm
-    out = {"coords": coords, "valid": valid.numpy().astype(np.int8),
+    extra = {}
+    if cfg.use_coordinate_graph:
+        l_mae = criterion.MAE().compute(coord_pred, torch.from_numpy(coords).float().view(-1, 2))
+        total = total + l_mae
+        extra = {"node_coords_in": node_coords.numpy(), "node_coords_out": coord_pred.detach().numpy(),
+                 "loss_mae": l_mae.detach().numpy()}
+    out = {**extra, "coords": coords, "valid": valid.numpy().astype(np.int8),
            "logits": logits.detach().numpy(), "loss_bce": l_bce.detach().numpy(),
            "loss_elmse": l_elm.detach().numpy(), "seed": np.array(seed), "batch": np.array(batch)}
     if training:
@@ -201,6 +213,11 @@ def make_models(skip_big: bool):
                                             gnn_dropout_p=0.0, classifier_dropout_p=0.0),
                             batch=2, seed=13, training=True)
     np.savez_compressed(os.path.join(HERE, "model_avgpool_S12_n3_conn_train.npz"), **o)
+    o = run_reference_model("avgpool", dict(frame_size=12, num_aux_graphs=3, use_coordinate_graph=True,
+                                            gnn_dropout_p=0.0, classifier_dropout_p=0.0),
+                            batch=3, seed=14, training=True)
+    np.savez_compressed(os.path.join(HERE, "model_avgpool_S12_n3_coord_train.npz"), **o)
+    print("coord", float(o["loss_bce"]), float(o["loss_elmse"]), float(o["loss_mae"]), flush=True)
     unet = dict(frame_size=16, num_aux_graphs=3, gnn_dropout_p=0.0, classifier_dropout_p=0.0)
     for training in (False, True):
         tag = "train" if training else "eval"
@@ -276,7 +293,7 @@ if __name__ == "__main__":
         make_graphs(a.skip_big)
     if a.only in ("", "labels"):
         make_labels()
-    if a.only in ("", "models"):
-        make_models(a.skip_big)
+    if a.only in ("", "models", "models-small"):
+        make_models(a.skip_big or a.only == "models-small")
     if a.only in ("", "evaluator"):
         make_evaluator()

@@ -130,8 +130,10 @@ def test_unsupported_configs_fail_loudly_and_cpu_inputs_are_rejected(eg):
     kw = dict(DEFAULT_KW)
     with pytest.raises(NotImplementedError):
         eg.HierarchicalPatchModel(**{**kw, "node_hidden_dim": 64})
-    with pytest.raises(NotImplementedError):
-        eg.HierarchicalPatchModel(**{**kw, "use_coordinate_graph": True})
+    coord = eg.HierarchicalPatchModel(**{**kw, "use_coordinate_graph": True})  # optional branch: 3 coordinate MLPs
+    assert [k for k in coord.state_dict() if k.startswith("node_coordinate_mlp.2.8.")] == \
+        ["node_coordinate_mlp.2.8.weight", "node_coordinate_mlp.2.8.bias"]
+    assert coord.state_dict()["node_coordinate_mlp.0.0.weight"].shape == (32, 136)
     with pytest.raises(TypeError):
         eg.HierarchicalPatchModel(**{**kw, "output_activation": "tanh"})
     with pytest.raises(AssertionError):

@@ -601,6 +601,47 @@ def test_module_matches_reference_golden(stem):
             assert abs(g.abs().sum().item() - z[k][1]) <= (5e-2 if unet else 2e-3) * abs(z[k][1]) + 1e-12, k
 
 
+def test_coordinate_graph_module_matches_reference_golden():
+    """`use_coordinate_graph=True`: the drop-in module (GCN layers on the sm_100a kernels over the graph with the K4
+    coordinate nodes, 4-tap bilinear re-sampling, coordinate MLPs) against the reference module's golden output:
+    logits, updated coordinates, the three losses and every gradient incl. the coordinate MLPs and dX."""
+    z = np.load(os.path.join(GOLDEN, "model_avgpool_S12_n3_coord_train.npz"))
+    cfg = R.Cfg(variant="avgpool", frame_size=12, num_aux_graphs=3, gnn_dropout_p=0.0, classifier_dropout_p=0.0,
+                use_coordinate_graph=True)
+    batch, seed = int(z["batch"]), int(z["seed"])
+    model = eg.HierarchicalPatchModel(
+        frame_size=12, gnn_dropout_p=0.0, classifier_dropout_p=0.0, node_embedding_dim=128, node_hidden_dim=128,
+        num_output_channels=4, num_gnn_layers=3, num_aux_graphs=3, gnn_jk_mode='last', classifier_hidden_dim=32,
+        residual=True, use_coordinate_graph=True, output_activation='logit').to(DEV)
+    model.load_state_dict(R.init_landmark_state(cfg, seed=seed), strict=True)
+    model.train()
+    x = torch.randn(batch, 128, 12, 12, generator=torch.Generator().manual_seed(seed + 1)).to(DEV).requires_grad_(True)
+    coords_in = torch.from_numpy(z["node_coords_in"]).to(DEV)
+    before = coords_in.clone()
+    ei = model.graph_spec.host_edge_index(batch).to(DEV)
+    logits, coords = model(x=x, node_coords=coords_in, edge_index=ei)
+    assert torch.equal(coords_in, before)  # the caller's tensor is not modified
+    ok, worst = close(logits.detach().cpu(), z["logits"], 1e-4, 1e-5)
+    assert ok, f"logits {worst}"
+    ok, worst = close(coords.detach().cpu(), z["node_coords_out"], 1e-4, 1e-5)
+    assert ok, f"coords {worst}"
+    y = torch.cat([R.node_labels(c, 12, 3) for c in z["coords"]], dim=0).to(DEV)
+    valid = torch.from_numpy(z["valid"].astype(np.float32)).to(DEV)
+    bce, elm = _criteria(cfg, batch)
+    l1 = bce.compute(logits.view(batch, -1, 4), y.view(batch, -1, 4), valid)
+    l2 = elm.compute(logits.view(batch, -1, 4), y.view(batch, -1, 4), valid)
+    l3 = eg.MAE().compute(coords, torch.from_numpy(z["coords"]).float().view(-1, 2).to(DEV))
+    for got, key in ((l1, "loss_bce"), (l2, "loss_elmse"), (l3, "loss_mae")):
+        assert abs(got.item() - float(z[key])) <= 1e-4 * abs(float(z[key])), key
+    (l1 + l2 + l3).backward()
+    ok, worst = close(x.grad.cpu(), z["grad_x"], 1e-3, 1e-4)
+    assert ok, f"grad_x {worst}"
+    params = dict(model.named_parameters())
+    want = {k[5:]: z[k] for k in z.files if k.startswith("grad/")}
+    bad = grads_close({k: params[k].grad.cpu() for k in want}, want, rtol=1e-3, atol_frac=1e-4)
+    assert not bad, bad
+
+
 def test_module_train_with_dropout_matches_oracle_given_same_masks():
     """Train mode with dropout ON: the counter-based masks are exported (eg_dropout_mask) and handed to
     the oracle, which then must agree on logits, loss and gradients."""

@@ -146,3 +146,36 @@ def test_expected_coordinate_evaluator_restatement_matches_reference_golden():
                 want = float(z[pre + "last/" + k])
                 assert abs(got[k] - want) <= 1e-5 * max(abs(want), 1.0), (name, step, k, got[k], want)
             assert np.allclose(preds[:, 3].numpy(), z[pre + "coord/pred_ivs"], rtol=1e-5, atol=1e-5)
+
+
+def test_coordinate_graph_branch_matches_reference():
+    """`use_coordinate_graph=True`: K4 coordinate nodes, per-layer coordinate MLP,
+    bilinear re-sampling, MAE 'coordinate' loss — oracle against values minted by the reference module
+    (src/core/models.py:438-473,539-553; src/core/criterion.py:52-64)."""
+    z = np.load(os.path.join(GOLDEN, "model_avgpool_S12_n3_coord_train.npz"))
+    cfg = R.Cfg(variant="avgpool", frame_size=12, num_aux_graphs=3, gnn_dropout_p=0.0, classifier_dropout_p=0.0,
+                use_coordinate_graph=True)
+    batch, seed = int(z["batch"]), int(z["seed"])
+    sd = R.clone_state(R.init_landmark_state(cfg, seed=seed), requires_grad=True)
+    x = torch.randn(batch, 128, 12, 12, generator=torch.Generator().manual_seed(seed + 1)).requires_grad_(True)
+    ei1, nt1 = R.build_edge_index(12, 3, coord=True)
+    n = nt1.shape[0]
+    logits, coords = R.landmark_forward(sd, cfg, x, R.batch_edge_index(ei1, n, batch), np.tile(nt1, batch), True,
+                                        node_coords=torch.from_numpy(z["node_coords_in"]))
+    ok, worst = close(logits.detach(), z["logits"], 1e-4, 1e-5)
+    assert ok, f"logits {worst}"
+    ok, worst = close(coords.detach(), z["node_coords_out"], 1e-5, 1e-6)
+    assert ok, f"coords {worst}"
+    y = torch.cat([R.node_labels(c, 12, 3) for c in z["coords"]], dim=0)
+    valid = torch.from_numpy(z["valid"].astype(np.float32))
+    losses = R.total_loss(logits, y, valid, cfg, batch)
+    mae = R.mae_loss(coords, torch.from_numpy(z["coords"]).float().view(-1, 2))
+    assert abs(mae.item() - float(z["loss_mae"])) <= 1e-5 * float(z["loss_mae"])
+    assert abs(losses["WeightedBceWithLogits"].item() - float(z["loss_bce"])) <= 1e-5 * abs(float(z["loss_bce"]))
+    (losses["total"] + mae).backward()
+    ok, worst = close(x.grad, z["grad_x"], 1e-3, 1e-4)
+    assert ok, f"grad_x {worst}"
+    want = {k[5:]: z[k] for k in z.files if k.startswith("grad/")}
+    assert any(k.startswith("node_coordinate_mlp.") for k in want)
+    bad = grads_close({k: sd[k].grad for k in want}, want)
+    assert not bad, bad
