@@ -270,6 +270,16 @@ def run_native(args):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    # informational only (never the headline): the same step with the PyTorch default `cudnn.allow_tf32 = True`
+    # for the out-of-scope UNet / embedder convolutions, i.e. what the unmodified reference runs on an Ampere+ GPU
+    ms_tf32 = None
+    if not args.cudnn_tf32:
+        torch.backends.cudnn.allow_tf32 = True
+        for _ in range(3):
+            step_resident()
+        ms_tf32 = timed(step_resident, args.steps)
+        torch.backends.cudnn.allow_tf32 = False
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -334,6 +344,9 @@ def run_native(args):
         "cpu_baseline": cpu_baseline,
         "kernels": kernels,
         "native_kernel_ms_per_step": native_ms,
+        "alt": {"note": "informational: same step with cudnn.allow_tf32=True (PyTorch default) for the UNet/embedder convolutions",
+                "frames_per_s": (frames_total / (ms_tf32 / 1e3)) if ms_tf32 else None,
+                "ms_per_step": (ms_tf32 / args.steps) if ms_tf32 else None},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

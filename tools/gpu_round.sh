@@ -11,4 +11,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
   --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --ncu-range > gpurun_out/${TAG}_ncu1.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gcn_tc_kernel -c 2 -f \
   -o gpurun_out/${TAG}_gcn_tc python tools/kernel_bench.py --only gcn_conv_fwd,linear128 --iters 1 > gpurun_out/${TAG}_ncu2.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gcn_tc_kernel|wgrad_tc_kernel" --launch-skip 6 -c 2 -f \
+  -o gpurun_out/${TAG}_bwd python tools/kernel_bench.py --only gcn_conv_bwd --iters 1 > gpurun_out/${TAG}_ncu3.log 2>&1
 ls -la gpurun_out | tail -12
