@@ -107,7 +107,7 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
 // Backward.  g = dX * (preact > 0);  d_in[b][c][p] = sum_o W[o][c] g[p][o];  per-block partials of
 // dW[o][c] = sum g[p][o] in[c][p] and dbias[o] = sum g[p][o]   (parts: [grid][128][CIN + 1], bias last).
 template <int CIN>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 level_embed_bwd_kernel(int N, int off, int P, int tiles_per_frame, int num_tiles, const float* __restrict__ in,
                        const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ dX,
                        float* __restrict__ d_in, float* __restrict__ parts) {

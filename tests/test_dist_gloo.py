@@ -29,9 +29,9 @@ def _worker(rank, world, port, out_dir):
     bucket.zero()
     loss = model(frames[mine.start:mine.stop]).square().mean()  # per-rank normaliser, as in the reference replicas
     loss.backward()
-    for p in model.parameters():  # gradients were accumulated INTO the flat buffer (views, no copies)
-        assert p.grad.data_ptr() >= bucket.flat.data_ptr()
     bucket.all_reduce_mean()
+    for p, v in zip(bucket.params, bucket.views):  # after the exchange every .grad IS its view of the flat buffer
+        assert p.grad.data_ptr() == v.data_ptr()
     torch.save({"flat": bucket.flat.clone(), "range": (mine.start, mine.stop)}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -49,7 +49,9 @@ def test_flat_bucket_allreduce_equals_global_batch_gradient(tmp_path):
     model = torch.nn.Sequential(torch.nn.Linear(16, 8), torch.nn.Tanh(), torch.nn.Linear(8, 1))
     bucket = egdist.FlatGradBucket(model.parameters())
     frames = torch.randn(8, 16, generator=torch.Generator().manual_seed(1))
+    bucket.zero()
     model(frames).square().mean().backward()
+    bucket.all_reduce_mean()  # world size 1: gathers the fresh gradients into the flat buffer
     assert torch.allclose(bucket.flat, outs[0]["flat"], rtol=1e-5, atol=1e-7)
 
 
