@@ -136,6 +136,26 @@ __device__ __forceinline__ float4 lds4(uint32_t addr) {
 __device__ __forceinline__ void sts4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// packed fp32 pairs (one FADD2 / FFMA2 issue slot for two elements): used by the epilogue
+struct F2 {
+  unsigned long long u;
+};
+__device__ __forceinline__ F2 f2_pack(float lo, float hi) {
+  return F2{((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo)};
+}
+__device__ __forceinline__ float f2_lo(F2 a) { return __uint_as_float((uint32_t)a.u); }
+__device__ __forceinline__ float f2_hi(F2 a) { return __uint_as_float((uint32_t)(a.u >> 32)); }
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+  F2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u));
+  return r;
+}
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+  F2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.u) : "l"(a.u), "l"(b.u), "l"(c.u));
+  return r;
+}
+
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
   acc.x = fmaf(w, x.x, acc.x);
   acc.y = fmaf(w, x.y, acc.y);
@@ -733,15 +753,21 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
           float s = 0.f, q = 0.f;
           tmem_ld_wait();
           if (cnt == 16) {
+            // two rows per packed instruction: o = v + bias, s += o, q += o * o  (24 instead of 48 issue slots)
+            const F2 b2 = f2_pack(bias, bias);
+            F2 s2 = f2_pack(0.f, 0.f), q2 = s2;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float o = __uint_as_float(v[i]) + bias;
+            for (int i = 0; i < 16; i += 2) {
+              const F2 o2 = f2_add(F2{((unsigned long long)v[i + 1] << 32) | v[i]}, b2);
 #ifndef EG_DBG_NOSTORE
-              EG_ST_OUT(out + i * 128, o);
+              EG_ST_OUT(out + i * 128, f2_lo(o2));
+              EG_ST_OUT(out + (i + 1) * 128, f2_hi(o2));
 #endif
-              s += o;
-              q = fmaf(o, o, q);
+              s2 = f2_add(s2, o2);
+              q2 = f2_fma(o2, o2, q2);
             }
+            s = f2_lo(s2) + f2_hi(s2);
+            q = f2_lo(q2) + f2_hi(q2);
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
