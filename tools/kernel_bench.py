@@ -38,9 +38,12 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="")
     ap.add_argument("--main-only", action="store_true", help="use_main_graph_only graph (all tiles are lattice tiles)")
+    ap.add_argument("--frame", type=int, default=224, help="frame size (BASELINE configs[3]: 448 with --naux 8)")
+    ap.add_argument("--naux", type=int, default=7)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
-    g = eg.DeviceGraph.get(eg.HierGraphSpec(use_main_graph_only=args.main_only), dev)
+    g = eg.DeviceGraph.get(eg.HierGraphSpec(frame_size=args.frame, num_aux_graphs=args.naux,
+                                            use_main_graph_only=args.main_only), dev)
     B, N = args.batch, g.meta.num_nodes
     rows = B * N
     U = rows * 128 * 4
