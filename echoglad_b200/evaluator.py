@@ -92,39 +92,40 @@ class LandmarkExpectedCoordiantesEvaluator(object):
                        'gt_lvid_bot': gt[:, 1], 'gt_lvpw': gt[:, 2]}
         self.detailed_performance = {'widths': widths, 'coordinates': coordinates}
 
+    # width name -> the two landmarks it spans (indices into lvid_top, lvid_bot, lvpw, ivs)
+    _SPANS = {'ivs': (3, 0), 'lvid': (0, 1), 'lvpw': (1, 2)}
+
     def calculate_widths(self, preds, gt, pix2mm_x, pix2mm_y):
-        gt = gt.to(preds.dtype)
-        pl = self.get_pixel_length
-        return {"pred_ivs_mm": pl(preds[:, 3, 1], preds[:, 3, 0], preds[:, 0, 1], preds[:, 0, 0], pix2mm_x, pix2mm_y),
-                "pred_lvid_mm": pl(preds[:, 0, 1], preds[:, 0, 0], preds[:, 1, 1], preds[:, 1, 0], pix2mm_x, pix2mm_y),
-                "pred_lvpw_mm": pl(preds[:, 1, 1], preds[:, 1, 0], preds[:, 2, 1], preds[:, 2, 0], pix2mm_x, pix2mm_y),
-                "gt_ivs_mm": pl(gt[:, 3, 1], gt[:, 3, 0], gt[:, 0, 1], gt[:, 0, 0], pix2mm_x, pix2mm_y),
-                "gt_lvid_mm": pl(gt[:, 0, 1], gt[:, 0, 0], gt[:, 1, 1], gt[:, 1, 0], pix2mm_x, pix2mm_y),
-                "gt_lvpw_mm": pl(gt[:, 1, 1], gt[:, 1, 0], gt[:, 2, 1], gt[:, 2, 0], pix2mm_x, pix2mm_y)}
+        """[B,4,2] coordinates -> {'pred_<w>_mm', 'gt_<w>_mm'}: physical lengths of the three measured widths."""
+        out = {}
+        for tag, pts in (('pred', preds), ('gt', gt.to(preds.dtype))):
+            for name, (a, b) in self._SPANS.items():
+                out[f'{tag}_{name}_mm'] = self.get_pixel_length(pts[:, a, 1], pts[:, a, 0], pts[:, b, 1], pts[:, b, 0],
+                                                               pix2mm_x, pix2mm_y)
+        return out
 
     @staticmethod
-    def calculate_width_MAE(widths):
-        return (torch.abs(widths['pred_ivs_mm'] - widths['gt_ivs_mm']),
-                torch.abs(widths['pred_lvid_mm'] - widths['gt_lvid_mm']),
-                torch.abs(widths['pred_lvpw_mm'] - widths['gt_lvpw_mm']))
+    def _width_abs_err(widths):
+        return {k: torch.abs(widths[f'pred_{k}_mm'] - widths[f'gt_{k}_mm']) for k in ('ivs', 'lvid', 'lvpw')}
 
-    @staticmethod
-    def calculate_width_MPE(widths):
-        return (100 * torch.abs(widths['pred_ivs_mm'] - widths['gt_ivs_mm']) / widths['gt_ivs_mm'],
-                100 * torch.abs(widths['pred_lvid_mm'] - widths['gt_lvid_mm']) / widths['gt_lvid_mm'],
-                100 * torch.abs(widths['pred_lvpw_mm'] - widths['gt_lvpw_mm']) / widths['gt_lvpw_mm'])
+    def calculate_width_MAE(self, widths):
+        e = self._width_abs_err(widths)
+        return e['ivs'], e['lvid'], e['lvpw']
+
+    def calculate_width_MPE(self, widths):
+        e = self._width_abs_err(widths)
+        return tuple(100 * e[k] / widths[f'gt_{k}_mm'] for k in ('ivs', 'lvid', 'lvpw'))
 
     def compute(self):
-        v = {k: np.asarray(self.valid_errors[k]) for k in self.valid_errors}
-        both = np.logical_and(v['lvid_top'], v['lvid_bot'])
-        temp = {k: np.asarray(self.coordinate_errors[k]).sum() / np.count_nonzero(v[k]) for k in _NAMES}
-        temp['ivs_w'] = np.asarray(self.width_MAE['ivs']).sum() / np.count_nonzero(v['ivs'])
-        temp['lvid_w'] = np.asarray(self.width_MAE['lvid']).sum() / np.count_nonzero(both)
-        temp['lvpw_w'] = np.asarray(self.width_MAE['lvpw']).sum() / np.count_nonzero(v['lvpw'])
-        temp['ivs_mpe'] = np.asarray(self.width_MPE['ivs']).sum() / np.count_nonzero(v['ivs'])
-        temp['lvid_mpe'] = np.asarray(self.width_MPE['lvid']).sum() / np.count_nonzero(both)
-        temp['lvpw_mpe'] = np.asarray(self.width_MPE['lvpw']).sum() / np.count_nonzero(v['lvpw'])
-        return temp
+        """Means over the recorded batches, each normalised by the number of batches in which the landmark (for
+        lvid: both of its landmarks) was valid."""
+        ok = {k: np.asarray(v) for k, v in self.valid_errors.items()}
+        ok['lvid'] = np.logical_and(ok['lvid_top'], ok['lvid_bot'])
+        out = {k: np.asarray(self.coordinate_errors[k]).sum() / np.count_nonzero(ok[k]) for k in _NAMES}
+        for suffix, rec in (('_w', self.width_MAE), ('_mpe', self.width_MPE)):
+            for k in ('ivs', 'lvid', 'lvpw'):
+                out[k + suffix] = np.asarray(rec[k]).sum() / np.count_nonzero(ok[k])
+        return out
 
     def get_sum_of_width_MAE(self):
         temp = self.compute()

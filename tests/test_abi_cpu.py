@@ -188,3 +188,34 @@ def test_registry_patch_with_evaluators(eg):
     assert set(ev.coordinate_errors) == {'ivs', 'lvid_top', 'lvid_bot', 'lvpw'} and ev.get_predictions() == {}
     with pytest.raises(eg.EchogladError, match="no CPU fallback"):
         ev.update(torch.zeros(8, 4), torch.zeros(8, 4), torch.ones(2), torch.ones(2), torch.ones(8, 4))
+
+
+def test_evaluator_host_arithmetic_matches_reference_golden(eg, monkeypatch):
+    """Host half of the drop-in evaluator (errors in mm, width MAE / MPE, accumulation over batches) against the
+    values the reference's own evaluator produced; the device half (eg_expected_coords) is replaced by the oracle's
+    restatement here and tested against it under -m gpu."""
+    from echoglad_b200 import evaluator as E
+    from oracle import restated as R
+    z = np.load(os.path.join(GOLDEN, "evaluator_expected_coords.npz"))
+
+    def fake(y_pred, y_true, valid, batch, frame):
+        p, g, v = R.expected_coords(y_pred, y_true, valid, batch, frame)
+        return p, g.to(torch.int32), v
+
+    monkeypatch.setattr(E, "expected_coords", fake)
+    for name, (frame, naux, batch) in {"S16_n3_B3": (16, 3, 3), "S28_n4_B2": (28, 4, 2)}.items():
+        ev = eg.LandmarkExpectedCoordiantesEvaluator(None, batch, frame, False)
+        for step in range(2):
+            pre = f"{name}/step{step}/"
+            y = torch.cat([R.node_labels(c, frame, naux) for c in z[pre + "coords"]], dim=0)
+            ev.update(torch.from_numpy(z[pre + "logits"]), y, torch.from_numpy(z[pre + "pix2mm_x"]),
+                      torch.from_numpy(z[pre + "pix2mm_y"]), torch.from_numpy(z[pre + "valid"]))
+            for k, v in ev.get_last().items():
+                want = float(z[pre + "last/" + k])
+                assert abs(v - want) <= 1e-5 * max(abs(want), 1.0), (name, step, k)
+            for k, v in ev.get_predictions()["widths"].items():
+                assert np.allclose(v.numpy(), z[pre + "width/" + k], rtol=1e-5, atol=1e-5), k
+        for k, v in ev.compute().items():
+            want = float(z[f"{name}/compute/{k}"])
+            assert abs(v - want) <= 1e-5 * max(abs(want), 1.0), (name, k)
+        assert abs(ev.get_sum_of_width_MAE() - sum(float(z[f"{name}/compute/{k}"]) for k in ("ivs_w", "lvid_w", "lvpw_w"))) < 1e-3
