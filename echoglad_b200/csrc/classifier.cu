@@ -144,12 +144,10 @@ clf_mid_bwd_kernel(long long rows, const float* __restrict__ A1, const float* __
     for (int r = 0; r < TR; ++r) {
       const float a = As[r * LDA + k * 32 + lane];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 4; ++q) {  // packed FFMA2: two output features per issue slot
         const float4 gz = *reinterpret_cast<const float4*>(Gs + r * LDO + k * 16 + q * 4);
-        wacc[4 * q] = fmaf(gz.x, a, wacc[4 * q]);
-        wacc[4 * q + 1] = fmaf(gz.y, a, wacc[4 * q + 1]);
-        wacc[4 * q + 2] = fmaf(gz.z, a, wacc[4 * q + 2]);
-        wacc[4 * q + 3] = fmaf(gz.w, a, wacc[4 * q + 3]);
+        fma2(wacc[4 * q], wacc[4 * q + 1], a, gz.x, gz.y);
+        fma2(wacc[4 * q + 2], wacc[4 * q + 3], a, gz.z, gz.w);
       }
       if (lane < 16) bacc += Gs[r * LDO + k * 16 + lane];
     }
@@ -167,10 +165,8 @@ clf_mid_bwd_kernel(long long rows, const float* __restrict__ A1, const float* __
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float4 w = *reinterpret_cast<const float4*>(Ws + (k * 16 + j) * 32 + i4 * 4);
-        o.x = fmaf(dz[j], w.x, o.x);
-        o.y = fmaf(dz[j], w.y, o.y);
-        o.z = fmaf(dz[j], w.z, o.z);
-        o.w = fmaf(dz[j], w.w, o.w);
+        fma2(o.x, o.y, dz[j], w.x, w.y);
+        fma2(o.z, o.w, dz[j], w.z, w.w);
       }
       *reinterpret_cast<float4*>(As + lane * LDA + k * 32 + i4 * 4) = o;
     }
