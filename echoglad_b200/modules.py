@@ -416,12 +416,12 @@ class UNETHierarchicalPatchModel(HierarchicalPatchModel):
         feats, used = self.decoder_features(x)
         return [TF.relu(self.linears[i](feats[i])) for i in used]
 
-    def create_node_pixels(self, x: torch.Tensor, graph: DeviceGraph) -> torch.Tensor:
+    def create_node_pixels(self, x: torch.Tensor, graph: DeviceGraph, node_coords=None) -> torch.Tensor:
         """Fused route (default.yml: no connection / coordinate nodes): the narrow decoder maps of the big levels
         go straight into eg_level_embed (1x1 conv + ReLU + packing in one pass)."""
         meta = graph.meta
         if meta.first_pixel_node or meta.num_coord_nodes or not self.fuse_level_embed:
-            return super().create_node_pixels(x, graph)
+            return super().create_node_pixels(x, graph, node_coords)
         feats, used = self.decoder_features(x)
         fused, args = [], []
         for l, i in enumerate(used):

@@ -642,6 +642,34 @@ def test_coordinate_graph_module_matches_reference_golden():
     assert not bad, bad
 
 
+def test_unet_variant_with_coordinate_graph_against_oracle():
+    """UNet variant + `use_coordinate_graph`: coordinate nodes start from the bilinear sample of the main-level
+    decoder map (src/core/models.py:743-744).  Oracle on identical weights; the PyTorch pyramid runs on both sides,
+    so the loose UNet tolerance of the golden test applies to the logits, the coordinates are held to 1e-3."""
+    cfg = R.Cfg(variant="unet", frame_size=16, num_aux_graphs=3, gnn_dropout_p=0.0, classifier_dropout_p=0.0,
+                use_coordinate_graph=True)
+    batch = 2
+    sd = R.init_landmark_state(cfg, seed=51)
+    model = eg.UNETHierarchicalPatchModel(
+        encoder_embedding_widths=[128, 64, 32, 16, 8, 4, 2], encoder_embedding_dims=[8, 16, 32, 64, 128, 256, 512],
+        frame_size=16, gnn_dropout_p=0.0, classifier_dropout_p=0.0, node_embedding_dim=128, node_hidden_dim=128,
+        num_output_channels=4, num_gnn_layers=3, num_aux_graphs=3, gnn_jk_mode='last', classifier_hidden_dim=32,
+        residual=True, use_coordinate_graph=True, output_activation='logit').to(DEV)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    x = torch.randn(batch, 4, 16, 16, generator=torch.Generator().manual_seed(52))
+    coords = torch.rand(4 * batch, 2, generator=torch.Generator().manual_seed(53)) * 15
+    logits, out = model(x=x.to(DEV), node_coords=coords.to(DEV))
+    ei1, nt1 = R.build_edge_index(16, 3, coord=True)
+    n = nt1.shape[0]
+    lo, co = R.landmark_forward(sd, cfg, x, R.batch_edge_index(ei1, n, batch), np.tile(nt1, batch), False,
+                                node_coords=coords.clone())
+    ok, worst = close(out.detach().cpu(), co.detach(), 1e-3, 1e-4)
+    assert ok, f"coords {worst}"
+    ok, worst = close(logits.detach().cpu(), lo.detach(), 5e-3, 5e-4)
+    assert ok, f"logits {worst}"
+
+
 def test_module_train_with_dropout_matches_oracle_given_same_masks():
     """Train mode with dropout ON: the counter-based masks are exported (eg_dropout_mask) and handed to
     the oracle, which then must agree on logits, loss and gradients."""
