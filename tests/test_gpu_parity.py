@@ -831,3 +831,62 @@ def test_default_yml_batch2_hot_path_against_oracle():
     assert torch.equal(yd.cpu(), y)
     _hot_path_vs_oracle(cfg, "unet", 2, frames, y, valid, R.init_landmark_state(cfg, seed=200),
                         R.init_embedder_state(4, seed=201))
+
+
+def test_engine_style_training_steps_through_the_registries():
+    """The reference Engine's training step (src/engine.py:239-275) replayed with the drop-in classes obtained
+    through the patched registries: embedder -> landmark(x=, node_coords=, edge_index=, batch_idx=, node_type=) ->
+    {criterion: .compute(...)} summed -> zero_grad / backward / Adam.step, then the evaluator, a strict state_dict
+    round trip into a fresh module and an eval-mode forward that reproduces bit for bit."""
+    from echoglad_b200 import register
+    models, criteria, evaluators = {}, {}, {}
+    register.patch(models, criteria, evaluators)
+    frame, naux, batch = 16, 3, 4
+    landmark_cfg = dict(frame_size=frame, gnn_dropout_p=0.5, classifier_dropout_p=0.5, node_embedding_dim=128,
+                        node_hidden_dim=128, num_output_channels=4, num_gnn_layers=3, num_aux_graphs=naux,
+                        gnn_jk_mode='last', classifier_hidden_dim=32, residual=True, use_coordinate_graph=False,
+                        output_activation='logit', use_connection_nodes=False, use_main_graph_only=False,
+                        encoder_embedding_widths=[128, 64, 32, 16, 8, 4, 2],
+                        encoder_embedding_dims=[8, 16, 32, 64, 128, 256, 512])
+    torch.manual_seed(0)
+    embedder = eg.CNN(out_channels=[4], kernel_sizes=[3], pool_sizes=[1], cnn_dropout_p=0.1).to(DEV)
+    landmark = models['unet_hierarchical_patch'](**landmark_cfg).to(DEV)
+    criterion = {'WeightedBceWithLogits': criteria['WeightedBceWithLogits'](reduction='none', ones_weight=9000, loss_weight=1),
+                 'ExpectedLandmarkMse': criteria['ExpectedLandmarkMse'](loss_weight=10, batch_size=batch, frame_size=frame,
+                                                                        num_aux_graphs=naux, use_main_graph_only=False,
+                                                                        num_output_channels=4)}
+    evaluator = evaluators['landmarkcoorderror'](logger=None, batch_size=batch, frame_size=frame, use_coord_graph=False)
+    opt = torch.optim.Adam(list(embedder.parameters()) + list(landmark.parameters()), lr=1e-3, weight_decay=1e-4)
+    frames, coords, y, valid = R.synthetic_batch(batch, frame, naux, seed=3)
+    spec = landmark.graph_spec
+    edge_index = spec.host_edge_index(batch).to(DEV)          # what the reference loader collates
+    node_type = torch.from_numpy(spec.host_node_type(batch)).to(DEV)
+    batch_idx = torch.arange(batch, device=DEV).repeat_interleave(node_type.numel() // batch)
+    frames, y, valid = frames.to(DEV), y.to(DEV), valid.to(DEV)
+    embedder.train(); landmark.train()
+    history = []
+    for _ in range(4):
+        x = embedder(frames)
+        preds, coord_preds = landmark(x=x, node_coords=None, edge_index=edge_index, batch_idx=batch_idx,
+                                      node_type=node_type)
+        assert coord_preds is None and preds.shape == y.shape
+        pv, yv = preds.view(batch, -1, 4), y.view(batch, -1, 4)
+        losses = {k: c.compute(pv, yv, valid) for k, c in criterion.items()}
+        loss = sum(losses.values())
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        history.append(loss.item())
+        assert all(torch.isfinite(p.grad).all() for p in landmark.parameters() if p.grad is not None)
+    assert all(np.isfinite(history)) and history[-1] < history[0]
+    landmark.eval(); embedder.eval()
+    with torch.no_grad():
+        ref_logits, _ = landmark(x=embedder(frames), edge_index=edge_index)
+        evaluator.update(ref_logits, y, torch.ones(batch, device=DEV), torch.ones(batch, device=DEV), valid)
+    assert set(evaluator.compute()) >= {'lvid_top', 'ivs_w', 'lvpw_mpe'}
+    clone = models['unet_hierarchical_patch'](**landmark_cfg).to(DEV)
+    clone.load_state_dict(landmark.state_dict(), strict=True)
+    clone.eval()
+    with torch.no_grad():
+        again, _ = clone(x=embedder(frames), edge_index=edge_index)
+    assert torch.equal(again, ref_logits)
