@@ -11,22 +11,27 @@ namespace {
 
 constexpr int kThreads = 256;
 
-struct ColParams {  // per-column constants staged in shared memory
-  float mean, sc /* gamma*invstd */, beta, invstd;
+// Per-column constants of the 4 columns a thread owns.  Every kernel below strides by a multiple of the row
+// width, so a thread keeps ONE column group for its whole life and the constants live in registers.  (They used to
+// be staged in shared memory as a 16-byte struct per column: a thread reading 4 consecutive structs strides the
+// warp by 64 B = a 4-way bank conflict on every load, and the kernels ran at 97 % LSU instead of at the HBM
+// roof -- ncu, r01h.)
+struct ColParams4 {
+  float mean[4], sc[4] /* gamma*invstd */, beta[4], invstd[4];
 };
 
-__device__ __forceinline__ void stage_params(ColParams* sp, int cols, const float* mean, const float* var,
-                                             const float* gamma, const float* beta, float eps) {
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    const float inv = 1.0f / sqrtf(__ldg(var + c) + eps);  // torch: 1/sqrt(var+eps), rounded once
-    ColParams p;
-    p.mean = __ldg(mean + c);
-    p.invstd = inv;
-    p.sc = __ldg(gamma + c) * inv;
-    p.beta = __ldg(beta + c);
-    sp[c] = p;
+__device__ __forceinline__ ColParams4 load_params(int c0, const float* mean, const float* var, const float* gamma,
+                                                  const float* beta, float eps) {
+  ColParams4 p;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float inv = 1.0f / sqrtf(__ldg(var + c0 + k) + eps);  // torch: 1/sqrt(var+eps), rounded once
+    p.mean[k] = __ldg(mean + c0 + k);
+    p.invstd[k] = inv;
+    p.sc[k] = __ldg(gamma + c0 + k) * inv;
+    p.beta[k] = __ldg(beta + c0 + k);
   }
-  __syncthreads();
+  return p;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -34,47 +39,53 @@ bn_act_fwd_kernel(long long rows, int cols, const float* __restrict__ H, const f
                   const float* __restrict__ var, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float eps, uint32_t thr, float keep_scale, uint64_t seed,
                   int relu, const float* __restrict__ res, float* __restrict__ Y) {
-  __shared__ ColParams sp[128];
-  stage_params(sp, cols, mean, var, gamma, beta, eps);
   const int cg = cols >> 2;
+  const ColParams4 p = load_params((threadIdx.x % cg) * 4, mean, var, gamma, beta, eps);  // kThreads % cg == 0
   const long long total = rows * cg;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cg) * 4;
-    float4 h = ldg4(H + i * 4);
-    float v[4] = {h.x, h.y, h.z, h.w};
-    uint32_t keep = thr ? drop_keep4(seed, (uint64_t)i, thr) : 0xfu;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const ColParams p = sp[c + k];
-      float y = fmaf(v[k] - p.mean, p.sc, p.beta);
-      y = ((keep >> k) & 1u) ? y * keep_scale : 0.f;
-      if (relu) y = fmaxf(y, 0.f);
-      v[k] = y;
-    }
+  const long long step = (long long)gridDim.x * blockDim.x;
+  // two groups per iteration: up to 4 independent 128-bit loads in flight per thread
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * step) {
+    const bool two = i + step < total;
+    const long long i2 = two ? i + step : i;
+    const float4 ha = ldg4(H + i * 4), hb = ldg4(H + i2 * 4);
+    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
     if (res) {
-      float4 r = ldg4(res + i * 4);
-      v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+      ra = ldg4(res + i * 4);
+      rb = ldg4(res + i2 * 4);
     }
-    st4(Y + i * 4, make_float4(v[0], v[1], v[2], v[3]));
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const long long iu = u ? i2 : i;
+      const float4 h = u ? hb : ha, r = u ? rb : ra;
+      float v[4] = {h.x, h.y, h.z, h.w};
+      const uint32_t keep = thr ? drop_keep4(seed, (uint64_t)iu, thr) : 0xfu;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float y = fmaf(v[k] - p.mean[k], p.sc[k], p.beta[k]);
+        y = ((keep >> k) & 1u) ? y * keep_scale : 0.f;
+        if (relu) y = fmaxf(y, 0.f);
+        v[k] = y;
+      }
+      st4(Y + iu * 4, make_float4(v[0] + r.x, v[1] + r.y, v[2] + r.z, v[3] + r.w));
+    }
   }
 }
 
 // Pass 1 of the backward: per-column sums of dA and dA*xhat, where dA = dY * dropmask * relumask.
 // Block = (cols/4) column groups x RY row lanes; each thread keeps its column group for all its rows.
 // If dH_eval != NULL (eval-mode BN) dH = sc * dA is written in the same pass.
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 3)
 bn_act_bwd_reduce_kernel(long long rows, int cols, const float* __restrict__ dY, const float* __restrict__ H,
                          const float* __restrict__ mean, const float* __restrict__ var,
                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                          uint32_t thr, float keep_scale, uint64_t seed, int relu,
                          float* __restrict__ dH_eval, double* __restrict__ parts) {
-  __shared__ ColParams sp[128];
   __shared__ double red[2][kThreads * 4];
-  stage_params(sp, cols, mean, var, gamma, beta, eps);
   const int cg = cols >> 2;
   const int ry = kThreads / cg;            // row lanes per block (cols=128 -> 8)
   const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
+  const ColParams4 p = load_params(tx * 4, mean, var, gamma, beta, eps);
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   double d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
   int since_flush = 0;
@@ -96,14 +107,13 @@ bn_act_bwd_reduce_kernel(long long rows, int cols, const float* __restrict__ dY,
         uint32_t keep = thr ? drop_keep4(seed, (uint64_t)i, thr) : 0xfu;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const ColParams p = sp[tx * 4 + k];
-          float xc = hv[k] - p.mean;
-          float bn = fmaf(xc, p.sc, p.beta);
+          float xc = hv[k] - p.mean[k];
+          float bn = fmaf(xc, p.sc[k], p.beta[k]);
           bool pass = ((keep >> k) & 1u) && (!relu || bn > 0.f);
           float dA = pass ? gv[k] * keep_scale : 0.f;
           s1[k] += dA;
-          s2[k] = fmaf(dA, xc * p.invstd, s2[k]);
-          o[k] = dA * p.sc;
+          s2[k] = fmaf(dA, xc * p.invstd[k], s2[k]);
+          o[k] = dA * p.sc[k];
         }
         if (dH_eval) st4(dH_eval + i * 4, make_float4(o[0], o[1], o[2], o[3]));
       }
@@ -179,31 +189,39 @@ bn_act_bwd_apply_kernel(long long rows, int cols, const float* __restrict__ dY, 
                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                         uint32_t thr, float keep_scale, uint64_t seed, int relu,
                         const float* __restrict__ coef, float* __restrict__ dH) {
-  __shared__ ColParams sp[128];
-  __shared__ float c1[128], c2[128];
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    c1[c] = __ldg(coef + c);
-    c2[c] = __ldg(coef + cols + c);
-  }
-  stage_params(sp, cols, mean, var, gamma, beta, eps);
   const int cg = cols >> 2;
-  const long long total = rows * cg;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cg) * 4;
-    float4 h = ldg4(H + i * 4), g = ldg4(dY + i * 4);
-    float hv[4] = {h.x, h.y, h.z, h.w}, gv[4] = {g.x, g.y, g.z, g.w}, o[4];
-    uint32_t keep = thr ? drop_keep4(seed, (uint64_t)i, thr) : 0xfu;
+  const int c0 = (threadIdx.x % cg) * 4;  // kThreads % cg == 0: one column group per thread
+  const ColParams4 p = load_params(c0, mean, var, gamma, beta, eps);
+  float c1[4], c2[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const ColParams p = sp[c + k];
-      float xc = hv[k] - p.mean;
-      float bn = fmaf(xc, p.sc, p.beta);
-      bool pass = ((keep >> k) & 1u) && (!relu || bn > 0.f);
-      float dA = pass ? gv[k] * keep_scale : 0.f;
-      o[k] = p.sc * (dA - c1[c + k] - xc * p.invstd * c2[c + k]);
+  for (int k = 0; k < 4; ++k) {
+    c1[k] = __ldg(coef + c0 + k);
+    c2[k] = __ldg(coef + cols + c0 + k);
+  }
+  const long long total = rows * cg;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * step) {
+    const bool two = i + step < total;
+    const long long i2 = two ? i + step : i;
+    const float4 ha = ldg4(H + i * 4), ga = ldg4(dY + i * 4);
+    const float4 hb = ldg4(H + i2 * 4), gb = ldg4(dY + i2 * 4);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const long long iu = u ? i2 : i;
+      const float4 h = u ? hb : ha, g = u ? gb : ga;
+      float hv[4] = {h.x, h.y, h.z, h.w}, gv[4] = {g.x, g.y, g.z, g.w}, o[4];
+      const uint32_t keep = thr ? drop_keep4(seed, (uint64_t)iu, thr) : 0xfu;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float xc = hv[k] - p.mean[k];
+        float bn = fmaf(xc, p.sc[k], p.beta[k]);
+        bool pass = ((keep >> k) & 1u) && (!relu || bn > 0.f);
+        float dA = pass ? gv[k] * keep_scale : 0.f;
+        o[k] = p.sc[k] * (dA - c1[k] - xc * p.invstd[k] * c2[k]);
+      }
+      st4(dH + iu * 4, make_float4(o[0], o[1], o[2], o[3]));
     }
-    st4(dH + i * 4, make_float4(o[0], o[1], o[2], o[3]));
   }
 }
 
@@ -289,10 +307,10 @@ inline int elem_grid(long long total_groups) {
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
-inline int reduce_grid(long long rows, int cols) {
+inline int reduce_grid(long long rows, int cols, int blocks_per_sm = kMaxParts / kNumSMs) {
   int ry = kThreads / (cols / 4);
   long long b = (rows + ry - 1) / ry;
-  long long cap = kMaxParts;
+  long long cap = (long long)blocks_per_sm * kNumSMs;  // one resident wave (<= kMaxParts partial slots)
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
@@ -356,7 +374,7 @@ int eg_bn_act_bwd(int64_t rows, int cols, const float* dY, const float* H, const
   const float ks = thr ? 1.0f / (1.0f - drop_p) : 1.0f;
   double* parts = reinterpret_cast<double*>(ws);
   float* coef = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);  // 2*cols floats
-  const int grid = reduce_grid(rows, cols);
+  const int grid = reduce_grid(rows, cols, 3);  // __launch_bounds__(kThreads, 3) of the reduce kernel
   ProfileScope prof("bn_act_bwd", s);
   bn_act_bwd_reduce_kernel<<<grid, kThreads, 0, s>>>(rows, cols, dY, H, mean, var, gamma, beta, eps, thr, ks, seed,
                                                      relu, batch_stats ? nullptr : dH, parts);
