@@ -8,178 +8,212 @@ using namespace eg;
 
 namespace {
 
-constexpr int kMidThreads = 128;  // warp k <-> head k, lane <-> row of the 32-row tile
-constexpr int kMidGrid = kNumSMs * 6;  // 6 resident blocks per SM (34 KB of shared memory each)
+// ---- layer 4: four block-diagonal [32 -> 16] transforms ---------------------------------------------------------
+// Lane mapping of both kernels: a warp owns whole rows; lane = 8 k + c  <->  head k, inputs 4c..4c+3 of that head,
+// i.e. the lane's float4 of the row's 512 contiguous bytes.  Every global access is a fully coalesced row (the
+// first version gave a thread its own rows: 32 different 128-byte lines per load instruction, LSU-bound at 89 %).
+// The lane's 64 weights W2[k][0..15][4c..4c+3] live in registers; there is no shared-memory traffic in the loops.
+constexpr int kMidFwdThreads = 256, kMidFwdBlocks = 2;   // per SM
+constexpr int kMidBwdThreads = 128, kMidBwdBlocks = 3;
+constexpr int kMidGrid = kNumSMs * 3;
 static_assert((size_t)kMidGrid * 128 * sizeof(double) <= kStatsBytes, "clf_mid_fwd partials fit the stats area");
-constexpr int TR = 32;
-constexpr int LDA = 132;          // A1 tile stride
-constexpr int LDO = 68;           // Z2 tile stride
 
-// sum over the 32 lanes of v[i] for i = 0..31; on return lane l holds the total of v[l] (31 shuffles)
-__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
+struct P2 {  // packed fp32 pair: one FFMA2 / FADD2 issue slot for two values
+  unsigned long long u;
+};
+__device__ __forceinline__ P2 p2(float lo, float hi) {
+  return P2{((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo)};
 }
-// (x, y) += a * (w.x, w.y): one packed FFMA2
-__device__ __forceinline__ void fma2(float& x, float& y, float a, float wx, float wy) {
-  unsigned long long c = ((unsigned long long)__float_as_uint(y) << 32) | __float_as_uint(x);
-  const unsigned long long a2 = ((unsigned long long)__float_as_uint(a) << 32) | __float_as_uint(a);
-  const unsigned long long w2 = ((unsigned long long)__float_as_uint(wy) << 32) | __float_as_uint(wx);
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a2), "l"(w2));
-  x = __uint_as_float((uint32_t)c);
-  y = __uint_as_float((uint32_t)(c >> 32));
+__device__ __forceinline__ float p2_lo(P2 a) { return __uint_as_float((uint32_t)a.u); }
+__device__ __forceinline__ float p2_hi(P2 a) { return __uint_as_float((uint32_t)(a.u >> 32)); }
+__device__ __forceinline__ P2 p2_fma(P2 a, P2 b, P2 c) {
+  P2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.u) : "l"(a.u), "l"(b.u), "l"(c.u));
+  return r;
+}
+__device__ __forceinline__ P2 p2_mul(P2 a, P2 b) {
+  P2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u));
+  return r;
+}
+__device__ __forceinline__ P2 p2_add(P2 a, P2 b) {
+  P2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.u) : "l"(a.u), "l"(b.u));
+  return r;
+}
+__device__ __forceinline__ P2 p2_shfl_xor(P2 a, int m) {
+  return P2{(unsigned long long)__shfl_xor_sync(0xffffffffu, a.u, m)};
 }
 
 // Z2[r][16k+j] = b2[k][j] + sum_i A1[r][32k+i] * W2[k][j][i]
-// Warp k <-> head k; a thread owns TWO rows (lane, lane + 32 of a 64-row tile) and reads its 128-byte slices of
-// A1 straight from global (16 independent 128-bit loads in flight per thread, no shared-memory staging, no block
-// barrier in the loop); the transposed weight Wt[k][i][0..15] is read as 4 broadcast LDS.128 per input feature and
-// shared by both rows; packed FFMA2.  Column statistics: 31-shuffle transpose-reduce per tile, double per thread.
-constexpr int TR2 = 64;
-__global__ void __launch_bounds__(kMidThreads)
+// Each lane forms the partial sums of all 16 outputs of its head over its 4 inputs (32 FFMA2), then the 8 lanes of
+// a head transpose-reduce them (8 + 4 + 2 shuffles) so that lane c ends with outputs 2c, 2c+1 = its float2 of the
+// row's 256 contiguous output bytes.  The exchange needs no selects: lane c keeps its partials in the order
+// m -> output m ^ 2c (a permutation of its register-resident weights), so in every stage every lane keeps the low
+// half of its accumulators and sends the high half.  Column statistics: a lane owns two columns for its whole life.
+__global__ void __launch_bounds__(kMidFwdThreads, kMidFwdBlocks)
 clf_mid_fwd_kernel(long long rows, const float* __restrict__ A1, const float* __restrict__ W2,
                    const float* __restrict__ b2, float* __restrict__ Z2, double* __restrict__ parts) {
-  __shared__ __align__(16) float Wt[4 * 32 * 16];  // Wt[k][i][j] = W2[k][j][i]
-  __shared__ float bs[64];
-  const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
-  for (int i = tid; i < 2048; i += kMidThreads) {
-    const int kk = i >> 9, j = (i >> 5) & 15, ii = i & 31;
-    Wt[(kk * 32 + ii) * 16 + j] = __ldg(W2 + i);
+  constexpr int kWarps = kMidFwdThreads / 32;
+  __shared__ double red[kWarps][128];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, k = lane >> 3, c = lane & 7;
+  // wp[jp][e] = (W2[k][2(jp^c)][4c+e], W2[k][2(jp^c)+1][4c+e])
+  P2 wp[8][4];
+#pragma unroll
+  for (int jp = 0; jp < 8; ++jp) {
+    const int j = 2 * (jp ^ c);
+    const float4 w0 = ldg4(W2 + (k * 16 + j) * 32 + c * 4), w1 = ldg4(W2 + (k * 16 + j + 1) * 32 + c * 4);
+    wp[jp][0] = p2(w0.x, w1.x);
+    wp[jp][1] = p2(w0.y, w1.y);
+    wp[jp][2] = p2(w0.z, w1.z);
+    wp[jp][3] = p2(w0.w, w1.w);
   }
-  if (tid < 64) bs[tid] = __ldg(b2 + tid);
-  __syncthreads();
-  double run = 0.0;  // lane l < 16: sum of column 16k + l; lane 16 + l: sum of squares of that column
-  const long long ntiles = (rows + TR2 - 1) / TR2;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long r0 = tile * TR2 + lane, r1 = r0 + 32;
-    const bool ok0 = r0 < rows, ok1 = r1 < rows;
-    float4 a0[8], a1[8];
+  const P2 bias = p2(__ldg(b2 + lane * 2), __ldg(b2 + lane * 2 + 1));
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  double ds0 = 0.0, ds1 = 0.0, dq0 = 0.0, dq1 = 0.0;
+  int since_flush = 0;
+  constexpr int R = 4;  // rows in flight per warp
+  const long long wid = (long long)blockIdx.x * kWarps + warp, nw = (long long)gridDim.x * kWarps;
+  for (long long r0 = wid * R; r0 < rows; r0 += nw * R) {
+    float4 a[R];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      a0[q] = ok0 ? ldg4(A1 + r0 * 128 + k * 32 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      a1[q] = ok1 ? ldg4(A1 + r1 * 128 + k * 32 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    float z0[16], z1[16];
+    for (int u = 0; u < R; ++u)
+      a[u] = r0 + u < rows ? ldg4(A1 + (r0 + u) * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) z0[j] = z1[j] = bs[k * 16 + j];
+    for (int u = 0; u < R; ++u) {
+      if (r0 + u >= rows) break;  // warp-uniform
+      const P2 ax = p2(a[u].x, a[u].x), ay = p2(a[u].y, a[u].y), az = p2(a[u].z, a[u].z), aw = p2(a[u].w, a[u].w);
+      P2 acc[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float av0[4] = {a0[q].x, a0[q].y, a0[q].z, a0[q].w}, av1[4] = {a1[q].x, a1[q].y, a1[q].z, a1[q].w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float* wrow = Wt + (k * 32 + q * 4 + e) * 16;
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 w = *reinterpret_cast<const float4*>(wrow + j4 * 4);
-          fma2(z0[4 * j4], z0[4 * j4 + 1], av0[e], w.x, w.y);
-          fma2(z0[4 * j4 + 2], z0[4 * j4 + 3], av0[e], w.z, w.w);
-          fma2(z1[4 * j4], z1[4 * j4 + 1], av1[e], w.x, w.y);
-          fma2(z1[4 * j4 + 2], z1[4 * j4 + 3], av1[e], w.z, w.w);
-        }
+      for (int jp = 0; jp < 8; ++jp) {
+        acc[jp] = p2_mul(ax, wp[jp][0]);
+        acc[jp] = p2_fma(ay, wp[jp][1], acc[jp]);
+        acc[jp] = p2_fma(az, wp[jp][2], acc[jp]);
+        acc[jp] = p2_fma(aw, wp[jp][3], acc[jp]);
       }
-    }
 #pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-      if (ok0) st4(Z2 + r0 * 64 + k * 16 + j4 * 4, make_float4(z0[4 * j4], z0[4 * j4 + 1], z0[4 * j4 + 2], z0[4 * j4 + 3]));
-      if (ok1) st4(Z2 + r1 * 64 + k * 16 + j4 * 4, make_float4(z1[4 * j4], z1[4 * j4 + 1], z1[4 * j4 + 2], z1[4 * j4 + 3]));
-    }
-    if (parts) {
-      float v[32];
+      for (int i = 0; i < 4; ++i) acc[i] = p2_add(acc[i], p2_shfl_xor(acc[i + 4], 4));
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float x0 = ok0 ? z0[j] : 0.f, x1 = ok1 ? z1[j] : 0.f;
-        v[j] = x0 + x1;
-        v[16 + j] = fmaf(x0, x0, x1 * x1);
-      }
-      run += (double)transpose_reduce32(v, lane);
+      for (int i = 0; i < 2; ++i) acc[i] = p2_add(acc[i], p2_shfl_xor(acc[i + 2], 2));
+      const P2 z = p2_add(p2_add(acc[0], p2_shfl_xor(acc[1], 1)), bias);
+      const float z0 = p2_lo(z), z1 = p2_hi(z);
+      *reinterpret_cast<float2*>(Z2 + (r0 + u) * 64 + lane * 2) = make_float2(z0, z1);
+      s0 += z0;
+      s1 += z1;
+      q0 = fmaf(z0, z0, q0);
+      q1 = fmaf(z1, z1, q1);
+    }
+    if (++since_flush == 16) {  // 64 rows per fp32 run, then double
+      ds0 += s0; ds1 += s1; dq0 += q0; dq1 += q1;
+      s0 = s1 = q0 = q1 = 0.f;
+      since_flush = 0;
     }
   }
-  if (parts) {  // parts[block][0..63] sums, [64..127] sums of squares
-    const int col = k * 16 + (lane & 15);
-    parts[(size_t)blockIdx.x * 128 + (lane < 16 ? col : 64 + col)] = run;
+  if (parts) {  // parts[block][0..63] sums, [64..127] sums of squares; warps combined in fixed order
+    red[warp][lane * 2] = ds0 + (double)s0;
+    red[warp][lane * 2 + 1] = ds1 + (double)s1;
+    red[warp][64 + lane * 2] = dq0 + (double)q0;
+    red[warp][64 + lane * 2 + 1] = dq1 + (double)q1;
+    __syncthreads();
+    if (tid < 128) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) t += red[w][tid];
+      parts[(size_t)blockIdx.x * 128 + tid] = t;
+    }
   }
 }
 
 // dA1[r][32k+i] = sum_j dZ2[r][16k+j] W2[k][j][i];  per-block partials of dW2[k][j][i], db2[k][j].
+// Same lane mapping.  Per row a lane needs its float4 of A1 and the 16 dZ2 values of its head, forms its float4 of
+// dA1 (32 FFMA2 against the register-resident weights) and accumulates its 16 x 4 block of dW2 (32 FFMA2); db2: the
+// lane's own float2 of the dZ2 row.  Weights + accumulators take 128 registers, so rows cannot be prefetched into
+// registers (one row in flight per warp: 2.9 TB/s, latency-bound); instead every warp streams its rows through a
+// PRIVATE shared-memory ring with cp.async (kMidDepth rows = 6 KB per warp in flight, no block-level barrier).
 constexpr int kMidPart = 2048 + 64;
-__global__ void __launch_bounds__(kMidThreads, 6)
+constexpr int kMidDepth = 8;                 // ring slots per warp
+constexpr int kMidRowBytes = 512 + 256;      // one row of A1 + one row of dZ2
+constexpr int kMidBwdSmem = (kMidBwdThreads / 32) * kMidDepth * kMidRowBytes;
+__global__ void __launch_bounds__(kMidBwdThreads, kMidBwdBlocks)
 clf_mid_bwd_kernel(long long rows, const float* __restrict__ A1, const float* __restrict__ W2,
                    const float* __restrict__ dZ2, float* __restrict__ dA1, float* __restrict__ parts) {
-  __shared__ __align__(16) float As[TR * LDA];   // A1 tile, then reused for the dA1 tile
-  __shared__ __align__(16) float Ws[4 * 16 * 32];
-  __shared__ __align__(16) float Gs[TR * LDO];   // dZ2 tile
-  const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
-  for (int i = tid; i < 2048; i += kMidThreads) Ws[i] = __ldg(W2 + i);
-  float wacc[16];  // dW2[k][j][lane]
+  constexpr int kWarps = kMidBwdThreads / 32;
+  constexpr int kRedFloats = kWarps * kMidPart;
+  constexpr int kRingFloats = kMidBwdSmem / 4;
+  __shared__ __align__(16) float smem[kRedFloats > kRingFloats ? kRedFloats : kRingFloats];  // ring, then the block reduction
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, k = lane >> 3, c = lane & 7;
+  P2 w[16][2];  // (W2[k][j][4c], [4c+1]), (W2[k][j][4c+2], [4c+3])
 #pragma unroll
-  for (int j = 0; j < 16; ++j) wacc[j] = 0.f;
-  float bacc = 0.f;  // db2[k][lane] for lane < 16
-  const long long ntiles = (rows + TR - 1) / TR;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long row0 = tile * TR;
-    const int nvalid = (int)min((long long)TR, rows - row0);
-    __syncthreads();
-    for (int i = tid; i < TR * 32; i += kMidThreads) {
-      int r = i >> 5, c4 = i & 31;
-      float4 v = r < nvalid ? ldg4(A1 + (row0 + r) * 128 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(As + r * LDA + c4 * 4) = v;
-    }
-    for (int i = tid; i < TR * 16; i += kMidThreads) {
-      int r = i >> 4, c4 = i & 15;
-      float4 v = r < nvalid ? ldg4(dZ2 + (row0 + r) * 64 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(Gs + r * LDO + c4 * 4) = v;
-    }
-    __syncthreads();
-    // weight / bias gradient: lane <-> input feature i
-#pragma unroll 4
-    for (int r = 0; r < TR; ++r) {
-      const float a = As[r * LDA + k * 32 + lane];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {  // packed FFMA2: two output features per issue slot
-        const float4 gz = *reinterpret_cast<const float4*>(Gs + r * LDO + k * 16 + q * 4);
-        fma2(wacc[4 * q], wacc[4 * q + 1], a, gz.x, gz.y);
-        fma2(wacc[4 * q + 2], wacc[4 * q + 3], a, gz.z, gz.w);
-      }
-      if (lane < 16) bacc += Gs[r * LDO + k * 16 + lane];
-    }
-    // input gradient: lane <-> row
-    float dz[16];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 gz = *reinterpret_cast<const float4*>(Gs + lane * LDO + k * 16 + q * 4);
-      dz[4 * q] = gz.x; dz[4 * q + 1] = gz.y; dz[4 * q + 2] = gz.z; dz[4 * q + 3] = gz.w;
-    }
-    __syncthreads();  // everyone is done reading the A1 tile -> reuse As for dA1
-#pragma unroll
-    for (int i4 = 0; i4 < 8; ++i4) {
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float4 w = *reinterpret_cast<const float4*>(Ws + (k * 16 + j) * 32 + i4 * 4);
-        fma2(o.x, o.y, dz[j], w.x, w.y);
-        fma2(o.z, o.w, dz[j], w.z, w.w);
-      }
-      *reinterpret_cast<float4*>(As + lane * LDA + k * 32 + i4 * 4) = o;
-    }
-    __syncthreads();
-    for (int i = tid; i < TR * 32; i += kMidThreads) {
-      int r = i >> 5, c4 = i & 31;
-      if (r < nvalid) st4(dA1 + (row0 + r) * 128 + c4 * 4, *reinterpret_cast<const float4*>(As + r * LDA + c4 * 4));
-    }
+  for (int j = 0; j < 16; ++j) {
+    const float4 v = ldg4(W2 + (k * 16 + j) * 32 + c * 4);
+    w[j][0] = p2(v.x, v.y);
+    w[j][1] = p2(v.z, v.w);
   }
-  float* P = parts + (size_t)blockIdx.x * kMidPart;
+  P2 wacc[16][2];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) P[(k * 16 + j) * 32 + lane] = wacc[j];
-  if (lane < 16) P[2048 + k * 16 + lane] = bacc;
+  for (int j = 0; j < 16; ++j) wacc[j][0] = wacc[j][1] = p2(0.f, 0.f);
+  P2 bacc = p2(0.f, 0.f);
+  const long long wid = (long long)blockIdx.x * kWarps + warp, nw = (long long)gridDim.x * kWarps;
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem) + warp * kMidDepth * kMidRowBytes;
+  // slot layout: [512 B of A1][256 B of dZ2]; lane l copies its 16 bytes of A1 and (l < 16) of dZ2
+  auto issue = [&](long long r, int slot) {
+    if (r < rows) {
+      const uint32_t dst = ring + slot * kMidRowBytes;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + lane * 16), "l"(A1 + r * 128 + lane * 4) : "memory");
+      if (lane < 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512 + lane * 16), "l"(dZ2 + r * 64 + lane * 4) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int d = 0; d < kMidDepth - 1; ++d) issue(wid + d * nw, d);
+  int slot = 0;
+  for (long long r = wid; r < rows; r += nw) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kMidDepth - 2) : "memory");
+    __syncwarp();
+    const float* row = smem + (warp * kMidDepth + slot) * (kMidRowBytes / 4);
+    const float4 a = *reinterpret_cast<const float4*>(row + lane * 4);
+    const float4 g0 = *reinterpret_cast<const float4*>(row + 128 + k * 16),
+                 g1 = *reinterpret_cast<const float4*>(row + 128 + k * 16 + 4),
+                 g2 = *reinterpret_cast<const float4*>(row + 128 + k * 16 + 8),
+                 g3 = *reinterpret_cast<const float4*>(row + 128 + k * 16 + 12);
+    const float2 gb = *reinterpret_cast<const float2*>(row + 128 + lane * 2);
+    __syncwarp();  // every lane has read the slot: refill it with the row kMidDepth - 1 ahead
+    issue(r + (long long)(kMidDepth - 1) * nw, (slot + kMidDepth - 1) % kMidDepth);
+    slot = (slot + 1) % kMidDepth;
+    const float dz[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w,
+                          g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
+    const P2 a01 = p2(a.x, a.y), a23 = p2(a.z, a.w);
+    P2 o01 = p2(0.f, 0.f), o23 = o01;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const P2 d = p2(dz[j], dz[j]);
+      o01 = p2_fma(d, w[j][0], o01);
+      o23 = p2_fma(d, w[j][1], o23);
+      wacc[j][0] = p2_fma(d, a01, wacc[j][0]);
+      wacc[j][1] = p2_fma(d, a23, wacc[j][1]);
+    }
+    bacc = p2_add(bacc, p2(gb.x, gb.y));
+    st4(dA1 + r * 128 + lane * 4, make_float4(p2_lo(o01), p2_hi(o01), p2_lo(o23), p2_hi(o23)));
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();  // all rings are drained: reuse the memory for the block reduction
+  // block partial: warps combined in fixed order.  Layout P[(k*16+j)*32 + i], P[2048 + 16k + j]
+  float* red = smem + warp * kMidPart;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    *reinterpret_cast<float4*>(red + (k * 16 + j) * 32 + c * 4) =
+        make_float4(p2_lo(wacc[j][0]), p2_hi(wacc[j][0]), p2_lo(wacc[j][1]), p2_hi(wacc[j][1]));
+  red[2048 + lane * 2] = p2_lo(bacc);
+  red[2048 + lane * 2 + 1] = p2_hi(bacc);
+  __syncthreads();
+  float* P = parts + (size_t)blockIdx.x * kMidPart;
+  for (int i = tid; i < kMidPart; i += kMidBwdThreads) {
+    float t = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < kWarps; ++wq) t += smem[wq * kMidPart + i];
+    P[i] = t;
+  }
 }
 
 __global__ void parts_reduce_kernel(int nparts, int width, const float* __restrict__ parts, int n_a,
@@ -282,11 +316,12 @@ int eg_clf_mid_fwd(int64_t rows, const float* A1, const float* W2, const float* 
     set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
     return EG_ERR_WORKSPACE;
   }
-  long long ntiles = (rows + TR2 - 1) / TR2;
-  int grid = (int)(ntiles < kMidGrid ? ntiles : kMidGrid);
+  const long long want = (rows + 31) / 32;  // >= 4 rows per warp
+  const int cap = kNumSMs * kMidFwdBlocks;
+  const int grid = (int)(want < cap ? want : cap);
   double* parts = stats ? reinterpret_cast<double*>(ws) : nullptr;
   ProfileScope prof("clf_mid_fwd", as_stream(stream));
-  clf_mid_fwd_kernel<<<grid, kMidThreads, 0, as_stream(stream)>>>(rows, A1, W2, b2, Z2, parts);
+  clf_mid_fwd_kernel<<<grid, kMidFwdThreads, 0, as_stream(stream)>>>(rows, A1, W2, b2, Z2, parts);
   EG_LAUNCH_CHECK();
   if (stats) return launch_stats_finalize(grid, 64, 64, rows, parts, mean, var, as_stream(stream));
   return EG_OK;
@@ -300,11 +335,12 @@ int eg_clf_mid_bwd(int64_t rows, const float* A1, const float* W2, const float* 
     return EG_ERR_WORKSPACE;
   }
   static_assert((size_t)kMidGrid * kMidPart * sizeof(float) <= kWgradBytes, "clf_mid_bwd partials fit the workspace");
-  long long ntiles = (rows + TR - 1) / TR;
-  int grid = (int)(ntiles < kMidGrid ? ntiles : kMidGrid);
+  const long long want = (rows + 15) / 16;
+  const int cap = kNumSMs * kMidBwdBlocks;
+  const int grid = (int)(want < cap ? want : cap);
   float* parts = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);
   ProfileScope prof("clf_mid_bwd", as_stream(stream));
-  clf_mid_bwd_kernel<<<grid, kMidThreads, 0, as_stream(stream)>>>(rows, A1, W2, dZ2, dA1, parts);
+  clf_mid_bwd_kernel<<<grid, kMidBwdThreads, 0, as_stream(stream)>>>(rows, A1, W2, dZ2, dA1, parts);
   EG_LAUNCH_CHECK();
   parts_reduce_kernel<<<(kMidPart + 255) / 256, 256, 0, as_stream(stream)>>>(grid, kMidPart, parts, 2048, dW2, db2);
   EG_LAUNCH_CHECK();

@@ -117,7 +117,7 @@ struct TcParams {
 };
 
 #ifdef EG_TC_TIMING
-__device__ long long g_tc_dbg[kNumSMs][8];  // per CTA: cycles spent waiting, by role (see eg_tc_debug_read)
+__device__ long long g_tc_dbg[kNumSMs][12];  // per CTA: cycles spent waiting, by role (see eg_tc_debug_read)
 #define TC_TIMED_WAIT(slot, bar, par)            \
   do {                                           \
     const long long _t = clock64();              \
@@ -183,6 +183,7 @@ template <bool GATHER>
 __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
 #ifdef EG_TC_TIMING
   long long dbg_acc[4] = {0, 0, 0, 0};
+  long long dbg_n = 0;
   const long long dbg_t0 = clock64();
 #endif
   extern __shared__ uint8_t smem_raw[];
@@ -394,6 +395,9 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
             release();
             continue;
 #endif
+#ifdef EG_TC_TIMING
+            const long long _tg = clock64();
+#endif
             float4 x[kIters][6];
 #pragma unroll
             for (int i = 0; i < kIters; ++i)
@@ -414,6 +418,10 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
               emit(a_hi, i, acc);
               aggv[i] = acc;
             }
+#ifdef EG_TC_TIMING
+            dbg_acc[3] += clock64() - _tg;  // lattice tiles: gather + split + operand stores of one chunk
+            ++dbg_n;
+#endif
             release();
             if (agg_out) {  // A_hat dH side output: stored after the chunk is handed to the MMA
 #pragma unroll
@@ -808,7 +816,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
 #ifdef EG_TC_TIMING
   if (lane == 0) {
     long long* d = g_tc_dbg[blockIdx.x];
-    if (warp == kProdWarp0) { d[0] = dbg_acc[0]; d[5] = dbg_acc[1]; d[7] = dbg_acc[2]; } // compute warp 0: wait operand stage, wait raw, fence
+    if (warp == kProdWarp0) { d[0] = dbg_acc[0]; d[5] = dbg_acc[1]; d[7] = dbg_acc[2]; d[8] = dbg_acc[3]; d[9] = dbg_n; } // compute warp 0: wait operand stage, wait raw, fence
     if (warp == kLoadWarp0) d[6] = dbg_acc[0];                       // loader: wait for a free raw stage
     if (warp == kMmaWarp) { d[1] = dbg_acc[0]; d[2] = dbg_acc[1]; } // MMA: wait acc_empty, wait full
     if (warp == 0) { d[3] = dbg_acc[0]; d[4] = clock64() - dbg_t0; } // epilogue: wait acc_full; total cycles
@@ -849,8 +857,8 @@ int launch(const TcParams& p, float* mean, float* var, void* ws, size_t ws_bytes
 }  // namespace
 
 #ifdef EG_TC_TIMING
-extern "C" int eg_tc_debug_read(long long* out) {  // HOST buffer of kNumSMs * 8 counters
-  return cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(long long) * kNumSMs * 8) == cudaSuccess ? 0 : -2;
+extern "C" int eg_tc_debug_read(long long* out) {  // HOST buffer of kNumSMs * 12 counters
+  return cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(long long) * kNumSMs * 12) == cudaSuccess ? 0 : -2;
 }
 #endif
 

@@ -80,7 +80,11 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
 // barrier receives one arrival from this thread once all its earlier cp.async have landed (.noinc: the
 // arrival is part of the barrier's initial expected count).
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+#ifdef EG_CP_L2_256
+  asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+#else
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

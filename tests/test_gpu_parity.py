@@ -274,6 +274,45 @@ def test_linear128_wgrad(rows):
     assert ok, worst
 
 
+@pytest.mark.parametrize("rows", [1, 3, 33, 1000, 144040, 300007])  # ragged: not a multiple of the 4 rows in flight
+def test_clf_mid_entry_points(rows):
+    """Layer 4 of the four classifier heads (src/core/models.py:363-377): 4 x Linear(32, 16) on the column blocks
+    of a [rows, 128] tensor, its column statistics, input / weight / bias gradients, against fp64 torch."""
+    from echoglad_b200._lib import check, lib
+    gen = torch.Generator().manual_seed(rows)
+    a1 = torch.randn(rows, 128, generator=gen)
+    w2 = torch.randn(4, 16, 32, generator=gen) * 0.3
+    b2 = torch.randn(4, 16, generator=gen)
+    dz2 = torch.randn(rows, 64, generator=gen)
+    a1d, w2d, b2d, dz2d = (t.to(DEV).contiguous() for t in (a1, w2, b2, dz2))
+    z2 = torch.empty(rows, 64, device=DEV)
+    mean, var = torch.empty(64, device=DEV), torch.empty(64, device=DEV)
+    ws = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib.eg_clf_mid_fwd(rows, a1d.data_ptr(), w2d.data_ptr(), b2d.data_ptr(), z2.data_ptr(), mean.data_ptr(),
+                             var.data_ptr(), ws.data_ptr(), WORKSPACE_BYTES, st), "eg_clf_mid_fwd")
+    ref = torch.einsum("rki,kji->rkj", a1.double().view(rows, 4, 32), w2.double()) + b2.double()
+    ref = ref.reshape(rows, 64)
+    ok, worst = close(z2.cpu(), ref, 1e-5, 1e-5)
+    assert ok, worst
+    ok, worst = close(mean.cpu(), ref.mean(0), 1e-5, 1e-5)
+    assert ok, worst
+    # E[z^2] - E[z]^2 with fp32 squares: absolute accuracy 1e-6 of the second moment (rows = 1: var = 0 exactly)
+    rvar = ref.var(0, unbiased=False)
+    assert ((var.cpu().double() - rvar).abs() <= 1e-4 * rvar + 2e-6 * (rvar + ref.mean(0) ** 2)).all()
+    da1 = torch.empty(rows, 128, device=DEV)
+    dw2, db2 = torch.empty(4, 16, 32, device=DEV), torch.empty(4, 16, device=DEV)
+    check(lib.eg_clf_mid_bwd(rows, a1d.data_ptr(), w2d.data_ptr(), dz2d.data_ptr(), da1.data_ptr(), dw2.data_ptr(),
+                             db2.data_ptr(), ws.data_ptr(), WORKSPACE_BYTES, st), "eg_clf_mid_bwd")
+    g = dz2.double().view(rows, 4, 16)
+    ok, worst = close(da1.cpu(), torch.einsum("rkj,kji->rki", g, w2.double()).reshape(rows, 128), 1e-5, 1e-5)
+    assert ok, worst
+    ok, worst = close(dw2.cpu(), torch.einsum("rkj,rki->kji", g, a1.double().view(rows, 4, 32)), 1e-4, 1e-5)
+    assert ok, worst
+    ok, worst = close(db2.cpu(), g.sum(0), 1e-4, 1e-5)
+    assert ok, worst
+
+
 # ---- BN + dropout + act + residual ----------------------------------------------------------------------------
 
 @pytest.mark.parametrize("cols", [64, 128])

@@ -79,6 +79,16 @@ def main():
                                                        1e-5, 0.5, 7, 1, 1, P(out), P(mean.clone()), P(var.clone()),
                                                        P(ws), WORKSPACE_BYTES, st)), 5 * U),
     }
+    w2 = torch.randn(4, 16, 32, device=dev, generator=gen) * 0.3
+    b2 = torch.randn(4, 16, device=dev, generator=gen)
+    z2 = torch.empty(rows, 64, device=dev)
+    dz2 = torch.randn(rows, 64, device=dev, generator=gen)
+    dw2, db2 = torch.empty(4, 16, 32, device=dev), torch.empty(4, 16, device=dev)
+    m2, v2 = torch.empty(64, device=dev), torch.empty(64, device=dev)
+    cases["clf_mid_fwd"] = (lambda: check(lib.eg_clf_mid_fwd(rows, P(x), P(w2), P(b2), P(z2), P(m2), P(v2), P(ws),
+                                                             WORKSPACE_BYTES, st)), U * 3 // 2)
+    cases["clf_mid_bwd"] = (lambda: check(lib.eg_clf_mid_bwd(rows, P(x), P(w2), P(dz2), P(out), P(dw2), P(db2), P(ws),
+                                                             WORKSPACE_BYTES, st)), U * 5 // 2)
     only = [s for s in args.only.split(",") if s]
     check(lib.eg_col_stats(rows, 128, P(x), P(mean), P(var), P(ws), WORKSPACE_BYTES, st))
     res = {}
@@ -89,13 +99,13 @@ def main():
         res[name] = {"ms": round(ms, 4), "algo_GB": round(nbytes / 1e9, 3), "GBps": round(nbytes / ms / 1e6, 1)}
         if hasattr(lib, "eg_tc_debug_read") and name in ("gcn_conv_fwd", "linear128", "gcn_conv_bwd"):
             import ctypes as C
-            buf = (C.c_longlong * (148 * 8))()
+            buf = (C.c_longlong * (148 * 12))()
             torch.cuda.synchronize()
             lib.eg_tc_debug_read(buf)
             import numpy as np
-            a = np.array(buf).reshape(148, 8).mean(0)
+            a = np.array(buf).reshape(148, 12).mean(0)
             print(f"   tc wait cycles/CTA: compute-wait-operand {a[0]:.0f} compute-wait-raw {a[5]:.0f} loader-wait-raw-empty {a[6]:.0f} "
-                  f"compute-fence {a[7]:.0f} mma-wait-acc-empty {a[1]:.0f} mma-wait-full {a[2]:.0f} epilogue-wait-acc-full {a[3]:.0f} total {a[4]:.0f}")
+                  f"compute-fence {a[7]:.0f} lattice-chunk-busy {a[8]:.0f} over {a[9]:.0f} chunks mma-wait-acc-empty {a[1]:.0f} mma-wait-full {a[2]:.0f} epilogue-wait-acc-full {a[3]:.0f} total {a[4]:.0f}")
         print(f"{name:14s} {ms:8.3f} ms   {nbytes / 1e9:6.2f} GB algorithmic   {nbytes / ms / 1e6:8.1f} GB/s", flush=True)
     print(json.dumps({"batch": B, "rows": rows, "results": res}))
 
