@@ -14,8 +14,8 @@ namespace {
 // first version gave a thread its own rows: 32 different 128-byte lines per load instruction, LSU-bound at 89 %).
 // The lane's 64 weights W2[k][0..15][4c..4c+3] live in registers; there is no shared-memory traffic in the loops.
 constexpr int kMidFwdThreads = 256, kMidFwdBlocks = 2;   // per SM
-constexpr int kMidBwdThreads = 128, kMidBwdBlocks = 3;
-constexpr int kMidGrid = kNumSMs * 3;
+constexpr int kMidBwdThreads = 128, kMidBwdBlocks = 4;
+constexpr int kMidGrid = kNumSMs * 4;
 static_assert((size_t)kMidGrid * 128 * sizeof(double) <= kStatsBytes, "clf_mid_fwd partials fit the stats area");
 
 struct P2 {  // packed fp32 pair: one FFMA2 / FADD2 issue slot for two values
@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(kMidFwdThreads, kMidFwdBlocks)
 clf_mid_fwd_kernel(long long rows, const float* __restrict__ A1, const float* __restrict__ W2,
                    const float* __restrict__ b2, float* __restrict__ Z2, double* __restrict__ parts) {
   constexpr int kWarps = kMidFwdThreads / 32;
+  constexpr int kFwdDepth = 8;
   __shared__ double red[kWarps][128];
+  __shared__ __align__(16) float ring[kWarps * kFwdDepth * 128];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, k = lane >> 3, c = lane & 7;
   // wp[jp][e] = (W2[k][2(jp^c)][4c+e], W2[k][2(jp^c)+1][4c+e])
   P2 wp[8][4];
@@ -72,43 +74,50 @@ clf_mid_fwd_kernel(long long rows, const float* __restrict__ A1, const float* __
   float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
   double ds0 = 0.0, ds1 = 0.0, dq0 = 0.0, dq1 = 0.0;
   int since_flush = 0;
-  constexpr int R = 4;  // rows in flight per warp
+  // rows stream through a private per-warp shared-memory ring (cp.async, kFwdDepth rows = 4 KB per warp in flight)
   const long long wid = (long long)blockIdx.x * kWarps + warp, nw = (long long)gridDim.x * kWarps;
-  for (long long r0 = wid * R; r0 < rows; r0 += nw * R) {
-    float4 a[R];
+  const uint32_t ring_u = (uint32_t)__cvta_generic_to_shared(ring) + warp * kFwdDepth * 512 + lane * 16;
+  auto issue = [&](long long r, int slot) {
+    if (r < rows)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_u + slot * 512), "l"(A1 + r * 128 + lane * 4) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
 #pragma unroll
-    for (int u = 0; u < R; ++u)
-      a[u] = r0 + u < rows ? ldg4(A1 + (r0 + u) * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int d = 0; d < kFwdDepth - 1; ++d) issue(wid + d * nw, d);
+  int slot = 0;
+  for (long long r = wid; r < rows; r += nw) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kFwdDepth - 2) : "memory");
+    // each lane reads back exactly the 16 bytes it copied itself: no warp barrier needed
+    const float4 a = *reinterpret_cast<const float4*>(ring + (warp * kFwdDepth + slot) * 128 + lane * 4);
+    issue(r + (long long)(kFwdDepth - 1) * nw, (slot + kFwdDepth - 1) % kFwdDepth);
+    slot = (slot + 1) % kFwdDepth;
+    const P2 ax = p2(a.x, a.x), ay = p2(a.y, a.y), az = p2(a.z, a.z), aw = p2(a.w, a.w);
+    P2 acc[8];
 #pragma unroll
-    for (int u = 0; u < R; ++u) {
-      if (r0 + u >= rows) break;  // warp-uniform
-      const P2 ax = p2(a[u].x, a[u].x), ay = p2(a[u].y, a[u].y), az = p2(a[u].z, a[u].z), aw = p2(a[u].w, a[u].w);
-      P2 acc[8];
-#pragma unroll
-      for (int jp = 0; jp < 8; ++jp) {
-        acc[jp] = p2_mul(ax, wp[jp][0]);
-        acc[jp] = p2_fma(ay, wp[jp][1], acc[jp]);
-        acc[jp] = p2_fma(az, wp[jp][2], acc[jp]);
-        acc[jp] = p2_fma(aw, wp[jp][3], acc[jp]);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = p2_add(acc[i], p2_shfl_xor(acc[i + 4], 4));
-#pragma unroll
-      for (int i = 0; i < 2; ++i) acc[i] = p2_add(acc[i], p2_shfl_xor(acc[i + 2], 2));
-      const P2 z = p2_add(p2_add(acc[0], p2_shfl_xor(acc[1], 1)), bias);
-      const float z0 = p2_lo(z), z1 = p2_hi(z);
-      *reinterpret_cast<float2*>(Z2 + (r0 + u) * 64 + lane * 2) = make_float2(z0, z1);
-      s0 += z0;
-      s1 += z1;
-      q0 = fmaf(z0, z0, q0);
-      q1 = fmaf(z1, z1, q1);
+    for (int jp = 0; jp < 8; ++jp) {
+      acc[jp] = p2_mul(ax, wp[jp][0]);
+      acc[jp] = p2_fma(ay, wp[jp][1], acc[jp]);
+      acc[jp] = p2_fma(az, wp[jp][2], acc[jp]);
+      acc[jp] = p2_fma(aw, wp[jp][3], acc[jp]);
     }
-    if (++since_flush == 16) {  // 64 rows per fp32 run, then double
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = p2_add(acc[i], p2_shfl_xor(acc[i + 4], 4));
+#pragma unroll
+    for (int i = 0; i < 2; ++i) acc[i] = p2_add(acc[i], p2_shfl_xor(acc[i + 2], 2));
+    const P2 z = p2_add(p2_add(acc[0], p2_shfl_xor(acc[1], 1)), bias);
+    const float z0 = p2_lo(z), z1 = p2_hi(z);
+    *reinterpret_cast<float2*>(Z2 + r * 64 + lane * 2) = make_float2(z0, z1);
+    s0 += z0;
+    s1 += z1;
+    q0 = fmaf(z0, z0, q0);
+    q1 = fmaf(z1, z1, q1);
+    if (++since_flush == 64) {  // 64 rows per fp32 run, then double
       ds0 += s0; ds1 += s1; dq0 += q0; dq1 += q1;
       s0 = s1 = q0 = q1 = 0.f;
       since_flush = 0;
     }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   if (parts) {  // parts[block][0..63] sums, [64..127] sums of squares; warps combined in fixed order
     red[warp][lane * 2] = ds0 + (double)s0;
     red[warp][lane * 2 + 1] = ds1 + (double)s1;
@@ -125,44 +134,48 @@ clf_mid_fwd_kernel(long long rows, const float* __restrict__ A1, const float* __
 }
 
 // dA1[r][32k+i] = sum_j dZ2[r][16k+j] W2[k][j][i];  per-block partials of dW2[k][j][i], db2[k][j].
-// Same lane mapping.  Per row a lane needs its float4 of A1 and the 16 dZ2 values of its head, forms its float4 of
-// dA1 (32 FFMA2 against the register-resident weights) and accumulates its 16 x 4 block of dW2 (32 FFMA2); db2: the
-// lane's own float2 of the dZ2 row.  Weights + accumulators take 128 registers, so rows cannot be prefetched into
-// registers (one row in flight per warp: 2.9 TB/s, latency-bound); instead every warp streams its rows through a
-// PRIVATE shared-memory ring with cp.async (kMidDepth rows = 6 KB per warp in flight, no block-level barrier).
+// A warp owns HALF rows (heads 2h, 2h+1; h = warp & 1): lane = 16 kk + c  <->  head 2h + kk, inputs 2c, 2c+1 of that
+// head = the lane's float2 of the half row's 256 contiguous bytes.  Per half row a lane needs its float2 of A1 and
+// the 16 dZ2 values of its head; the packed FFMA2 run over PAIRS OF j, so the dZ2 pairs are used as they sit in the
+// registers of a 128-bit load (no broadcast packing): dA1 = even-j + odd-j partial sums (16 FFMA2 + 2 adds), the
+// lane's 16 x 2 block of dW2 (16 FFMA2).  Weights + accumulators take 64 registers, which leaves room for 16 warps
+// per SM; every warp streams its half rows through a PRIVATE shared-memory ring with cp.async (kMidDepth slots
+// in flight, no block-level barrier in the loop).
 constexpr int kMidPart = 2048 + 64;
 constexpr int kMidDepth = 8;                 // ring slots per warp
-constexpr int kMidRowBytes = 512 + 256;      // one row of A1 + one row of dZ2
-constexpr int kMidBwdSmem = (kMidBwdThreads / 32) * kMidDepth * kMidRowBytes;
+constexpr int kMidSlotBytes = 256 + 128;     // half a row of A1 + half a row of dZ2
+constexpr int kMidHalfPart = 1024 + 32;      // one half's share of a partial
 __global__ void __launch_bounds__(kMidBwdThreads, kMidBwdBlocks)
 clf_mid_bwd_kernel(long long rows, const float* __restrict__ A1, const float* __restrict__ W2,
                    const float* __restrict__ dZ2, float* __restrict__ dA1, float* __restrict__ parts) {
   constexpr int kWarps = kMidBwdThreads / 32;
-  constexpr int kRedFloats = kWarps * kMidPart;
-  constexpr int kRingFloats = kMidBwdSmem / 4;
-  __shared__ __align__(16) float smem[kRedFloats > kRingFloats ? kRedFloats : kRingFloats];  // ring, then the block reduction
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, k = lane >> 3, c = lane & 7;
-  P2 w[16][2];  // (W2[k][j][4c], [4c+1]), (W2[k][j][4c+2], [4c+3])
+  constexpr int kRingFloats = kWarps * kMidDepth * kMidSlotBytes / 4, kRedFloats = kWarps * kMidHalfPart;
+  __shared__ __align__(16) float smem[kRedFloats > kRingFloats ? kRedFloats : kRingFloats];  // rings, then the block reduction
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, h = warp & 1, kk = lane >> 4, c = lane & 15;
+  const int head = 2 * h + kk;
+  // wq[m][e] = (W2[head][2m][2c+e], W2[head][2m+1][2c+e])
+  P2 wq[8][2];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float4 v = ldg4(W2 + (k * 16 + j) * 32 + c * 4);
-    w[j][0] = p2(v.x, v.y);
-    w[j][1] = p2(v.z, v.w);
+  for (int m = 0; m < 8; ++m) {
+    const float2 w0 = __ldg(reinterpret_cast<const float2*>(W2 + (head * 16 + 2 * m) * 32 + 2 * c));
+    const float2 w1 = __ldg(reinterpret_cast<const float2*>(W2 + (head * 16 + 2 * m + 1) * 32 + 2 * c));
+    wq[m][0] = p2(w0.x, w1.x);
+    wq[m][1] = p2(w0.y, w1.y);
   }
-  P2 wacc[16][2];
+  P2 wacc[8][2];  // (dW2[head][2m][2c+e], dW2[head][2m+1][2c+e])
 #pragma unroll
-  for (int j = 0; j < 16; ++j) wacc[j][0] = wacc[j][1] = p2(0.f, 0.f);
-  P2 bacc = p2(0.f, 0.f);
-  const long long wid = (long long)blockIdx.x * kWarps + warp, nw = (long long)gridDim.x * kWarps;
-  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem) + warp * kMidDepth * kMidRowBytes;
-  // slot layout: [512 B of A1][256 B of dZ2]; lane l copies its 16 bytes of A1 and (l < 16) of dZ2
+  for (int m = 0; m < 8; ++m) wacc[m][0] = wacc[m][1] = p2(0.f, 0.f);
+  float bacc = 0.f;  // db2 of column 32h + lane
+  const long long wid = (long long)blockIdx.x * (kWarps / 2) + (warp >> 1), nw = (long long)gridDim.x * (kWarps / 2);
+  float* ringf = smem + warp * (kMidDepth * kMidSlotBytes / 4);
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(ringf);
+  // slot layout: [256 B of A1][128 B of dZ2]; lanes 0-15 copy A1, lanes 16-23 dZ2, 16 bytes each
+  const float* src0 = lane < 16 ? A1 + 64 * h + lane * 4 : dZ2 + 32 * h + (lane - 16) * 4;
+  const long long src_stride = lane < 16 ? 128 : 64;
+  const uint32_t dst0 = ring + (lane < 16 ? lane * 16 : 256 + (lane - 16) * 16);
   auto issue = [&](long long r, int slot) {
-    if (r < rows) {
-      const uint32_t dst = ring + slot * kMidRowBytes;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + lane * 16), "l"(A1 + r * 128 + lane * 4) : "memory");
-      if (lane < 16)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512 + lane * 16), "l"(dZ2 + r * 64 + lane * 4) : "memory");
-    }
+    if (r < rows && lane < 24)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + slot * kMidSlotBytes), "l"(src0 + r * src_stride) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 #pragma unroll
@@ -171,48 +184,57 @@ clf_mid_bwd_kernel(long long rows, const float* __restrict__ A1, const float* __
   for (long long r = wid; r < rows; r += nw) {
     asm volatile("cp.async.wait_group %0;" ::"n"(kMidDepth - 2) : "memory");
     __syncwarp();
-    const float* row = smem + (warp * kMidDepth + slot) * (kMidRowBytes / 4);
-    const float4 a = *reinterpret_cast<const float4*>(row + lane * 4);
-    const float4 g0 = *reinterpret_cast<const float4*>(row + 128 + k * 16),
-                 g1 = *reinterpret_cast<const float4*>(row + 128 + k * 16 + 4),
-                 g2 = *reinterpret_cast<const float4*>(row + 128 + k * 16 + 8),
-                 g3 = *reinterpret_cast<const float4*>(row + 128 + k * 16 + 12);
-    const float2 gb = *reinterpret_cast<const float2*>(row + 128 + lane * 2);
+    const float* row = ringf + slot * (kMidSlotBytes / 4);
+    const float2 a = *reinterpret_cast<const float2*>(row + lane * 2);
+    const float4 g0 = *reinterpret_cast<const float4*>(row + 64 + kk * 16),
+                 g1 = *reinterpret_cast<const float4*>(row + 64 + kk * 16 + 4),
+                 g2 = *reinterpret_cast<const float4*>(row + 64 + kk * 16 + 8),
+                 g3 = *reinterpret_cast<const float4*>(row + 64 + kk * 16 + 12);
+    const float gb = row[64 + lane];
     __syncwarp();  // every lane has read the slot: refill it with the row kMidDepth - 1 ahead
     issue(r + (long long)(kMidDepth - 1) * nw, (slot + kMidDepth - 1) % kMidDepth);
     slot = (slot + 1) % kMidDepth;
-    const float dz[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w,
-                          g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
-    const P2 a01 = p2(a.x, a.y), a23 = p2(a.z, a.w);
-    P2 o01 = p2(0.f, 0.f), o23 = o01;
+    const P2 dz[8] = {p2(g0.x, g0.y), p2(g0.z, g0.w), p2(g1.x, g1.y), p2(g1.z, g1.w),
+                      p2(g2.x, g2.y), p2(g2.z, g2.w), p2(g3.x, g3.y), p2(g3.z, g3.w)};
+    const P2 a0 = p2(a.x, a.x), a1 = p2(a.y, a.y);
+    P2 o0 = p2(0.f, 0.f), o1 = o0, o2 = o0, o3 = o0;  // (even-j, odd-j) partial sums of inputs 2c, 2c+1; two chains each
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const P2 d = p2(dz[j], dz[j]);
-      o01 = p2_fma(d, w[j][0], o01);
-      o23 = p2_fma(d, w[j][1], o23);
-      wacc[j][0] = p2_fma(d, a01, wacc[j][0]);
-      wacc[j][1] = p2_fma(d, a23, wacc[j][1]);
+    for (int m = 0; m < 8; m += 2) {
+      o0 = p2_fma(dz[m], wq[m][0], o0);
+      o1 = p2_fma(dz[m], wq[m][1], o1);
+      o2 = p2_fma(dz[m + 1], wq[m + 1][0], o2);
+      o3 = p2_fma(dz[m + 1], wq[m + 1][1], o3);
     }
-    bacc = p2_add(bacc, p2(gb.x, gb.y));
-    st4(dA1 + r * 128 + lane * 4, make_float4(p2_lo(o01), p2_hi(o01), p2_lo(o23), p2_hi(o23)));
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      wacc[m][0] = p2_fma(dz[m], a0, wacc[m][0]);
+      wacc[m][1] = p2_fma(dz[m], a1, wacc[m][1]);
+    }
+    bacc += gb;
+    o0 = p2_add(o0, o2);
+    o1 = p2_add(o1, o3);
+    *reinterpret_cast<float2*>(dA1 + r * 128 + 64 * h + lane * 2) =
+        make_float2(p2_lo(o0) + p2_hi(o0), p2_lo(o1) + p2_hi(o1));
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();  // all rings are drained: reuse the memory for the block reduction
-  // block partial: warps combined in fixed order.  Layout P[(k*16+j)*32 + i], P[2048 + 16k + j]
-  float* red = smem + warp * kMidPart;
+  // red[warp][(kk*16 + j)*32 + i] for the warp's two heads, then [1024 + lane] for db2
+  float* red = smem + warp * kMidHalfPart;
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    *reinterpret_cast<float4*>(red + (k * 16 + j) * 32 + c * 4) =
-        make_float4(p2_lo(wacc[j][0]), p2_hi(wacc[j][0]), p2_lo(wacc[j][1]), p2_hi(wacc[j][1]));
-  red[2048 + lane * 2] = p2_lo(bacc);
-  red[2048 + lane * 2 + 1] = p2_hi(bacc);
+  for (int m = 0; m < 8; ++m) {
+    *reinterpret_cast<float2*>(red + (kk * 16 + 2 * m) * 32 + 2 * c) = make_float2(p2_lo(wacc[m][0]), p2_lo(wacc[m][1]));
+    *reinterpret_cast<float2*>(red + (kk * 16 + 2 * m + 1) * 32 + 2 * c) = make_float2(p2_hi(wacc[m][0]), p2_hi(wacc[m][1]));
+  }
+  red[1024 + lane] = bacc;
   __syncthreads();
+  // block partial, warps of a half combined in fixed order.  Layout P[(k*16+j)*32 + i], P[2048 + 16k + j]
   float* P = parts + (size_t)blockIdx.x * kMidPart;
-  for (int i = tid; i < kMidPart; i += kMidBwdThreads) {
+  for (int i = tid; i < 2 * kMidHalfPart; i += kMidBwdThreads) {
+    const int hh = i / kMidHalfPart, q = i - hh * kMidHalfPart;
     float t = 0.f;
 #pragma unroll
-    for (int wq = 0; wq < kWarps; ++wq) t += smem[wq * kMidPart + i];
-    P[i] = t;
+    for (int wq2 = 0; wq2 < kWarps / 2; ++wq2) t += smem[(2 * wq2 + hh) * kMidHalfPart + q];
+    P[q < 1024 ? hh * 1024 + q : 2048 + hh * 32 + (q - 1024)] = t;
   }
 }
 
@@ -316,7 +338,7 @@ int eg_clf_mid_fwd(int64_t rows, const float* A1, const float* W2, const float* 
     set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
     return EG_ERR_WORKSPACE;
   }
-  const long long want = (rows + 31) / 32;  // >= 4 rows per warp
+  const long long want = (rows + 31) / 32;
   const int cap = kNumSMs * kMidFwdBlocks;
   const int grid = (int)(want < cap ? want : cap);
   double* parts = stats ? reinterpret_cast<double*>(ws) : nullptr;
