@@ -365,6 +365,12 @@ def main():
     ap.add_argument("--ncu-range", action="store_true", help="wrap --steps steps in cudaProfilerStart/Stop and exit")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler table of one step to this file")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): libraries that print to fd 1 from native code (NCCL's version banner
+    # at communicator creation) are routed to stderr until the line is printed.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
