@@ -26,8 +26,8 @@
 // crosses L2 -> SM once per tile instead of once per edge; 16 COMPUTE warps then gather / weight / sum
 // from shared memory.  A lattice tile (every main-level tile: <= 5 staged neighbours + the row itself) keeps
 // its slot offsets and weights in registers for the whole tile; its inner loop is 6 LDS.128 + 12 FFMA2
-// (packed fp32 pairs) per row.  The 2x2 children of an aux node are not staged (512 rows) and are read
-// from global, issued before the staged part.  The sums are split into tf32 hi/lo and fill a 3-stage
+// (packed fp32 pairs) per row.  The 2x2 children of an aux node are not staged (512 rows per tile) and are read
+// from global one row group ahead (general tile class).  The sums are split into tf32 hi/lo and fill a 3-stage
 // OPERAND ring ([128 rows x 128 B] hi + lo = 32 KB).  The compute warps are the critical resource of the
 // kernel (measured: they are busy > 80 % of the time while loaders, MMA and epilogue wait), so everything
 // that can live elsewhere does: row copies in the loader warps, waits with a suspend hint.
@@ -430,63 +430,10 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
           }
           continue;
         }
-        if (ks <= 5 && !has_csr) {
-          // ---- aux lattice tile (128x128, 64x64 ... levels): as above plus the 2x2 children of every row, which
-          // are not staged (512 rows) and come from global / L2.  All 8 child loads of the chunk are issued before
-          // the barrier waits so that their latency overlaps the wait and the staged part; slots and weights are
-          // re-read from the plan rows in shared memory (broadcast LDS) to leave the registers to the loads.
-          prefetch_plan(tile + gridDim.x, pbuf ^ 1u);
-#pragma unroll 1
-          for (int kc = 0; kc < 4; ++kc) {
-            const int coff = kc * 32 + j * 4;
-            float4 fx[kIters][4];
-#pragma unroll
-            for (int i = 0; i < kIters; ++i) {
-              const float4 fn = lds4(prow + i * 4 * sizeof(PlanRow) + 48);
-              fx[i][0] = ldg4(fbase + (long long)__float_as_int(fn.x) * 128 + coff);
-              fx[i][1] = ldg4(fbase + (long long)__float_as_int(fn.y) * 128 + coff);
-              fx[i][2] = ldg4(fbase + (long long)__float_as_int(fn.z) * 128 + coff);
-              fx[i][3] = ldg4(fbase + (long long)__float_as_int(fn.w) * 128 + coff);
-            }
-            acquire(raw, a_hi);
-            const uint32_t rawl = raw + lane_raw;
-            float4 aggv[kIters];
-#pragma unroll
-            for (int i = 0; i < kIters; ++i) {
-              const float4 a = lds4(prow + i * 4 * sizeof(PlanRow));
-              const float4 wa = lds4(prow + i * 4 * sizeof(PlanRow) + 16);
-              const float4 wb = lds4(prow + i * 4 * sizeof(PlanRow) + 32);
-              const float4 fw = lds4(prow + i * 4 * sizeof(PlanRow) + 64);
-              const uint32_t s_lo = __float_as_uint(a.x), s_hi = __float_as_uint(a.y);
-              const float4 x0 = lds4(rawl + (__byte_perm(s_lo, 0, 0x4440) << 7));
-              const float4 x1 = lds4(rawl + (__byte_perm(s_lo, 0, 0x4441) << 7));
-              const float4 x2 = lds4(rawl + (__byte_perm(s_lo, 0, 0x4442) << 7));
-              const float4 x3 = lds4(rawl + (__byte_perm(s_lo, 0, 0x4443) << 7));
-              const float4 x4 = lds4(rawl + (__byte_perm(s_hi, 0, 0x4440) << 7));
-              const float4 xs = lds4(rawl + (__byte_perm(s_hi, 0, 0x4443) << 7));  // the row itself
-              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-              fma4_x2(acc, wa.x, x0);
-              fma4_x2(acc, wa.y, x1);
-              fma4_x2(acc, wa.z, x2);
-              fma4_x2(acc, wa.w, x3);
-              fma4_x2(acc, wb.x, x4);
-              fma4_x2(acc, fw.x, fx[i][0]);
-              fma4_x2(acc, fw.y, fx[i][1]);
-              fma4_x2(acc, fw.z, fx[i][2]);
-              fma4_x2(acc, fw.w, fx[i][3]);
-              fma4_x2(acc, wb.w, xs);  // self loop last
-              emit(a_hi, i, acc);
-              aggv[i] = acc;
-            }
-            release();
-            if (agg_out) {
-#pragma unroll
-              for (int i = 0; i < kIters; ++i) store_agg(i, coff, aggv[i]);
-            }
-          }
-          continue;
-        }
-        // ---- general tile: up to 7 staged neighbours, 4 far neighbours read from global, CSR rows (hubs)
+        // ---- general tile (aux levels, hubs, ragged lattices): up to 7 staged neighbours, 4 far neighbours read from
+        // global (the 2x2 children of an aux node: 512 rows per tile, not staged), CSR rows (hubs).  A dedicated class
+        // for aux lattice tiles (all 8 child loads of a chunk in flight, FFMA2, plan re-read from shared memory) was
+        // measured equal in the forward and 1-3 % slower in the backward (r01h/i) and removed.
         uint2 slots[kIters];
         float4 w0[kIters], w1[kIters];
 #pragma unroll

@@ -3,6 +3,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -202,33 +203,16 @@ HostPlan build_plan(const Topo& t, const std::vector<int32_t>& tiles) {
   hp.rows.assign((size_t)T * 128, zero);
   std::vector<std::pair<int, int>> uses;  // (source, count)
   std::vector<int> nb, st, far;
-  auto level_of = [&](int v) {  // lattice level of a node, -1 for padding / connection / coordinate nodes
-    for (int l = 0; l < t.nlev; ++l)
-      if (v >= t.loff[l] && v < t.loff[l] + t.lsize[l] * t.lsize[l]) return l;
-    return -1;
-  };
   for (int ti = 0; ti < T; ++ti) {
     uses.clear();
     // hub rows have thousands of neighbours: they are CSR rows and do not vote for staged sources
     constexpr int kVoteDegree = kPlanStaged + kPlanFar;
-    // A full 8 x 16 patch of an aux lattice has 512 children (the 2x2 blocks of the next finer level), far more
-    // than the stage holds.  Staging the handful that would win the tie-break gives those rows 6-7 staged
-    // neighbours and turns the whole tile into a "general" tile of the fused kernel (measured r01h: ALL 155 aux
-    // tiles with children of the default graph, 2x the time of a lattice tile); children of a patch tile therefore
-    // never vote and are always far edges, so the tile keeps <= 5 staged neighbours (the aux-lattice class).
-    int tile_level = level_of(tiles[(size_t)ti * 128]);
-    for (int r = 0; r < 128 && tile_level >= 0; ++r)
-      if (level_of(tiles[(size_t)ti * 128 + r]) != tile_level) tile_level = -1;
-    const bool patch_tile = tile_level >= 0 && t.lsize[tile_level] % 16 == 0;
     for (int r = 0; r < 128; ++r) {
       const int v = tiles[(size_t)ti * 128 + r];
       if (v < 0) continue;
       uses.emplace_back(v, 1 << 20);  // own rows always staged (the self loop is read from the stage)
       if (degree_of(t, v) > kVoteDegree) continue;
-      for_each_neighbor(t, v, true, [&](int u) {
-        if (patch_tile && level_of(u) == tile_level + 1) return;
-        uses.emplace_back(u, 1);
-      });
+      for_each_neighbor(t, v, true, [&](int u) { uses.emplace_back(u, 1); });
     }
     std::sort(uses.begin(), uses.end());
     {  // merge duplicates
@@ -493,7 +477,7 @@ int eg_graph_plan_check(const eg_graph_spec* spec, int64_t* stats) {
   const HostPlan hp = build_plan(t, tiles);
   const int T = (int)(tiles.size() / 128);
   long long bad = 0, plan_rows = 0, csr_rows = 0, far_edges = 0, staged_edges = 0, max_src = 0;
-  long long cls[3] = {0, 0, 0};
+  long long cls[2] = {0, 0};
   std::vector<int> seen(t.N, 0);
   for (int32_t v : tiles)
     if (v >= 0) {
@@ -515,10 +499,9 @@ int eg_graph_plan_check(const eg_graph_spec* spec, int64_t* stats) {
   for (int ti = 0; ti < T; ++ti) {
     const int4 h = hp.hdr[ti];
     max_src = std::max<long long>(max_src, h.x);
-    // tile classes of the fused kernel (gcn_tc.cu): lattice / aux lattice (2x2 children read from global) / general
+    // tile classes of the fused kernel (gcn_tc.cu): lattice (<= 5 staged neighbours, nothing else) / general
     if (h.y <= 5 && !h.z && !h.w) ++cls[0];
-    else if (h.y <= 5 && !h.w) ++cls[1];
-    else ++cls[2];
+    else ++cls[1];
     bad += h.x < 1 || h.x > kPlanSrc || h.y < 0 || h.y > kPlanStaged || (h.z != 0 && h.z != kPlanFar);
     const int32_t* src = &hp.src[(size_t)ti * kPlanSrc];
     for (int k = 0; k < kPlanSrc; ++k) bad += (k < h.x) ? (src[k] < 0 || src[k] >= t.N) : (src[k] != -1);
@@ -567,7 +550,7 @@ int eg_graph_plan_check(const eg_graph_spec* spec, int64_t* stats) {
   if (stats) {
     stats[0] = T, stats[1] = plan_rows, stats[2] = csr_rows, stats[3] = far_edges, stats[4] = staged_edges;
     stats[5] = max_src;
-    stats[6] = cls[0], stats[7] = cls[1], stats[8] = cls[2];
+    stats[6] = cls[0], stats[7] = cls[1];
   }
   return (int)std::min<long long>(bad, 1 << 30);
 }

@@ -81,9 +81,9 @@ int eg_graph_csr(const eg_graph* g, const int32_t** rowptr, const int32_t** col,
  * frame (-1 = padding), every node exactly once; 8x16 lattice patches where the level allows it. */
 int eg_graph_tiles(const eg_graph* g, const int32_t** tile_nodes, int32_t* tiles_per_frame);
 /* Host-only consistency check of the tile table and of the per-tile gather plan of the fused kernel against
- * the closed-form neighbour lists and gcn_norm weights (no GPU needed).  stats (optional): int64[9] = tiles,
+ * the closed-form neighbour lists and gcn_norm weights (no GPU needed).  stats (optional): int64[8] = tiles,
  * plan rows, CSR rows, far edges, staged edges, largest staged-source count, and the number of tiles in each
- * class of the fused kernel (lattice, aux lattice, general).  Returns the number of
+ * class of the fused kernel (lattice, general).  Returns the number of
  * violations (0 = consistent) or a negative EG_ERR_* code. */
 int eg_graph_plan_check(const eg_graph_spec* spec, int64_t* stats);
 /* edge_index exactly as the reference's loader produces it for a batch of `batch` frames:

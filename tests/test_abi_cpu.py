@@ -90,10 +90,10 @@ def test_host_closed_form_graph_hashes_224(eg):
 
 
 @pytest.mark.parametrize("kw,classes", [
-    (dict(), (408, 154, 1)),                                  # default.yml: 392 main + 16 childless aux tiles, 154 aux tiles with children
-    (dict(use_main_graph_only=True), (392, 0, 0)),
-    (dict(frame_size=448, num_aux_graphs=8), (1688, 562, 1)),  # BASELINE configs[3]
-    (dict(use_coordinate_graph=True), (408, 154, 1)),
+    (dict(), (408, 155)),                                     # default.yml: 392 main + 16 childless aux tiles; 155 tiles with children / ragged
+    (dict(use_main_graph_only=True), (392, 0)),
+    (dict(frame_size=448, num_aux_graphs=8), (1688, 563)),  # BASELINE configs[3]
+    (dict(use_coordinate_graph=True), (408, 155)),
     (dict(use_connection_nodes=True), None),
     (dict(frame_size=64, num_aux_graphs=5), None),
     (dict(frame_size=32, num_aux_graphs=4, main_graph_type="grid-diagonal", aux_graph_type="grid-diagonal"), None),
@@ -101,17 +101,17 @@ def test_host_closed_form_graph_hashes_224(eg):
 ])
 def test_gather_plan_is_consistent_and_tiles_land_in_their_kernel_class(eg, kw, classes):
     """Host-only self check of the tile table + gather plan of the fused kernel against the closed-form neighbour
-    lists and gcn_norm weights, and the class every tile runs in (lattice / aux lattice / general): a tile that
-    silently falls into the general class costs twice the time (r01h: all aux tiles of the default graph did)."""
+    lists and gcn_norm weights, and the class every tile runs in (lattice / general): every main-level tile must be a
+    lattice tile (a general tile costs twice the time)."""
     from echoglad_b200._lib import lib
     spec = eg.HierGraphSpec(**kw)
-    stats = (ctypes.c_int64 * 9)()
+    stats = (ctypes.c_int64 * 8)()
     assert lib.eg_graph_plan_check(ctypes.byref(spec.c_spec()), stats) == 0
     tiles, plan_rows, csr_rows = stats[0], stats[1], stats[2]
     assert plan_rows + csr_rows == spec.info().num_nodes
-    assert stats[6] + stats[7] + stats[8] == tiles
+    assert stats[6] + stats[7] == tiles
     if classes is not None:
-        assert (stats[6], stats[7], stats[8]) == classes
+        assert (stats[6], stats[7]) == classes
 
 
 def test_malformed_spec_is_rejected(eg):

@@ -14,3 +14,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:gcn_
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gcn_tc_kernel|wgrad_tc_kernel" --launch-skip 6 -c 2 -f \
   -o gpurun_out/${TAG}_bwd python tools/kernel_bench.py --only gcn_conv_bwd --iters 1 > gpurun_out/${TAG}_ncu3.log 2>&1
 ls -la gpurun_out | tail -12
+# BASELINE configs[1] (main graph only, batch 32) and configs[3] (448 px / 8 aux levels, batch 16): per-entry-point microbench
+{ echo "== configs[1]: use_main_graph_only, batch 32"; timeout 300 python tools/kernel_bench.py --main-only --batch 32 --only gcn_conv_fwd,gcn_conv_bwd,aggregate | grep -v "^{";
+  echo "== configs[3]: frame 448, 8 aux levels, batch 16"; timeout 300 python tools/kernel_bench.py --frame 448 --naux 8 --batch 16 --only gcn_conv_fwd,gcn_conv_bwd,aggregate | grep -v "^{"; } > gpurun_out/${TAG}_configs_c2_c4.txt 2>&1
+cat gpurun_out/${TAG}_configs_c2_c4.txt
