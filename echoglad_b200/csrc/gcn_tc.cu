@@ -179,6 +179,10 @@ __device__ __forceinline__ void fma4_x2(float4& acc, float w, const float4& x) {
   acc.w = __uint_as_float((uint32_t)(a1 >> 32));
 }
 
+// 128-bit load of a far (not staged) source row slice: read once per SM, so it bypasses the ~28 KB of L1 left beside
+// the 203 KB of shared memory (ld.global.cg; measured -1 % against ld.global.nc, L1::no_allocate +4 %).
+__device__ __forceinline__ float4 ld_far(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
 template <bool GATHER>
 __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
 #ifdef EG_TC_TIMING
@@ -188,7 +192,13 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
 #endif
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned base in the shared address space (the swizzle patterns are functions of the shared address)
-  const uint32_t sm = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // The kernel has no static shared memory and is never launched in a cluster, so its dynamic shared memory starts
+  // right after the 1 KB the system reserves per CTA: shared-window address 0x400, already 1024-byte aligned.
+  // Using the literal turns every ring / barrier address below into an immediate (the compiler otherwise keeps the
+  // base in a register that the register-tight lattice loop spilled to local memory: 2 % of the kernel, r01j).
+  // Checked once per thread; a different layout traps (launch failure) instead of corrupting memory.
+  constexpr uint32_t sm = 0x400;
+  if (((smem_u32(smem_raw) + 1023u) & ~1023u) != sm) __trap();
   uint8_t* smem = smem_raw + (sm - smem_u32(smem_raw));
   uint8_t* sA = smem;                     // [stage][hi|lo][16 KB]
   uint8_t* sRaw = sA + kABytes;           // [raw stage][kRawRows][128 B]
@@ -450,10 +460,10 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
           float4 fx[4];
           if (nfar) {  // far rows of the first row group: in flight across the barrier waits
             const float4 fn = lds4(prow + 48);
-            fx[0] = ldg4(fbase + (long long)__float_as_int(fn.x) * 128 + coff);
-            fx[1] = ldg4(fbase + (long long)__float_as_int(fn.y) * 128 + coff);
-            fx[2] = ldg4(fbase + (long long)__float_as_int(fn.z) * 128 + coff);
-            fx[3] = ldg4(fbase + (long long)__float_as_int(fn.w) * 128 + coff);
+            fx[0] = ld_far(fbase + (long long)__float_as_int(fn.x) * 128 + coff);
+            fx[1] = ld_far(fbase + (long long)__float_as_int(fn.y) * 128 + coff);
+            fx[2] = ld_far(fbase + (long long)__float_as_int(fn.z) * 128 + coff);
+            fx[3] = ld_far(fbase + (long long)__float_as_int(fn.w) * 128 + coff);
           }
           acquire(raw, a_hi);
           const uint32_t rawl = raw + lane_raw;
@@ -492,10 +502,10 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
               fma4(acc, fw.w, fx[3]);
               if (i + 1 < kIters) {
                 const float4 fn = lds4(prow + (i + 1) * 4 * sizeof(PlanRow) + 48);
-                fx[0] = ldg4(fbase + (long long)__float_as_int(fn.x) * 128 + coff);
-                fx[1] = ldg4(fbase + (long long)__float_as_int(fn.y) * 128 + coff);
-                fx[2] = ldg4(fbase + (long long)__float_as_int(fn.z) * 128 + coff);
-                fx[3] = ldg4(fbase + (long long)__float_as_int(fn.w) * 128 + coff);
+                fx[0] = ld_far(fbase + (long long)__float_as_int(fn.x) * 128 + coff);
+                fx[1] = ld_far(fbase + (long long)__float_as_int(fn.y) * 128 + coff);
+                fx[2] = ld_far(fbase + (long long)__float_as_int(fn.z) * 128 + coff);
+                fx[3] = ld_far(fbase + (long long)__float_as_int(fn.w) * 128 + coff);
               }
             }
             fma4(acc, w1[i].w, x2);  // self loop last

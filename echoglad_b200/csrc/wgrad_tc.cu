@@ -90,8 +90,12 @@ __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(long long rows, const float* __restrict__ G, const float* __restrict__ X,
                 float* __restrict__ parts, double* __restrict__ colsum_parts) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t sm = smem_u32(smem);
+  // dynamic shared memory of a CTA without static shared memory / cluster starts at shared-window address 0x400
+  // (1 KB system reserve), already 1024-byte aligned: a literal base makes every ring / barrier address an immediate
+  // (see gcn_tc.cu); any other layout traps.
+  constexpr uint32_t sm = 0x400;
+  if (((smem_u32(smem_raw) + 1023u) & ~1023u) != sm) __trap();
+  uint8_t* smem = smem_raw + (sm - smem_u32(smem_raw));
   const uint32_t bar_raw_full = sm + kOffBars, bar_raw_empty = bar_raw_full + 8 * kRaw,
                  bar_lo_full = bar_raw_empty + 8 * kRaw, bar_lo_empty = bar_lo_full + 8 * kLo,
                  bar_acc_full = bar_lo_empty + 8 * kLo, bar_acc_empty = bar_acc_full + 16;
