@@ -34,6 +34,11 @@
 // TMEM: 256 columns of weight + 2 x 128 of accumulator.
 // Warps: 0-3 epilogue (TMEM lane quadrant = warp id), 4 MMA issuer, 5-7 loaders, 8-23 compute; the compute
 // warpgroups raise their register budget to 88 with setmaxnreg, the epilogue drops to 72, MMA + loaders to 56.
+//
+// Development switches (never defined in the shipped build; `EG_NVCC_EXTRA=-D... python echoglad_b200/build.py`,
+// A/B driver tools/gpu_ab.sh): EG_TC_TIMING adds per-role wait-cycle counters (eg_tc_debug_read, printed by
+// tools/kernel_bench.py); EG_DBG_NOGATHER / NOEMIT / NOFENCE / NOCOMPUTE / NOLOAD / NOMMA / NOSTORE / NOEPI /
+// SMALLOUT each remove one piece of work (WRONG results, timing only: the knock-out table of DESIGN.md 4.1).
 #include "common.cuh"
 #include "tc05.cuh"
 
