@@ -55,6 +55,7 @@ BIG_SPECS = [
     (224, 0, True, False, False, "grid", "grid"),
     (224, 7, False, True, False, "grid", "grid"),
     (224, 7, False, False, True, "grid", "grid"),
+    (448, 8, False, False, False, "grid", "grid"),   # BASELINE configs[3]: 2x resolution, centre crop c = 16
 ]
 
 
@@ -72,8 +73,25 @@ def sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def make_graphs(skip_big: bool):
+def make_graphs(skip_big: bool, big_only: str = ""):
+    """big_only: mint only the BIG_SPECS entry with this key and merge it into graph_hashes.json."""
     import networkx as nx
+
+    if big_only:
+        path = os.path.join(HERE, "graph_hashes.json")
+        hashes = json.load(open(path))
+        (s,) = [s for s in BIG_SPECS if spec_key(s) == big_only]
+        t = time.time()
+        ei, nt = ref_graph(s)
+        e = ei.numpy().astype(np.int64)
+        hashes["specs"][spec_key(s)] = {
+            "num_nodes": int(nt.shape[0]), "num_edges": int(e.shape[1]),
+            "edge_index_sha256": sha(e), "node_type_sha256": sha(nt.astype(np.float64)),
+            "first_edges": e[:, :8].T.tolist()}
+        print(spec_key(s), nt.shape[0], e.shape[1], f"{time.time() - t:.1f}s", flush=True)
+        with open(path, "w") as fh:
+            json.dump(hashes, fh, indent=1)
+        return
 
     out = {}
     for s in SMALL_SPECS:
@@ -286,11 +304,12 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-big", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--big-spec", default="", help="with --only graphs: mint just this BIG_SPECS key into graph_hashes.json")
     a = ap.parse_args()
     torch.manual_seed(0)
     torch.backends.cudnn.allow_tf32 = False
     if a.only in ("", "graphs"):
-        make_graphs(a.skip_big)
+        make_graphs(a.skip_big, a.big_spec)
     if a.only in ("", "labels"):
         make_labels()
     if a.only in ("", "models", "models-small"):
