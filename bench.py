@@ -36,6 +36,19 @@ LANDMARK_KW = dict(frame_size=224, gnn_dropout_p=0.5, classifier_dropout_p=0.5, 
                    output_activation='logit', use_connection_nodes=False, use_main_graph_only=False)
 
 
+def workload_config(batch: int, world: int, cudnn_tf32: bool = False) -> dict:
+    """`config` of the JSON line: identical on both arms (the reference arm times a bounded sample of this
+    workload and says which in `cpu_baseline.sample`)."""
+    return {"workload": f"default.yml full hierarchical graph, batch {batch} per GPU, training step "
+                        "(embedder + UNet + GNN stack + classifiers + both losses, fwd+bwd, Adam)",
+            "frame_size": 224, "num_aux_graphs": 7, "num_gnn_layers": 3, "batch_per_gpu": batch,
+            "global_batch": batch * world, "nodes_per_step": batch * world * N_NODES,
+            "parallelism": f"dp{world} (frames sharded, flat-bucket NCCL grad all-reduce)",
+            "l2": "working set (2.36 GB per node tensor) >> 126 MB L2, no flush",
+            "precision": "fp32 storage; 3xTF32 tensor-core transforms with fp32 accumulate; "
+                         f"cuDNN TF32 {'on' if cudnn_tf32 else 'off'}"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -100,8 +113,10 @@ def cpu_oracle_step_factory(batch: int):
     landmark -> both losses -> backward -> Adam.  Only bench.py's baseline legs execute this."""
     from oracle import restated as R
     import numpy as np
-    from echoglad_b200.graph import HierGraphSpec  # host closed form == reference edge_index (bit-exact, tested)
 
+    # nothing of echoglad_b200 (and so no libechoglad_b200.so) is imported on this arm: the graph comes from the
+    # oracle's networkx restatement of `create_graphs` + `from_networkx` (built once, outside the timed steps, as
+    # the reference's data set builds it once per sample in its loader workers)
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = R.Cfg()
     sd = R.clone_state(R.init_landmark_state(cfg, seed=200), requires_grad=True)
@@ -109,9 +124,9 @@ def cpu_oracle_step_factory(batch: int):
     params = [v for v in list(sd.values()) + list(esd.values()) if v.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-4)
     frames, coords, y, valid = R.synthetic_batch(batch, 224, 7, seed=200)
-    spec = HierGraphSpec()
-    ei = spec.host_edge_index(batch)
-    node_type = spec.host_node_type(batch)
+    ei1, nt1 = R.build_edge_index(224, 7)
+    ei = R.batch_edge_index(ei1, nt1.shape[0], batch)
+    node_type = np.tile(nt1, batch)
 
     def step():
         opt.zero_grad(set_to_none=True)
@@ -140,19 +155,20 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 2
+    batch = 2  # bounded sample: 2 of the workload's frames per step (the CPU rate is per frame; batch 64 needs ~100 GB)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     fps, sec = time_cpu_oracle(batch, max(1, args.steps), max(0, args.warmup))
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": max(1, args.steps), "warmup": max(0, args.warmup), "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "default.yml EchoGLAD training step (fwd + both losses + bwd + Adam), "
-                               "bounded sample: batch 2 frames per step on the host CPU",
-                   "frame_size": 224, "num_aux_graphs": 7, "num_gnn_layers": 3, "batch_per_step": batch},
+        "config": workload_config(args.batch, max(world, args.gpus), bool(args.cudnn_tf32)),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{max(1, args.steps)} steps of batch {batch} (oracle/restated.py, torch CPU, "
-                                   f"{cores} threads); the reference itself needs torch_geometric, absent here"},
+                         "sample": f"bounded sample of the workload: {max(1, args.steps)} training steps of {batch} "
+                                   f"frames each instead of {args.batch} (same graph, model, losses and optimizer; "
+                                   f"oracle/restated.py on torch CPU with {cores} threads, graph from its networkx "
+                                   "restatement); the reference itself needs torch_geometric, absent here"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -320,14 +336,7 @@ def run_native(args):
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"default.yml full hierarchical graph, batch {B} per GPU, training step "
-                               "(embedder + UNet + GNN stack + classifiers + both losses, fwd+bwd, Adam)",
-                   "frame_size": 224, "num_aux_graphs": 7, "num_gnn_layers": 3, "batch_per_gpu": B,
-                   "global_batch": B * world, "nodes_per_step": B * world * N_NODES,
-                   "parallelism": f"dp{world} (frames sharded, flat-bucket NCCL grad all-reduce)",
-                   "l2": "working set (2.36 GB per node tensor) >> 126 MB L2, no flush",
-                   "precision": "fp32 storage; 3xTF32 tensor-core transforms with fp32 accumulate; "
-                                f"cuDNN TF32 {'on' if args.cudnn_tf32 else 'off'}"},
+        "config": workload_config(B, world, bool(args.cudnn_tf32)),
         "clocks": clocks,
         "e2e": {"value": frames_total / (ms_e2e / 1e3), "unit": "frames/s",
                 "h2d_bytes_per_step": int(frames_h.numel() * 4 + coords_h.numel() * 4) * world,

@@ -10,8 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line():
+    # EG_LIB_PATH points nowhere: importing echoglad_b200 (and so mapping libechoglad_b200.so) on this arm would raise
+    env = dict(os.environ, EG_LIB_PATH="/nonexistent/libechoglad_b200.so")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.split("\n") if ln.strip()]
     assert len(lines) == 1, r.stdout[:2000]
@@ -25,3 +27,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["value"] == d["value"] and d["e2e"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+    # the same `config` as the native arm prints (the bounded sample is described in cpu_baseline.sample)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config(64, 1)
+    assert "bounded sample" in d["cpu_baseline"]["sample"]
