@@ -206,7 +206,20 @@ class HierarchicalPatchModel(nn.Module):
     def forward(self, data_batch=None, x: torch.Tensor = None, node_coords: torch.Tensor = None,
                 edge_index: torch.Tensor = None, node_type=None, batch_idx: torch.Tensor = None):
         if data_batch is not None:
-            x, edge_index = data_batch.x, data_batch.edge_index
+            # the reference's two data_batch forms (src/core/models.py:408-413, src/engine.py:243-248): a collated
+            # PyG `Batch` (attributes x / edge_index / batch / node_type / node_coords), or -- on the multi-GPU route,
+            # where PyG's DataParallel would have collated it -- the raw list of per-frame `Data` objects
+            if isinstance(data_batch, (list, tuple)):
+                x = torch.cat([d.x for d in data_batch], dim=0)
+                graph1 = DeviceGraph.get(self.graph_spec, x.device)
+                graph1.validate_edge_index_once(getattr(data_batch[0], "edge_index", None), 1)
+                edge_index = None
+                if self.use_coordinate_graph and node_coords is None:
+                    node_coords = torch.cat([d.node_coords.reshape(-1, 2) for d in data_batch], dim=0)
+            else:
+                x, edge_index = data_batch.x, data_batch.edge_index
+                if self.use_coordinate_graph and node_coords is None:
+                    node_coords = data_batch.node_coords
         if x is None or not x.is_cuda:
             raise EchogladError("the landmark module needs CUDA inputs: echoglad_b200 has no CPU fallback")
         batch = x.shape[0]
@@ -215,8 +228,6 @@ class HierarchicalPatchModel(nn.Module):
 
         coords = None
         if self.use_coordinate_graph:
-            if node_coords is None and data_batch is not None:
-                node_coords = data_batch.node_coords
             if node_coords is None:
                 raise EchogladError("use_coordinate_graph=True needs node_coords [4*B, 2]")
             coords = node_coords.to(torch.float32).reshape(batch, 4, 2)  # not modified in place (the reference does)

@@ -1110,3 +1110,35 @@ def test_config2_batch33_eval_forward_frames_0_and_32_against_oracle():
         assert ok, f"frame {f}: {worst}"
         ok, worst = close(fused[f].cpu(), lo[i], 1e-4, 1e-5)
         assert ok, f"frame {f} (fused embed route): {worst}"
+
+
+def test_forward_accepts_the_reference_data_batch_forms():
+    """`forward(data_batch=...)` (src/core/models.py:408-413): a collated Batch-like object and the list of per-frame
+    Data objects the multi-GPU route passes (src/engine.py:243-248) give the same logits as the keyword call."""
+    from types import SimpleNamespace
+    cfg = R.Cfg(variant="avgpool", frame_size=12, num_aux_graphs=3, gnn_dropout_p=0.0, classifier_dropout_p=0.0,
+                use_coordinate_graph=True)
+    model = eg.HierarchicalPatchModel(
+        frame_size=12, gnn_dropout_p=0.0, classifier_dropout_p=0.0, node_embedding_dim=128, node_hidden_dim=128,
+        num_output_channels=4, num_gnn_layers=3, num_aux_graphs=3, gnn_jk_mode='last', classifier_hidden_dim=32,
+        residual=True, use_coordinate_graph=True, output_activation='logit').to(DEV)
+    model.load_state_dict(R.init_landmark_state(cfg, seed=71), strict=True)
+    model.eval()
+    batch = 3
+    gen = torch.Generator().manual_seed(72)
+    x = torch.randn(batch, 128, 12, 12, generator=gen).to(DEV)
+    coords = (torch.rand(4 * batch, 2, generator=gen) * 11).to(DEV)
+    spec = model.graph_spec
+    n = spec.info().num_nodes
+    ei = spec.host_edge_index(batch).to(DEV)
+    nt = torch.from_numpy(spec.host_node_type(batch)).to(DEV)
+    bidx = torch.arange(batch, device=DEV).repeat_interleave(n)
+    with torch.no_grad():
+        want, want_c = model(x=x, node_coords=coords, edge_index=ei, batch_idx=bidx, node_type=nt)
+        got, got_c = model(SimpleNamespace(x=x, edge_index=ei, batch=bidx, node_type=nt, node_coords=coords))
+        ei1 = spec.host_edge_index(1).to(DEV)
+        items = [SimpleNamespace(x=x[b:b + 1], edge_index=ei1, node_type=nt[:n], node_coords=coords[4 * b:4 * b + 4])
+                 for b in range(batch)]
+        got_l, got_lc = model(items)
+    assert torch.equal(got, want) and torch.equal(got_c, want_c)
+    assert torch.equal(got_l, want) and torch.equal(got_lc, want_c)
