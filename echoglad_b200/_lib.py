@@ -70,7 +70,7 @@ SIGNATURES = {
     "eg_clf_out_bwd": (_I, [_L, _P, _P, _P, _P, _I, _P, _P, _P, _P, _SZ, _P]),
     "eg_bce_multilevel": (_I, [_L, _P, _P, _P, _F, _F, _P, _P, _P, _SZ, _P]),
     "eg_expected_landmark_mse": (_I, [_I, _I, _I, C.POINTER(C.c_int32), _P, _P, _P, _F, _P, _P, _P, _SZ, _P]),
-    "eg_node_labels": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int32), _P, _P, _P]),
+    "eg_node_labels": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int32), _P, _P, _P, _P]),
     "eg_expected_coords": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "eg_profile_enable": (_I, [_I]),
     "eg_profile_read": (_I, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(_L)]),

@@ -19,7 +19,8 @@ class WeightedBCEWithLogitsLoss(object):
     def compute(self, pred_y, y, valid=None):
         if valid is None:
             raise AttributeError("'NoneType' object has no attribute 'view'")  # reference behaviour (criterion.py:15)
-        return ops.WeightedBCEWithLogits.apply(pred_y, y, valid, float(self.ones_weight), float(self.loss_weight))
+        with ops.device_of(pred_y):
+            return ops.WeightedBCEWithLogits.apply(pred_y, y, valid, float(self.ones_weight), float(self.loss_weight))
 
 
 class ExpectedLandmarkMSE(object):
@@ -39,8 +40,10 @@ class ExpectedLandmarkMSE(object):
             self.grid_sizes = [2 ** k for k in range(1, num_aux_graphs + 1)] + [frame_size]
 
     def compute(self, pred_y, y, valid):
-        return ops.ExpectedLandmarkMSEFn.apply(pred_y, y, valid, int(self.batch_size), int(self.num_output_channels),
-                                               tuple(self.grid_sizes), float(self.loss_weight))
+        with ops.device_of(pred_y):
+            return ops.ExpectedLandmarkMSEFn.apply(pred_y, y, valid, int(self.batch_size),
+                                                   int(self.num_output_channels), tuple(self.grid_sizes),
+                                                   float(self.loss_weight))
 
 
 class MAE(object):

@@ -303,14 +303,14 @@ inline bool cols_ok(int cols) { return cols >= 4 && cols <= 128 && (cols % 4) ==
 
 inline int elem_grid(long long total_groups) {
   long long b = (total_groups + kThreads - 1) / kThreads;
-  long long cap = (long long)kNumSMs * 16;
+  long long cap = (long long)num_sms() * 16;
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
 inline int reduce_grid(long long rows, int cols, int blocks_per_sm = kMaxParts / kNumSMs) {
   int ry = kThreads / (cols / 4);
   long long b = (rows + ry - 1) / ry;
-  long long cap = (long long)blocks_per_sm * kNumSMs;  // one resident wave (<= kMaxParts partial slots)
+  long long cap = (long long)blocks_per_sm * num_sms();  // one resident wave (<= kMaxParts partial slots)
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 

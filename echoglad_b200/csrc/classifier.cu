@@ -339,7 +339,7 @@ int eg_clf_mid_fwd(int64_t rows, const float* A1, const float* W2, const float* 
     return EG_ERR_WORKSPACE;
   }
   const long long want = (rows + 31) / 32;
-  const int cap = kNumSMs * kMidFwdBlocks;
+  const int cap = num_sms() * kMidFwdBlocks;
   const int grid = (int)(want < cap ? want : cap);
   double* parts = stats ? reinterpret_cast<double*>(ws) : nullptr;
   ProfileScope prof("clf_mid_fwd", as_stream(stream));
@@ -358,7 +358,7 @@ int eg_clf_mid_bwd(int64_t rows, const float* A1, const float* W2, const float* 
   }
   static_assert((size_t)kMidGrid * kMidPart * sizeof(float) <= kWgradBytes, "clf_mid_bwd partials fit the workspace");
   const long long want = (rows + 15) / 16;
-  const int cap = kNumSMs * kMidBwdBlocks;
+  const int cap = num_sms() * kMidBwdBlocks;
   const int grid = (int)(want < cap ? want : cap);
   float* parts = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);
   ProfileScope prof("clf_mid_bwd", as_stream(stream));
@@ -373,7 +373,7 @@ int eg_clf_out_fwd(int64_t rows, const float* A2, const float* W3, const float* 
                    void* stream) {
   EG_CHECK_ARG(rows >= 1 && A2 && W3 && b3 && out, "eg_clf_out_fwd: NULL argument");
   long long blocks = (rows * 16 + 255) / 256;
-  long long cap = (long long)kNumSMs * 16;
+  long long cap = (long long)num_sms() * 16;
   int grid = (int)(blocks < cap ? blocks : cap);
   ProfileScope prof("clf_out_fwd", as_stream(stream));
   clf_out_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(rows, A2, W3, b3, sigmoid, out);

@@ -50,8 +50,14 @@ class ProfileScope {
     EG_CUDA(cudaGetLastError());                   \
   } while (0)
 
-constexpr int kNumSMs = 148;            // B200
+constexpr int kNumSMs = 148;            // B200: UPPER BOUND used to size workspaces / partial-slot tables at compile time
 constexpr int kMaxParts = 4 * kNumSMs;  // upper bound on per-CTA partial slots of any reduction
+// SM count of the CURRENT device (cudaDevAttrMultiProcessorCount, cached per device), capped at kNumSMs so that
+// every grid sized from it fits the workspace layout: the launch helpers size persistent grids with this.
+int num_sms();
+// true exactly once per (mask, current device): guards per-device one-time setup such as
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), which is a per-device attribute.  Thread-safe.
+bool first_use_on_current_device(std::atomic<unsigned long long>& mask);
 // workspace: [kMaxParts][2][128] doubles for column statistics + [kNumSMs][128*128] floats for the
 // weight-gradient partials + slack
 constexpr size_t kStatsBytes = (size_t)kMaxParts * 2 * 128 * sizeof(double);

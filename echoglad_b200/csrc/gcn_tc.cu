@@ -799,12 +799,11 @@ int launch(const TcParams& p, float* mean, float* var, void* ws, size_t ws_bytes
     set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
     return EG_ERR_WORKSPACE;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_mask{0};  // per template instance, one bit per device
+  if (first_use_on_current_device(attr_mask))
     EG_CUDA(cudaFuncSetAttribute(gcn_tc_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_done = true;
-  }
-  const int grid = (int)(p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs);
+  const int sms = num_sms();
+  const int grid = (int)(p.num_tiles < sms ? p.num_tiles : sms);
   TcParams q = p;
   q.stat_parts = stats ? reinterpret_cast<double*>(ws) : nullptr;
   {

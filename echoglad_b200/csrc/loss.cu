@@ -239,13 +239,20 @@ elmse_grad_kernel(Levels lv, const float* __restrict__ x, const SegStat* __restr
 }
 
 __global__ void labels_kernel(int batch, int channels, int frame, Levels lv, const int32_t* __restrict__ coords,
-                              float* __restrict__ y) {
+                              float* __restrict__ y, int32_t* __restrict__ oob_count) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= batch * channels * lv.n) return;
   const int l = idx % lv.n, c = (idx / lv.n) % channels, b = idx / (lv.n * channels);
   const int g = lv.size[l];
   int h = coords[(b * channels + c) * 2], w = coords[(b * channels + c) * 2 + 1];
-  if (h >= frame || w >= frame || h < -frame || w < -frame) return;  // reference raises IndexError here
+  if (h >= frame || w >= frame || h < -frame || w < -frame) {
+    // the reference raises IndexError here (datasets.py:536-537); a kernel cannot raise, and an all-zero heat map
+    // would silently train on gt = (0, 0): poison the level's first node (every loss of the frame turns NaN) and
+    // count the coordinate for the caller
+    y[((long long)b * lv.total + lv.start[l]) * channels + c] = __int_as_float(0x7fc00000);
+    if (oob_count && l == 0) atomicAdd(oob_count, 1);
+    return;
+  }
   // np.digitize(h, linspace(0, frame, g+1)) - 1 == floor(h*g/frame) for 0 <= h < frame; a negative
   // coordinate lands in bin -1, which numpy indexing wraps to the last row/column (datasets.py:532-537)
   int bh = (l == lv.n - 1) ? h : (h < 0 ? -1 : (int)(((long long)h * g) / frame));
@@ -408,7 +415,7 @@ int eg_expected_landmark_mse(int batch, int channels, int num_levels, const int3
 }
 
 int eg_node_labels(int batch, int channels, int frame_size, int num_levels, const int32_t* level_size,
-                   const int32_t* coords, float* y, void* stream) {
+                   const int32_t* coords, float* y, int32_t* oob_count, void* stream) {
   EG_CHECK_ARG(batch >= 1 && channels >= 1 && coords && y, "eg_node_labels: bad argument");
   Levels lv;
   EG_CHECK_ARG(make_levels(num_levels, level_size, lv) == 0, "eg_node_labels: bad level list");
@@ -416,7 +423,7 @@ int eg_node_labels(int batch, int channels, int frame_size, int num_levels, cons
   cudaStream_t s = as_stream(stream);
   EG_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)batch * lv.total * channels, s));
   const int total = batch * channels * num_levels;
-  labels_kernel<<<(total + 127) / 128, 128, 0, s>>>(batch, channels, frame_size, lv, coords, y);
+  labels_kernel<<<(total + 127) / 128, 128, 0, s>>>(batch, channels, frame_size, lv, coords, y, oob_count);
   EG_LAUNCH_CHECK();
   return EG_OK;
 }

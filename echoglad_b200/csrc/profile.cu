@@ -12,6 +12,26 @@
 namespace eg {
 
 std::atomic<long long> g_launches{0};
+
+int num_sms() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+    if (n > kNumSMs) n = kNumSMs;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
+bool first_use_on_current_device(std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;  // unknown device: always set up
+  const unsigned long long bit = 1ull << dev;
+  return (mask.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+}
 static std::atomic<int> g_profile_on{0};
 
 struct Span {
@@ -27,8 +47,8 @@ static cudaEvent_t get_event() {
     g_pool.pop_back();
     return e;
   }
-  cudaEvent_t e;
-  cudaEventCreate(&e);
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return nullptr;  // the scope then records nothing (see ProfileScope)
   return e;
 }
 
@@ -37,6 +57,12 @@ ProfileScope::ProfileScope(const char* name, cudaStream_t s) : name_(name), stre
   std::lock_guard<std::mutex> lk(g_mu);
   beg_ = get_event();
   end_ = get_event();
+  if (!beg_ || !end_) {  // event creation failed: give back what we got and profile nothing for this scope
+    if (beg_) g_pool.push_back(reinterpret_cast<cudaEvent_t>(beg_));
+    if (end_) g_pool.push_back(reinterpret_cast<cudaEvent_t>(end_));
+    on_ = false;
+    return;
+  }
   cudaEventRecord(reinterpret_cast<cudaEvent_t>(beg_), stream_);
 }
 

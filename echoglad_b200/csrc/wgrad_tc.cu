@@ -282,13 +282,12 @@ int launch_wgrad_tc(long long rows, const float* G, const float* X, float* dW, f
     set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
     return EG_ERR_WORKSPACE;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_mask{0};
+  if (first_use_on_current_device(attr_mask))
     EG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_done = true;
-  }
   const long long nblocks = (rows + kRows - 1) / kRows;
-  const int grid = (int)(nblocks < kNumSMs ? nblocks : kNumSMs);
+  const int sms = num_sms();
+  const int grid = (int)(nblocks < sms ? nblocks : sms);
   double* colsum = reinterpret_cast<double*>(ws);
   float* parts = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kStatsBytes);
   ProfileScope prof("wgrad_tc", s);

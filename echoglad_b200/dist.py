@@ -3,8 +3,17 @@ bucket all-reduced over NCCL (NVLink 5 / NVSwitch) per step.
 
 Replaces the reference's single-process `torch_geometric.nn.DataParallel` / `nn.DataParallel`
 (src/engine.py:105-110), which re-broadcasts all parameters and gathers logits to GPU 0 every step.
-The batched graph is block-diagonal, so frames are independent through the whole GNN path; BatchNorm
-statistics and loss normalisers stay per rank, exactly as they are per replica in the reference.
+The batched graph is block-diagonal, so frames are independent through the whole GNN path.  BatchNorm
+statistics stay per rank, exactly as they are per replica in the reference's DataParallel.
+
+Loss normalisers are NOT per replica in the reference: DataParallel gathers the logits and `compute_loss` runs
+once, so `sum(valid)` (BCE) and the per-level `num_valid` (expected-landmark MSE) are GLOBAL sums
+(src/engine.py:589-598).  Here every rank normalises by its own sums and the gradients are averaged, which
+equals the global loss exactly when all ranks hold the same normalisers -- true for the all-ones `valid` of the
+synthetic benchmark and for equal shards of fully labelled frames.  For unevenly distributed invalid landmarks,
+`global_normaliser_scale` gives the factor that turns a rank's `S_r / V_r` into its share of `sum S / sum V`
+(exact for the BCE term; for the expected-landmark term it is exact when `valid` is constant over the nodes of
+a frame and channel and the per-channel counts agree across ranks, otherwise an approximation).
 """
 from __future__ import annotations
 
@@ -40,6 +49,18 @@ def shard_range(num_frames: int, rank: int, world: int) -> range:
     return range(rank * per, (rank + 1) * per)
 
 
+def global_normaliser_scale(local_normaliser: torch.Tensor, group=None) -> torch.Tensor:
+    """G * V_r / sum_r V_r as a 0-dim tensor on the normaliser's device (1 when not distributed).  Multiplying rank
+    r's loss `S_r / V_r` by it before `backward()` makes the averaged gradient equal the gradient of the reference's
+    global `sum_r S_r / sum_r V_r`:  (1/G) sum_r [G V_r / V] grad(S_r) / V_r = sum_r grad(S_r) / V."""
+    v = local_normaliser.detach().to(torch.float32).reshape(())
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return torch.ones_like(v)
+    total = v.clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return v * dist.get_world_size(group) / total.clamp_min(torch.finfo(torch.float32).tiny)
+
+
 class FlatGradBucket:
     """All gradients of `params` end up in one contiguous fp32 buffer, so the data-parallel reduction is a single
     all-reduce and the optimizer reads views of that buffer.
@@ -73,7 +94,10 @@ class FlatGradBucket:
             p.grad = None
 
     def gather(self) -> None:
-        """Fresh gradients -> flat buffer (parameters without a gradient contribute zeros); `.grad` = the views."""
+        """Fresh gradients -> flat buffer; `.grad` = the views.  A parameter that received no gradient contributes
+        zeros to the reduction and KEEPS `.grad = None`, so the optimizer skips it (no weight decay / momentum on
+        unused parameters, as in the reference's single-process step); every rank runs the same graph, so the set
+        of unused parameters is the same everywhere."""
         src, dst = [], []
         for p, v in zip(self.params, self.views):
             if p.grad is None:
@@ -84,7 +108,8 @@ class FlatGradBucket:
         if src:
             torch._foreach_copy_(dst, src)
         for p, v in zip(self.params, self.views):
-            p.grad = v
+            if p.grad is not None:
+                p.grad = v
 
     def all_reduce_mean(self, group=None) -> None:
         self.gather()

@@ -18,7 +18,16 @@ _NAMES = ('lvid_top', 'lvid_bot', 'lvpw', 'ivs')
 def expected_coords(y_pred: torch.Tensor, y_true: torch.Tensor, valid, batch_size: int, frame_size: int):
     """-> preds float[B,4,2], gt int32[B,4,2], valid_subset float[B,4] (device tensors)."""
     if not y_pred.is_cuda:
-        raise EchogladError("expected_coords needs CUDA tensors: echoglad_b200 has no CPU fallback")
+        # the unmodified engine hands the evaluator `.cpu()` copies (src/engine.py:471-490): the kernel still runs
+        # on the GPU -- the tensors go back to the current CUDA device (there is no CPU implementation)
+        if not torch.cuda.is_available():
+            raise EchogladError("expected_coords needs a CUDA device: echoglad_b200 has no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        y_pred, y_true = y_pred.to(dev), y_true.to(dev)
+        valid = None if valid is None else valid.to(dev)
+    elif y_true.device != y_pred.device or (valid is not None and valid.device != y_pred.device):
+        y_true = y_true.to(y_pred.device)
+        valid = None if valid is None else valid.to(y_pred.device)
     lg = y_pred.detach().to(torch.float32).contiguous().view(-1, 4)
     yt = y_true.detach().to(torch.float32).contiguous().view(-1, 4)
     vd = None if valid is None else valid.detach().to(torch.float32).contiguous().view(-1, 4)
@@ -30,9 +39,10 @@ def expected_coords(y_pred: torch.Tensor, y_true: torch.Tensor, valid, batch_siz
     preds = torch.empty(batch_size, 4, 2, device=dev)
     gt = torch.empty(batch_size, 4, 2, device=dev, dtype=torch.int32)
     vs = torch.empty(batch_size, 4, device=dev)
-    check(lib.eg_expected_coords(batch_size, 4, n0, frame_size, lg.data_ptr(), yt.data_ptr(),
-                                 None if vd is None else vd.data_ptr(), preds.data_ptr(), gt.data_ptr(),
-                                 vs.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "eg_expected_coords")
+    with torch.cuda.device(dev):
+        check(lib.eg_expected_coords(batch_size, 4, n0, frame_size, lg.data_ptr(), yt.data_ptr(),
+                                     None if vd is None else vd.data_ptr(), preds.data_ptr(), gt.data_ptr(),
+                                     vs.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "eg_expected_coords")
     return preds, gt, vs
 
 
@@ -145,3 +155,66 @@ class LandmarkExpectedCoordiantesEvaluator(object):
 
     def get_predictions(self):
         return self.detailed_performance
+
+    # ---- visualisation helpers used by Engine.log_heatmap_wandb (src/engine.py:560-578); host-side, not on the hot
+    # path: plain torch on whatever device the tensors live on, matplotlib imported only when a figure is asked for
+    _CHANNEL_RGB = ((0.0, 1.0, 1.0), (1.0, 0.7, 0.9), (0.0, 1.0, 0.0), (1.0, 0.0, 0.0))
+
+    def get_softmaxed_heatmap(self, y_pred):
+        """[N, nodes, C] logits -> [N, S, S, C]: softmax over the main-level nodes of every frame and channel
+        (src/core/evaluators.py:451-461)."""
+        s = self.frame_size
+        main = y_pred[:, -s * s:, :]
+        return torch.softmax(main, dim=1).view(-1, s, s, y_pred.shape[-1])
+
+    def create_overlay_image(self, x, hms):
+        """Gray frame [S,S] + C heat maps [S,S,C] -> PIL image; overlapping channels keep the brightest colour
+        (src/core/evaluators.py:592-613)."""
+        import torchvision
+        hms = torch.as_tensor(hms, dtype=torch.float32)
+        img = (0.8 * torch.as_tensor(x, dtype=torch.float32)).clamp_min(0).expand(3, -1, -1).clone()
+        for c, rgb in enumerate(self._CHANNEL_RGB[:hms.shape[-1]]):
+            img = torch.maximum(img, torch.tensor(rgb).view(3, 1, 1) * hms[:, :, c])
+        return torchvision.transforms.ToPILImage()(img)
+
+    def get_heatmaps(self, x, landmark_preds, landmark_y, coord_preds, pix2mm_x, pix2mm_y):
+        """matplotlib figure of the first frame of the batch: predicted vs ground-truth heat maps with the landmark
+        points, the three measured widths and their errors (src/core/evaluators.py:463-590).  Needs `update()` to have
+        run on the same batch."""
+        import matplotlib.pyplot as plt
+        s, b = self.frame_size, self.batch_size
+        frame = x[0, 0].detach().cpu()
+        gt_map = landmark_y.detach().cpu().view(b, -1, 4)[0, -s * s:, :].view(s, s, 4)
+        hms = self.get_softmaxed_heatmap(landmark_preds.detach().cpu().view(b, -1, 4)[0:1])[0]
+        hms = hms / hms.amax(dim=(0, 1), keepdim=True)
+        panels = {'pred': self.create_overlay_image(frame, hms), 'gt': self.create_overlay_image(frame, gt_map)}
+        widths = {k: v[0] for k, v in self.detailed_performance['widths'].items()}
+        mae = dict(zip(('ivs', 'lvid', 'lvpw'), self.calculate_width_MAE(widths)))
+        mpe = dict(zip(('ivs', 'lvid', 'lvpw'), self.calculate_width_MPE(widths)))
+        pts = {k: v[0].tolist() for k, v in self.detailed_performance['coordinates'].items()}
+        order = ['pred', 'gt']
+        if coord_preds is not None:
+            cp = coord_preds.detach().cpu().view(b, -1, 2)[0]
+            for name, k in zip(_NAMES, range(4)):
+                pts[f'coord_{name}'] = cp[k].tolist()
+            for name, (i, j) in self._SPANS.items():
+                widths[f'coord_{name}_mm'] = self.get_pixel_length(cp[i, 0], cp[i, 1], cp[j, 0], cp[j, 1],
+                                                                   pix2mm_x[0], pix2mm_y[0])
+            panels['coord'] = self.create_overlay_image(frame, torch.zeros_like(hms))
+            order = ['pred', 'coord', 'gt']
+        fig, axs = plt.subplots(1, len(order), figsize=(4 * len(order), 5))
+        for ax, tag in zip(axs, order):
+            ax.imshow(panels[tag])
+            for name in _NAMES:
+                ax.plot(pts[f'{tag}_{name}'][1], pts[f'{tag}_{name}'][0], marker='x', color='white', markersize=4)
+            for a, c, colour in (('ivs', 'lvid_top', 'dodgerblue'), ('lvid_bot', 'lvpw', 'dodgerblue'),
+                                 ('lvid_top', 'lvid_bot', 'red')):
+                ax.plot([pts[f'{tag}_{a}'][1], pts[f'{tag}_{c}'][1]], [pts[f'{tag}_{a}'][0], pts[f'{tag}_{c}'][0]],
+                        color=colour, linewidth=1.5)
+            ax.set_title(f"{tag}: [{float(widths[f'{tag}_ivs_mm']):.1f}, {float(widths[f'{tag}_lvid_mm']):.1f}, "
+                         f"{float(widths[f'{tag}_lvpw_mm']):.1f}]")
+        plt.setp(axs[1].get_yticklabels(), visible=False)
+        fig.tight_layout()
+        fig.suptitle(f"MAE [mm] | IVS: {float(mae['ivs']):.1f} | LVID: {float(mae['lvid']):.1f} | LVPW: {float(mae['lvpw']):.1f}\n"
+                     f"MPE [%] | IVS: {float(mpe['ivs']):.1f} | LVID: {float(mpe['lvid']):.1f} | LVPW: {float(mpe['lvpw']):.1f}")
+        return fig

@@ -56,11 +56,14 @@ class _GNNBlock(nn.Module):
 def _update_running(bn: nn.BatchNorm1d, mean: torch.Tensor, var: torch.Tensor, n: int, sl=slice(None)) -> None:
     """torch BatchNorm train-mode bookkeeping: momentum update with the UNBIASED variance."""
     with torch.no_grad():
-        m = bn.momentum if bn.momentum is not None else 0.1
+        bn.num_batches_tracked += 1
+        if bn.momentum is None:  # torch: cumulative moving average, factor 1 / num_batches_tracked
+            m = 1.0 / float(bn.num_batches_tracked)
+        else:
+            m = bn.momentum
         unbiased = var[sl] * (n / max(n - 1, 1))
         bn.running_mean.mul_(1 - m).add_(mean[sl], alpha=m)
         bn.running_var.mul_(1 - m).add_(unbiased, alpha=m)
-        bn.num_batches_tracked += 1
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -159,8 +162,9 @@ class HierarchicalPatchModel(nn.Module):
                                         use_coordinate_graph=bool(use_coordinate_graph),
                                         use_connection_nodes=bool(use_connection_nodes),
                                         main_graph_type=main_graph_type, aux_graph_type=aux_graph_type)
-        self._step = 0
-        self.dropout_seed = 0x5EED
+        self._step = 0              # training forwards so far (advances the dropout stream; not part of state_dict,
+        self.dropout_seed = 0x5EED  # like torch's own RNG state, which the reference does not checkpoint either)
+        self._dropout_stream = None
 
     # -- node features ---------------------------------------------------------------------------------------
     def pyramid(self, x: torch.Tensor) -> List[torch.Tensor]:
@@ -205,6 +209,17 @@ class HierarchicalPatchModel(nn.Module):
     # -- forward ---------------------------------------------------------------------------------------------
     def forward(self, data_batch=None, x: torch.Tensor = None, node_coords: torch.Tensor = None,
                 edge_index: torch.Tensor = None, node_type=None, batch_idx: torch.Tensor = None):
+        # The kernels launch on the CURRENT CUDA device: make it the inputs' device for the whole forward, so a
+        # module living on cuda:1 of a multi-GPU process works (the backward runs on autograd's per-device thread,
+        # which already does this).  One process per GPU (torchrun) remains the supported multi-GPU route.
+        ref = x if x is not None else (data_batch[0].x if isinstance(data_batch, (list, tuple)) else
+                                       getattr(data_batch, "x", None))
+        if ref is None or not ref.is_cuda:
+            raise EchogladError("the landmark module needs CUDA inputs: echoglad_b200 has no CPU fallback")
+        with torch.cuda.device(ref.device):
+            return self._forward(data_batch, x, node_coords, edge_index, node_type, batch_idx)
+
+    def _forward(self, data_batch, x, node_coords, edge_index, node_type, batch_idx):
         if data_batch is not None:
             # the reference's two data_batch forms (src/core/models.py:408-413, src/engine.py:243-248): a collated
             # PyG `Batch` (attributes x / edge_index / batch / node_type / node_coords), or -- on the multi-GPU route,
@@ -240,11 +255,22 @@ class HierarchicalPatchModel(nn.Module):
             a = graph.meta.first_pixel_node
             h = h.view(batch, graph.meta.num_nodes, F)[:, a:a + graph.meta.num_pixel_nodes].reshape(-1, F)
         out = self.classify(h)
-        self._step += 1
+        if self.training:
+            self._step += 1
         return out.squeeze(1), (None if coords is None else coords.reshape(batch * 4, 2))
 
+    def _stream_id(self) -> int:
+        """Distinguishes dropout streams of different runs / replicas: torch's global seed (the engine sets it from
+        `train.seed`, src/engine.py:31-33) and the data-parallel rank, so ranks do not apply the same masks."""
+        if self._dropout_stream is None:
+            rank = 0
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                rank = torch.distributed.get_rank()
+            self._dropout_stream = (torch.initial_seed() * 0x2545F4914F6CDD1D + rank * 0x9E3779B97F4A7C15) & ((1 << 63) - 1)
+        return self._dropout_stream
+
     def _seed(self, salt: int) -> int:
-        return (self.dropout_seed * 0x9E3779B1 + self._step * 1000003 + salt * 7919) & 0x7FFFFFFFFFFFFFFF
+        return (self.dropout_seed * 0x9E3779B1 + self._stream_id() + self._step * 1000003 + salt * 7919) & 0x7FFFFFFFFFFFFFFF
 
     def update_coordinates(self, i: int, y: torch.Tensor, coords: torch.Tensor, graph: DeviceGraph, batch: int):
         """Coordinate update after GNN layer i (src/core/models.py:438-473): relative-position features + the

@@ -32,8 +32,27 @@ def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+def device_of(t: torch.Tensor):
+    """Context manager: the tensor's CUDA device becomes the current one (the C ABI launches on the current device)."""
+    if not t.is_cuda:
+        raise EchogladError("expected a CUDA tensor: echoglad_b200 has no CPU fallback")
+    return torch.cuda.device(t.device)
+
+
+_WS_CACHE = {}
+
+
 def _ws(device) -> torch.Tensor:
-    return torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+    """The library's scratch area (per-CTA partials of reductions), cached per (device, stream): every entry point
+    finishes with its workspace inside the call, and calls on one stream are ordered, so one buffer per stream is
+    enough (it was a fresh 10 MB allocation per call)."""
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    t = _WS_CACHE.get(key)
+    if t is None:
+        t = _WS_CACHE[key] = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=torch.device("cuda", idx))
+    return t
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -110,8 +129,11 @@ def bn_act_bwd(dy, h, mean, var, gamma, beta, eps, drop_p, seed, relu, batch_sta
     return dh, dgamma, dbeta
 
 
-def node_labels(coords: torch.Tensor, frame_size: int, level_size: Sequence[int]) -> torch.Tensor:
-    """coords int32[B, C, 2] (h, w) on device -> y float32[B, n0, C] (create_node_labels on device)."""
+def node_labels(coords: torch.Tensor, frame_size: int, level_size: Sequence[int], validate: bool = True) -> torch.Tensor:
+    """coords int32[B, C, 2] (h, w) on device -> y float32[B, n0, C] (create_node_labels on device).
+    validate=True raises IndexError, as the reference does (src/core/datasets.py:536-537), when a coordinate is
+    >= frame_size (one host sync); validate=False skips the sync -- such labels are NaN-poisoned by the kernel, so a
+    loss computed from them is NaN rather than silently wrong."""
     if not coords.is_cuda:
         raise EchogladError("coords must be a CUDA tensor")
     coords = coords.to(torch.int32).contiguous()
@@ -119,8 +141,12 @@ def node_labels(coords: torch.Tensor, frame_size: int, level_size: Sequence[int]
     n0 = sum(s * s for s in level_size)
     y = torch.empty(b, n0, c, device=coords.device)
     ls = (C.c_int32 * len(level_size))(*level_size)
-    check(lib.eg_node_labels(b, c, frame_size, len(level_size), ls, coords.data_ptr(), y.data_ptr(),
+    oob = torch.zeros(1, dtype=torch.int32, device=coords.device) if validate else None
+    check(lib.eg_node_labels(b, c, frame_size, len(level_size), ls, coords.data_ptr(), y.data_ptr(), _ptr(oob),
                              _stream(coords)), "eg_node_labels")
+    if validate and int(oob.item()):
+        raise IndexError(f"{int(oob.item())} landmark coordinate(s) outside [-{frame_size}, {frame_size}): the "
+                         "reference's create_node_labels raises IndexError for them (src/core/datasets.py:536-537)")
     return y
 
 

@@ -21,9 +21,10 @@ def host_batch(batch: int, frame_size: int, seed: int = 200, pin: bool = True):
     return frames, coords
 
 
-def device_labels(coords_dev: torch.Tensor, spec: HierGraphSpec):
-    """coords int32[B,4,2] on device -> (y, valid) float32[B*N0, 4]."""
+def device_labels(coords_dev: torch.Tensor, spec: HierGraphSpec, validate: bool = False):
+    """coords int32[B,4,2] on device -> (y, valid) float32[B*N0, 4].  validate=False: no host sync per step (the
+    synthetic coordinates are in range by construction; out-of-range ones would NaN-poison the labels)."""
     meta = spec.info()
-    y = ops.node_labels(coords_dev, spec.frame_size, meta.level_size)
+    y = ops.node_labels(coords_dev, spec.frame_size, meta.level_size, validate=validate)
     y = y.view(-1, y.shape[-1])
     return y, torch.ones_like(y)

@@ -207,9 +207,11 @@ int eg_expected_landmark_mse(int batch, int channels, int num_levels, const int3
                              float* loss_out, float* dlogits, void* ws, size_t ws_bytes, void* stream);
 /* Multi-level one-hot labels on device from landmark pixel coordinates — replaces create_node_labels
  * (src/core/datasets.py:523-549).  coords: DEVICE int32[batch, channels, 2] (h, w) in [0, frame);
- * y: float[batch, n0, channels]. */
+ * y: float[batch, n0, channels].  A coordinate >= frame (the reference raises IndexError, :536-537) or < -frame
+ * cannot be labelled: the (frame, channel)'s labels are poisoned with NaN so that every loss computed from them is
+ * NaN instead of silently wrong, and *oob_count (DEVICE int32, optional, caller-zeroed) is incremented. */
 int eg_node_labels(int batch, int channels, int frame_size, int num_levels, const int32_t* level_size,
-                   const int32_t* coords, float* y, void* stream);
+                   const int32_t* coords, float* y, int32_t* oob_count, void* stream);
 
 /* ---- post-path metric: expected landmark coordinates (src/core/evaluators.py:310-348) ----------------
  * On the main level (the last frame_size^2 of the nodes_per_frame pixel nodes of every frame): softmax over the

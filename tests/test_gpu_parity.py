@@ -378,6 +378,15 @@ def test_node_labels_bit_exact():
     frames, coords, y, valid = R.synthetic_batch(5, 224, 7, seed=3)
     got = ops.node_labels(coords.to(DEV), 224, R.level_sizes(224, 7)).view(-1, 4).cpu()
     assert torch.equal(got, y)
+    # a coordinate == frame_size: IndexError as in the reference (src/core/datasets.py:536-537); without the check the
+    # labels of that (frame, channel) are NaN-poisoned, never silently all-zero
+    bad = coords.clone()
+    bad[2, 1, 0] = 224
+    with pytest.raises(IndexError):
+        ops.node_labels(bad.to(DEV), 224, R.level_sizes(224, 7))
+    poisoned = ops.node_labels(bad.to(DEV), 224, R.level_sizes(224, 7), validate=False)
+    assert torch.isnan(poisoned[2, :, 1]).any() and not torch.isnan(poisoned[2, :, 0]).any()
+    assert not torch.isnan(poisoned[[0, 1, 3, 4]]).any()
 
 
 @pytest.mark.parametrize("frame,naux,main_only,batch", [(12, 3, False, 3), (224, 7, False, 2), (16, 1, True, 4)])
@@ -987,6 +996,10 @@ def test_engine_style_training_steps_through_the_registries():
         ref_logits, _ = landmark(x=embedder(frames), edge_index=edge_index)
         evaluator.update(ref_logits, y, torch.ones(batch, device=DEV), torch.ones(batch, device=DEV), valid)
     assert set(evaluator.compute()) >= {'lvid_top', 'ivs_w', 'lvpw_mpe'}
+    # the unmodified engine hands the evaluator `.cpu()` tensors (src/engine.py:471-490): same numbers
+    dev_last = evaluator.get_last()
+    evaluator.update(ref_logits.cpu(), y.cpu(), torch.ones(batch), torch.ones(batch), valid.cpu())
+    assert evaluator.get_last() == dev_last
     clone = models['unet_hierarchical_patch'](**landmark_cfg).to(DEV)
     clone.load_state_dict(landmark.state_dict(), strict=True)
     clone.eval()

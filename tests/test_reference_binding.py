@@ -123,3 +123,23 @@ def test_other_registry_entries_and_flags_round_trip(ref_builders, name, extra):
     assert type(ours).__module__.startswith("echoglad_b200")
     ours.load_state_dict(ref.state_dict(), strict=True)
     assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+
+
+def test_evaluator_visual_helpers_match_the_reference_class(ref_builders):
+    """`get_softmaxed_heatmap` / `create_overlay_image`, which Engine.log_heatmap_wandb calls through the evaluator
+    (src/engine.py:575), against the reference class on the same inputs (bit-exact: same torch ops)."""
+    import sys
+    import numpy as np
+    import echoglad_b200 as eg
+    _, _, eb = ref_builders
+    plt = sys.modules["matplotlib.pyplot"]
+    if not hasattr(plt, "get_cmap"):  # stubbed matplotlib of the build container
+        plt.get_cmap = lambda name: None
+    ref = eb.EVALUATORS["landmarkcoorderror"](None, 2, 16, False)
+    ours = eg.LandmarkExpectedCoordiantesEvaluator(None, 2, 16, False)
+    g = torch.Generator().manual_seed(3)
+    y = torch.randn(2, 84 + 256, 4, generator=g)
+    assert torch.equal(ref.get_softmaxed_heatmap(y), ours.get_softmaxed_heatmap(y))
+    for x in (torch.rand(16, 16, generator=g), torch.randn(16, 16, generator=g)):
+        h = torch.rand(16, 16, 4, generator=g)
+        assert np.array_equal(np.asarray(ref.create_overlay_image(x, h)), np.asarray(ours.create_overlay_image(x, h)))
