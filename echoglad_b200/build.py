@@ -15,8 +15,10 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(PKG, "build")
-LIB = os.path.join(PKG, "libechoglad_b200.so")
+# EG_LIB_OUT=<path>: build a development variant somewhere else (objects beside it), e.g. with EG_NVCC_EXTRA=-D...;
+# load it with EG_LIB_PATH=<path> (tools/build_variants.sh prebuilds such variants so that GPU time is not spent in nvcc)
+LIB = os.environ.get("EG_LIB_OUT") or os.path.join(PKG, "libechoglad_b200.so")
+OBJ = os.path.join(PKG, "build") if not os.environ.get("EG_LIB_OUT") else LIB + ".obj"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -71,9 +71,15 @@ __device__ __forceinline__ bool mbar_try_wait_hint_a(uint32_t bar, uint32_t pari
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait_a(bar, parity)) return;
   uint32_t spins = 0;
+#ifdef EG_WAIT_SPIN  // development: plain try_wait polling (no suspend-time hint)
+  while (!mbar_try_wait_a(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
+#else
   while (!mbar_try_wait_hint_a(bar, parity)) {
     if (++spins > (1u << 22)) __trap();  // seconds: a protocol bug, never a legitimate wait
   }
+#endif
 }
 
 // 16-byte asynchronous global -> shared copy (LDGSTS, L2 only) and its completion on an mbarrier: the
