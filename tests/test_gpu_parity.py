@@ -813,7 +813,7 @@ def _outside(a, b, rtol, atol_frac):
 
 
 def _hot_path_vs_oracle(cfg, variant, batch, frames_or_x, y, valid, sd, embed_sd=None, node_feats=None,
-                        edge_index=None, tag=""):
+                        edge_index=None, tag="", strict_dtype=torch.float32):
     """Packing -> GNN stack -> classifiers -> both losses, forward and backward, on identical pyramid maps (or,
     with `node_feats` [B*N,128], on identical node features: SURVEY.md 8(d) allows synthetic `randn(Nt,128)`
     features for configs[3], which the UNet cannot be configured for).
@@ -824,7 +824,11 @@ def _hot_path_vs_oracle(cfg, variant, batch, frames_or_x, y, valid, sd, embed_sd
     (2) UN-IMPOSED: the oracle is run a second time with its OWN ReLU decisions (the unmodified reference
     function); the fraction of logits / input-gradient entries outside the same bounds is reported
     (gpurun_out/parity_report.jsonl) and must stay below 1 % (SURVEY.md 7.3 expects <~ 0.3 %: a pre-activation
-    within rounding of zero flips between any two fp32 implementations)."""
+    within rounding of zero flips between any two fp32 implementations).
+    `strict_dtype=torch.float64` evaluates the strict pass of the same restatement in double: at 288,084 nodes x 6
+    layers the fp32 oracle's OWN distance from its fp64 evaluation exceeds the gradient bound (1.3 x on
+    node_classifiers.1.8.bias, 2.0 x on node_classifiers.3.0.weight: the column sum of 288 k cancelling softmax
+    gradients), so at that size the device is held to the bound against the more accurate target."""
     model = _build_module(cfg, variant).to(DEV)
     model.load_state_dict(sd, strict=True)
     model.train()
@@ -871,16 +875,16 @@ def _hot_path_vs_oracle(cfg, variant, batch, frames_or_x, y, valid, sd, embed_sd
     else:  # a host edge_index pinned to the reference's sha256 by the CPU tier (tests/test_abi_cpu.py)
         ei_b, nt_b = edge_index, np.zeros(feats.shape[0])
 
-    def oracle(use_masks):
-        osd = R.clone_state(sd, requires_grad=True)
-        cl = [t.detach().cpu().requires_grad_(True) for t in leaves]
+    def oracle(use_masks, dtype=torch.float32):
+        osd = R.clone_state({k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}, requires_grad=True)
+        cl = [t.detach().cpu().to(dtype).requires_grad_(True) for t in leaves]
         ofeats = R.pack_nodes(cfg, cl) if node_feats is None else cl[0]
         lo = R.landmark_forward(osd, cfg, None, ei_b, nt_b, True, use_masks, node_feats=ofeats)
-        want = R.total_loss(lo, y, valid, cfg, batch)
+        want = R.total_loss(lo, y.to(dtype), valid.to(dtype), cfg, batch)
         want["total"].backward()
         return osd, cl, lo.detach(), want
 
-    osd, cl, lo, want = oracle(masks)
+    osd, cl, lo, want = oracle(masks, strict_dtype)
     for key, count, margin in masks.get("relu_margin", []):
         assert margin <= 1e-4, f"ReLU sign of {key} differs at {count} positions, largest |pre-activation| {margin:.2e}"
     ok, worst = close(logits.detach().cpu(), lo, 1e-4, 1e-5)
@@ -1037,7 +1041,7 @@ def test_config3_448px_8aux_6layers_hot_path_against_oracle():
     _, _, y, valid = R.synthetic_batch(batch, 448, 8, seed=61)
     feats = torch.randn(batch * n, 128, generator=torch.Generator().manual_seed(62))
     _hot_path_vs_oracle(cfg, "avgpool", batch, None, y, valid, R.init_landmark_state(cfg, seed=63), node_feats=feats,
-                        edge_index=ei, tag="configs[3]_S448_n8_L6_B1")
+                        edge_index=ei, tag="configs[3]_S448_n8_L6_B1", strict_dtype=torch.float64)
 
 
 def test_config2_batch64_gcn_entry_points_frames_against_oracle():
