@@ -66,6 +66,13 @@ using namespace eg::tc;
 #define EG_ST_OUT(ptr, v) __stcs((ptr), (v))
 #define EG_ST_AGG(ptr, v) st4((ptr), (v))
 
+// L2 prefetch distance of the loader warps, in tile rounds (0 = off).  r02e on B200, batch 64: 1 -> forward 1.442 ms
+// (off: 1.478), backward 3.17 (3.24); 2 / 3 / 5 -> 1.50 / 1.56 / 1.58 ms (the prefetched rows compete with the
+// frame's halo rows for the L2).
+#ifndef EG_PF_TILES
+#define EG_PF_TILES 1
+#endif
+
 namespace {
 
 constexpr int kStages = 3;                 // operand ring (hi + lo tiles)
@@ -122,7 +129,7 @@ struct TcParams {
 };
 
 #ifdef EG_TC_TIMING
-__device__ long long g_tc_dbg[kNumSMs][12];  // per CTA: cycles spent waiting, by role (see eg_tc_debug_read)
+__device__ long long g_tc_dbg[kNumSMs][20];  // per CTA: cycles spent waiting, by role (see eg_tc_debug_read)
 #define TC_TIMED_WAIT(slot, bar, par)            \
   do {                                           \
     const long long _t = clock64();              \
@@ -191,7 +198,7 @@ __device__ __forceinline__ float4 ld_far(const float* p) { return __ldcg(reinter
 template <bool GATHER>
 __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
 #ifdef EG_TC_TIMING
-  long long dbg_acc[4] = {0, 0, 0, 0};
+  long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long dbg_n = 0;
   const long long dbg_t0 = clock64();
 #endif
@@ -273,6 +280,9 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLoad));
   }
+#ifdef EG_TC_TIMING
+  dbg_acc[6] = clock64() - dbg_t0;  // one-time setup (TMEM allocation, weight -> TMEM, barriers)
+#endif
   if (warp >= kProdWarp0) {
     // ===== compute warps: copy raw rows two chunks ahead, gather -> split -> swizzled operand tile ==========
     const int pw = warp - kProdWarp0;
@@ -325,12 +335,18 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
 #elif !defined(EG_DBG_NOFENCE)
       fence_proxy_async_smem();
 #endif
+#ifdef EG_TC_TIMING
+      const long long _ta = clock64();
+#endif
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_a(sm + kOffFull + (chunk % kStages) * 8);
         mbar_arrive_a(sm + kOffRawEmpty + (chunk % kRawStages) * 8);
       }
       ++chunk;
+#ifdef EG_TC_TIMING
+      dbg_acc[5] += clock64() - _ta;
+#endif
     };
     auto emit = [&](uint32_t a_hi, int i, const float4& acc) {  // 3xTF32 split -> operand tiles
 #ifdef EG_DBG_NOEMIT
@@ -377,6 +393,9 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
           const int node = __ldg(tnode + i * 4);
           if (node >= 0) EG_ST_AGG(p.AggOut + (frow0 + node) * 128 + coff, acc);
         };
+#ifdef EG_TC_TIMING
+        const long long _tp = clock64();
+#endif
         cp_async_wait_all();  // this tile's plan rows (prefetched one tile ahead)
         __syncwarp();
         uint32_t raw, a_hi;
@@ -403,8 +422,14 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
             wv[i][0] = wa.x, wv[i][1] = wa.y, wv[i][2] = wa.z, wv[i][3] = wa.w, wv[i][4] = wb.x, wv[i][5] = wb.w;
           }
           prefetch_plan(tile + gridDim.x, pbuf ^ 1u);
+#ifdef EG_TC_TIMING
+          dbg_acc[4] += clock64() - _tp;
+#endif
 #pragma unroll 1
           for (int kc = 0; kc < 4; ++kc) {
+#ifdef EG_TC_TIMING
+            const long long _tl = clock64();
+#endif
             acquire(raw, a_hi);
 #ifdef EG_DBG_NOCOMPUTE
             release();
@@ -442,6 +467,9 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
 #pragma unroll
               for (int i = 0; i < kIters; ++i) store_agg(i, kc * 32 + j * 4, aggv[i]);
             }
+#ifdef EG_TC_TIMING
+            dbg_acc[7] += clock64() - _tl;
+#endif
           }
           continue;
         }
@@ -549,7 +577,27 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
     int nxt[kPer];
     load_src(blockIdx.x, nxt);
     uint32_t chunk = 0;
+#if EG_PF_TILES > 0
+    // L2 prefetch of the OWN rows of the tile EG_PF_TILES rounds ahead (its 16-row groups are contiguous 8 KB
+    // segments: one bulk prefetch each, issued by 8 threads of the first loader warp).  The raw ring only holds
+    // 3 chunks (0.75 tile) of loads in flight per SM, which does not cover the DRAM latency under load (ncu r02d:
+    // 22 % of the compute warps' samples wait for a raw stage); with the rows already in L2 the ring only has to
+    // cover the L2 latency.
+    auto prefetch_tile = [&](int tile) {
+      if (!GATHER || tile >= p.num_tiles || q >= 8) return;
+      const int b = tile / p.tiles_per_frame, t = tile - b * p.tiles_per_frame;
+      const int first = __ldg(p.tile_groups + t * 16 + q), cnt = __ldg(p.tile_groups + t * 16 + 8 + q);
+      if (first < 0 || cnt <= 0) return;
+      const float* src = p.X + ((long long)b * p.nodes_per_frame + first) * 128;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(cnt * 512) : "memory");
+    };
+#pragma unroll 1
+    for (int d = 1; d < EG_PF_TILES; ++d) prefetch_tile(blockIdx.x + d * gridDim.x);
+#endif
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+#if EG_PF_TILES > 0
+      prefetch_tile(tile + EG_PF_TILES * gridDim.x);
+#endif
       int srow[kPer];  // global row (< 2^31, checked by the launcher), or -1
       if (GATHER) {
         const int base = (tile / p.tiles_per_frame) * p.nodes_per_frame;
@@ -778,7 +826,8 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
 #ifdef EG_TC_TIMING
   if (lane == 0) {
     long long* d = g_tc_dbg[blockIdx.x];
-    if (warp == kProdWarp0) { d[0] = dbg_acc[0]; d[5] = dbg_acc[1]; d[7] = dbg_acc[2]; d[8] = dbg_acc[3]; d[9] = dbg_n; } // compute warp 0: wait operand stage, wait raw, fence
+    if (warp == kProdWarp0) { d[0] = dbg_acc[0]; d[5] = dbg_acc[1]; d[7] = dbg_acc[2]; d[8] = dbg_acc[3]; d[9] = dbg_n; d[10] = clock64() - dbg_t0; d[16] = dbg_acc[4]; d[17] = dbg_acc[5]; d[18] = dbg_acc[6]; d[19] = dbg_acc[7]; } // compute warp 0: wait operand stage, wait raw, fence; span
+    if (warp == kProdWarp0 + kProdWarps - 1) { d[11] = dbg_acc[3]; d[12] = dbg_acc[0]; d[13] = dbg_acc[1]; d[14] = clock64() - dbg_t0; d[15] = dbg_acc[2]; }  // last compute warp
     if (warp == kLoadWarp0) d[6] = dbg_acc[0];                       // loader: wait for a free raw stage
     if (warp == kMmaWarp) { d[1] = dbg_acc[0]; d[2] = dbg_acc[1]; } // MMA: wait acc_empty, wait full
     if (warp == 0) { d[3] = dbg_acc[0]; d[4] = clock64() - dbg_t0; } // epilogue: wait acc_full; total cycles
@@ -818,8 +867,8 @@ int launch(const TcParams& p, float* mean, float* var, void* ws, size_t ws_bytes
 }  // namespace
 
 #ifdef EG_TC_TIMING
-extern "C" int eg_tc_debug_read(long long* out) {  // HOST buffer of kNumSMs * 12 counters
-  return cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(long long) * kNumSMs * 12) == cudaSuccess ? 0 : -2;
+extern "C" int eg_tc_debug_read(long long* out) {  // HOST buffer of kNumSMs * 16 counters
+  return cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(long long) * kNumSMs * 20) == cudaSuccess ? 0 : -2;
 }
 #endif
 

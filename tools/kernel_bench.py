@@ -99,13 +99,13 @@ def main():
         res[name] = {"ms": round(ms, 4), "algo_GB": round(nbytes / 1e9, 3), "GBps": round(nbytes / ms / 1e6, 1)}
         if hasattr(lib, "eg_tc_debug_read") and name in ("gcn_conv_fwd", "linear128", "gcn_conv_bwd"):
             import ctypes as C
-            buf = (C.c_longlong * (148 * 12))()
+            buf = (C.c_longlong * (148 * 20))()
             torch.cuda.synchronize()
             lib.eg_tc_debug_read(buf)
             import numpy as np
-            a = np.array(buf).reshape(148, 12).mean(0)
+            a = np.array(buf).reshape(148, 20).mean(0)
             print(f"   tc wait cycles/CTA: compute-wait-operand {a[0]:.0f} compute-wait-raw {a[5]:.0f} loader-wait-raw-empty {a[6]:.0f} "
-                  f"compute-fence {a[7]:.0f} lattice-chunk-busy {a[8]:.0f} over {a[9]:.0f} chunks mma-wait-acc-empty {a[1]:.0f} mma-wait-full {a[2]:.0f} epilogue-wait-acc-full {a[3]:.0f} total {a[4]:.0f}")
+                  f"compute-fence {a[7]:.0f} lattice-chunk-busy {a[8]:.0f} over {a[9]:.0f} chunks mma-wait-acc-empty {a[1]:.0f} mma-wait-full {a[2]:.0f} epilogue-wait-acc-full {a[3]:.0f} total {a[4]:.0f} | compute0 span {a[10]:.0f} lattice-prologue {a[16]:.0f} release-tail {a[17]:.0f} setup {a[18]:.0f} lattice-loop-total {a[19]:.0f} | compute15: busy {a[11]:.0f} wait-operand {a[12]:.0f} wait-raw {a[13]:.0f} fence {a[15]:.0f} span {a[14]:.0f}")
         print(f"{name:14s} {ms:8.3f} ms   {nbytes / 1e9:6.2f} GB algorithmic   {nbytes / ms / 1e6:8.1f} GB/s", flush=True)
     print(json.dumps({"batch": B, "rows": rows, "results": res}))
 
