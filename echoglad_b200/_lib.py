@@ -27,6 +27,18 @@ class GraphInfo(C.Structure):
                 ("max_degree", C.c_int32), ("crop_offset", C.c_int32)]
 
 
+class ClassifierParams(C.Structure):
+    """eg_classifier_params (include/echoglad_b200.h)."""
+    _fields_ = [(n, C.c_void_p) for n in ("w1", "b1", "g1", "be1", "w2", "b2", "g2", "be2", "w3", "b3")] + \
+               [("eps", C.c_float), ("drop_p", C.c_float), ("seed", C.c_uint64), ("batch_stats", C.c_int32),
+                ("sigmoid", C.c_int32)]
+
+
+class ClassifierGrads(C.Structure):
+    """eg_classifier_grads."""
+    _fields_ = [(n, C.c_void_p) for n in ("dw1", "db1", "dg1", "dbe1", "dw2", "db2", "dg2", "dbe2", "dw3", "db3")]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _L = C.c_int64
@@ -68,6 +80,9 @@ SIGNATURES = {
     "eg_clf_mid_bwd": (_I, [_L, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "eg_clf_out_fwd": (_I, [_L, _P, _P, _P, _I, _P, _P]),
     "eg_clf_out_bwd": (_I, [_L, _P, _P, _P, _P, _I, _P, _P, _P, _P, _SZ, _P]),
+    "eg_classifier_fwd": (_I, [_L, _P, C.POINTER(ClassifierParams), _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "eg_classifier_bwd": (_I, [_L, _P, C.POINTER(ClassifierParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                               C.POINTER(ClassifierGrads), _P, _SZ, _P]),
     "eg_bce_multilevel": (_I, [_L, _P, _P, _P, _F, _F, _P, _P, _P, _SZ, _P]),
     "eg_expected_landmark_mse": (_I, [_I, _I, _I, C.POINTER(C.c_int32), _P, _P, _P, _F, _P, _P, _P, _SZ, _P]),
     "eg_node_labels": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int32), _P, _P, _P, _P]),

@@ -323,6 +323,22 @@ int launch_stats_finalize(int nparts, int cols, int stride, long long rows, cons
   EG_LAUNCH_CHECK();
   return EG_OK;
 }
+// dZ = sc * (G - c1 - xhat * c2): the apply pass of a train-mode BatchNorm backward whose masked input gradient G and
+// coefficients coef = (c1[cols], c2[cols]) were produced elsewhere (classifier_fused.cu).  dZ may alias G.
+int launch_bn_bwd_apply(long long rows, int cols, const float* G, const float* Z, const float* mean, const float* var,
+                        const float* gamma, float eps, const float* coef, float* dZ, cudaStream_t s) {
+  if (!cols_ok(cols)) {
+    set_error("launch_bn_bwd_apply: unsupported cols %d", cols);
+    return EG_ERR_INVALID;
+  }
+  const long long groups = rows * (cols / 4);
+  ProfileScope prof("bn_bwd_apply", s);
+  // no dropout (thr = 0), no ReLU: the kernel's mask is all-pass and dA = G
+  bn_act_bwd_apply_kernel<<<elem_grid(groups), kThreads, 0, s>>>(rows, cols, G, Z, mean, var, gamma, /*beta=*/gamma, eps,
+                                                                0u, 1.0f, 0ull, 0, coef, dZ);
+  EG_LAUNCH_CHECK();
+  return EG_OK;
+}
 int launch_col_sums(long long rows, int cols, const float* Z, float* sums, void* ws, size_t ws_bytes,
                     cudaStream_t s) {
   if (!ws || ws_bytes < kWorkspaceBytes) {

@@ -343,66 +343,68 @@ class GCNLayer(torch.autograd.Function):
 
 
 class ClassifierHeads(torch.autograd.Function):
-    """The four node classifiers (reference src/core/models.py:363-377,488-490) as stacked / block-diagonal
-    transforms.  Inputs are the STACKED parameters: w1 [128,128] (4 x [32,128]), b1 [128], g1/be1 [128],
+    """The four node classifiers (reference src/core/models.py:363-377,488-490) as ONE chain per direction
+    (eg_classifier_fwd / eg_classifier_bwd): stacked / block-diagonal transforms whose BatchNorm / ReLU / Dropout are
+    recomputed from the two saved pre-activations z1 [rows,128] and z2 [rows,64]; no activated tensor is written.
+    Inputs are the STACKED parameters: w1 [128,128] (4 x [32,128]), b1 [128], g1/be1 [128],
     w2 [4,16,32], b2 [4,16], g2/be2 [64], w3 [4,16], b3 [4].
     Returns (out [rows,4], mean1, var1, mean2, var2)."""
+
+    @staticmethod
+    def _params(w1, b1, g1, be1, w2, b2, g2, be2, w3, b3, eps, p, seed, training, sigmoid):
+        from ._lib import ClassifierParams
+        return ClassifierParams(w1.data_ptr(), b1.data_ptr(), g1.data_ptr(), be1.data_ptr(), w2.data_ptr(),
+                                b2.data_ptr(), g2.data_ptr(), be2.data_ptr(), w3.data_ptr(), b3.data_ptr(),
+                                float(eps), float(p), int(seed), int(training), int(sigmoid))
 
     @staticmethod
     def forward(ctx, h, w1, b1, g1, be1, m1_in, v1_in, w2, b2, g2, be2, m2_in, v2_in, w3, b3, training: bool,
                 eps: float, drop_p: float, seed: int, sigmoid: bool):
         h = _f32(h, "h")
-        rows = h.shape[0]
-        dev = h.device
-        st = _stream(h)
+        rows, dev, st = h.shape[0], h.device, _stream(h)
+        if h.shape[1] != F:
+            raise EchogladError(f"ClassifierHeads: h must be [rows, {F}], got {tuple(h.shape)}")
         p = float(drop_p) if training else 0.0
-        ws = _ws(dev)
-        z1 = torch.empty_like(h)
+        prm = [_f32(t, "classifier parameter") for t in (w1, b1, g1, be1, w2, b2, g2, be2, w3, b3)]
         if training:
             m1, v1 = torch.empty(F, device=dev), torch.empty(F, device=dev)
             m2, v2 = torch.empty(64, device=dev), torch.empty(64, device=dev)
         else:
-            m1, v1, m2, v2 = m1_in, v1_in, m2_in, v2_in
-        check(lib.eg_linear128(rows, h.data_ptr(), w1.data_ptr(), 1, b1.data_ptr(), None, z1.data_ptr(),
-                               m1.data_ptr() if training else None, v1.data_ptr() if training else None,
-                               ws.data_ptr(), WORKSPACE_BYTES, st), "eg_linear128")
-        a1 = bn_act_fwd(z1, m1, v1, g1, be1, eps, p, seed, True)
+            m1, v1, m2, v2 = (_f32(t, "running statistics") for t in (m1_in, v1_in, m2_in, v2_in))
+        z1 = torch.empty(rows, F, device=dev)
         z2 = torch.empty(rows, 64, device=dev)
-        check(lib.eg_clf_mid_fwd(rows, a1.data_ptr(), w2.data_ptr(), b2.data_ptr(), z2.data_ptr(),
-                                 m2.data_ptr() if training else None, v2.data_ptr() if training else None,
-                                 ws.data_ptr(), WORKSPACE_BYTES, st), "eg_clf_mid_fwd")
-        a2 = bn_act_fwd(z2, m2, v2, g2, be2, eps, p, seed + 1, True)
-        if CAPTURE_RELU is not None:
-            CAPTURE_RELU.append(("clf_a", (a1 if p == 0.0 else bn_act_fwd(z1, m1, v1, g1, be1, eps, 0.0, seed, True)) > 0))
-            CAPTURE_RELU.append(("clf_b", (a2 if p == 0.0 else bn_act_fwd(z2, m2, v2, g2, be2, eps, 0.0, seed, True)) > 0))
         out = torch.empty(rows, 4, device=dev)
-        check(lib.eg_clf_out_fwd(rows, a2.data_ptr(), w3.data_ptr(), b3.data_ptr(), int(sigmoid), out.data_ptr(), st),
-              "eg_clf_out_fwd")
-        ctx.save_for_backward(h, w1, g1, be1, m1, v1, w2, g2, be2, m2, v2, w3, z1, a1, z2, a2, out)
+        cp = ClassifierHeads._params(*prm, eps, p, seed, training, sigmoid)
+        ws = _ws(dev)
+        check(lib.eg_classifier_fwd(rows, h.data_ptr(), C.byref(cp), m1.data_ptr(), v1.data_ptr(), m2.data_ptr(),
+                                    v2.data_ptr(), z1.data_ptr(), z2.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                    WORKSPACE_BYTES, st), "eg_classifier_fwd")
+        if CAPTURE_RELU is not None:  # sign patterns of the two ReLU inputs (same arithmetic as the chain's kernels)
+            CAPTURE_RELU.append(("clf_a", bn_act_fwd(z1, m1, v1, prm[2], prm[3], eps, 0.0, seed, True) > 0))
+            CAPTURE_RELU.append(("clf_b", bn_act_fwd(z2, m2, v2, prm[6], prm[7], eps, 0.0, seed, True) > 0))
+        ctx.save_for_backward(h, *prm, m1, v1, m2, v2, z1, z2, out)
         ctx.cfg = (training, eps, p, seed, sigmoid)
         ctx.mark_non_differentiable(m1, v1, m2, v2)
         return out, m1, v1, m2, v2
 
     @staticmethod
     def backward(ctx, dout, *_):
-        h, w1, g1, be1, m1, v1, w2, g2, be2, m2, v2, w3, z1, a1, z2, a2, out = ctx.saved_tensors
+        h, w1, b1, g1, be1, w2, b2, g2, be2, w3, b3, m1, v1, m2, v2, z1, z2, out = ctx.saved_tensors
         training, eps, p, seed, sigmoid = ctx.cfg
+        from ._lib import ClassifierGrads
         dout = _f32(dout, "dout")
         rows, dev, st = h.shape[0], h.device, _stream(h)
+        cp = ClassifierHeads._params(w1, b1, g1, be1, w2, b2, g2, be2, w3, b3, eps, p, seed, training, sigmoid)
+        grads = [torch.empty_like(t) for t in (w1, b1, g1, be1, w2, b2, g2, be2, w3, b3)]
+        cg = ClassifierGrads(*[t.data_ptr() for t in grads])
+        scratch = torch.empty(rows, F, device=dev)
+        dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
         ws = _ws(dev)
-        da2 = torch.empty_like(a2)
-        dw3, db3 = torch.empty_like(w3), torch.empty(4, device=dev)
-        check(lib.eg_clf_out_bwd(rows, a2.data_ptr(), w3.data_ptr(), out.data_ptr(), dout.data_ptr(), int(sigmoid),
-                                 da2.data_ptr(), dw3.data_ptr(), db3.data_ptr(), ws.data_ptr(), WORKSPACE_BYTES, st),
-              "eg_clf_out_bwd")
-        dz2, dg2, dbe2 = bn_act_bwd(da2, z2, m2, v2, g2, be2, eps, p, seed + 1, True, training)
-        da1 = torch.empty_like(a1)
-        dw2, db2 = torch.empty_like(w2), torch.empty(4, 16, device=dev)
-        check(lib.eg_clf_mid_bwd(rows, a1.data_ptr(), w2.data_ptr(), dz2.data_ptr(), da1.data_ptr(), dw2.data_ptr(),
-                                 db2.data_ptr(), ws.data_ptr(), WORKSPACE_BYTES, st), "eg_clf_mid_bwd")
-        dz1, dg1, dbe1 = bn_act_bwd(da1, z1, m1, v1, g1, be1, eps, p, seed, True, training)
-        dw1, db1 = linear128_wgrad(dz1, h, True)
-        dh = linear128(dz1, w1, False) if ctx.needs_input_grad[0] else None
+        check(lib.eg_classifier_bwd(rows, h.data_ptr(), C.byref(cp), m1.data_ptr(), v1.data_ptr(), m2.data_ptr(),
+                                    v2.data_ptr(), z1.data_ptr(), z2.data_ptr(), out.data_ptr(), dout.data_ptr(),
+                                    scratch.data_ptr(), _ptr(dh), C.byref(cg), ws.data_ptr(), WORKSPACE_BYTES, st),
+              "eg_classifier_bwd")
+        dw1, db1, dg1, dbe1, dw2, db2, dg2, dbe2, dw3, db3 = grads
         return (dh, dw1, db1, dg1, dbe1, None, None, dw2, db2, dg2, dbe2, None, None, dw3, db3) + (None,) * 5
 
 

@@ -222,6 +222,40 @@ int eg_expected_coords(int batch, int channels, int nodes_per_frame, int frame_s
                        const float* y, const float* valid, float* pred_hw, int32_t* gt_hw, float* valid_mean,
                        void* stream);
 
+/* ---- the four node classifiers as one chain (replaces node_classifiers[0..3] applied to h and concatenated,
+ * src/core/models.py:363-377,488-490, and their autograd) --------------------------------------------------------
+ * Stacked / block-diagonal parameters: w1 float[128,128] = 4 x Linear(128,32).weight stacked, b1 float[128];
+ * g1 / be1 float[128] = 4 x BatchNorm1d(32) weight / bias; w2 float[4,16,32], b2 float[4,16]; g2 / be2 float[64];
+ * w3 float[4,16], b3 float[4].  batch_stats != 0: train-mode BatchNorm (batch statistics are COMPUTED into
+ * mean1/var1/mean2/var2); 0: those four vectors are INPUTS (running statistics).  Dropout (p = drop_p, counter-based
+ * with `seed` for layer 1 and `seed + 1` for layer 2, as eg_bn_act_fwd) is applied when drop_p > 0.
+ * Forward keeps only the two pre-activations z1 float[rows,128] and z2 float[rows,64] for the backward; no activated
+ * tensor is materialised.  out: float[rows,4] (logits, or probabilities when sigmoid != 0). */
+typedef struct eg_classifier_params {
+  const float *w1, *b1, *g1, *be1;
+  const float *w2, *b2, *g2, *be2;
+  const float *w3, *b3;
+  float eps;
+  float drop_p;
+  uint64_t seed;
+  int32_t batch_stats;
+  int32_t sigmoid;
+} eg_classifier_params;
+typedef struct eg_classifier_grads {  /* all required; same shapes as the parameters */
+  float *dw1, *db1, *dg1, *dbe1;
+  float *dw2, *db2, *dg2, *dbe2;
+  float *dw3, *db3;
+} eg_classifier_grads;
+int eg_classifier_fwd(int64_t rows, const float* h, const eg_classifier_params* p, float* mean1, float* var1,
+                      float* mean2, float* var2, float* z1, float* z2, float* out, void* ws, size_t ws_bytes,
+                      void* stream);
+/* Backward from dout float[rows,4].  scratch: float[rows,128] (overwritten: masked layer-1 gradient, then dz1);
+ * dh (optional): float[rows,128] gradient with respect to h; `out` is read for the sigmoid head only. */
+int eg_classifier_bwd(int64_t rows, const float* h, const eg_classifier_params* p, const float* mean1,
+                      const float* var1, const float* mean2, const float* var2, const float* z1, const float* z2,
+                      const float* out, const float* dout, float* scratch, float* dh,
+                      const eg_classifier_grads* g, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- measurement hooks (no reference counterpart) ---------------------------------------------------
  * eg_profile_enable(1) clears and starts recording CUDA-event spans around every launch helper on the
  * caller's stream; eg_profile_read sums the device time and span count recorded under `name`

@@ -202,6 +202,11 @@ def test_argument_validation_happens_before_any_cuda_call(eg):
     assert lib.eg_expected_coords(2, 4, 10, 4, 1, 1, None, 1, 1, 1, None) < 0   # frame^2 > nodes per frame
     assert lib.eg_linear128_wgrad(0, None, None, None, None, None, 0, None) < 0
     assert lib.eg_gcn_conv_fwd(None, 1, None, None, None, None, None, None, None, 0, None) < 0
+    assert lib.eg_classifier_fwd(4, None, None, None, None, None, None, None, None, None, None, 0, None) < 0
+    assert b"eg_classifier_fwd" in lib.eg_last_error()
+    assert lib.eg_classifier_bwd(4, None, None, None, None, None, None, None, None, None, None, None, None, None,
+                                 None, 0, None) < 0
+    assert b"eg_classifier_bwd" in lib.eg_last_error()
 
 
 def test_registry_patch_with_evaluators(eg):

@@ -314,6 +314,77 @@ def test_clf_mid_entry_points(rows):
     assert ok, worst
 
 
+@pytest.mark.parametrize("rows", [1, 5, 33, 1000, 144040, 300007])
+@pytest.mark.parametrize("training,drop_p,sigmoid", [(True, 0.0, False), (True, 0.3, True), (False, 0.0, False),
+                                                     (False, 0.0, True)])
+def test_classifier_chain_entry_points(rows, training, drop_p, sigmoid):
+    """eg_classifier_fwd / eg_classifier_bwd (the four heads as one chain, activations recomputed from the saved
+    pre-activations) against float64 torch autograd of the reference module structure Linear-BN-ReLU-Drop-Linear-BN-
+    ReLU-Drop-Linear(-Sigmoid) per head (src/core/models.py:363-377), with the chain's own dropout masks."""
+    if rows == 1 and training:
+        pytest.skip("train-mode BatchNorm over one row has zero variance (torch raises)")
+    gen = torch.Generator().manual_seed(rows * 7 + int(training) + 2 * int(sigmoid))
+    r = lambda *s: torch.randn(*s, generator=gen)  # noqa: E731
+    h = r(rows, 128)
+    prm = dict(w1=r(128, 128) * 0.15, b1=r(128) * 0.1, g1=torch.rand(128, generator=gen) + 0.5, be1=r(128) * 0.2,
+               w2=r(4, 16, 32) * 0.3, b2=r(4, 16) * 0.1, g2=torch.rand(64, generator=gen) + 0.5, be2=r(64) * 0.2,
+               w3=r(4, 16) * 0.4, b3=r(4) * 0.1)
+    run = dict(m1=r(128) * 0.1, v1=torch.rand(128, generator=gen) + 0.5, m2=r(64) * 0.1,
+               v2=torch.rand(64, generator=gen) + 0.5)
+    dout = r(rows, 4)
+    seed, eps = 4242, 1e-5
+    dev = {k: v.to(DEV).requires_grad_(True) for k, v in prm.items()}
+    hd = h.to(DEV).requires_grad_(True)
+    ops.CAPTURE_RELU = []  # the device's ReLU sign patterns (a pre-activation within rounding of 0 flips between fp32 and fp64)
+    try:
+        out, m1, v1, m2, v2 = ops.ClassifierHeads.apply(
+            hd, dev["w1"], dev["b1"], dev["g1"], dev["be1"], run["m1"].to(DEV), run["v1"].to(DEV), dev["w2"], dev["b2"],
+            dev["g2"], dev["be2"], run["m2"].to(DEV), run["v2"].to(DEV), dev["w3"], dev["b3"], training, eps, drop_p, seed,
+            sigmoid)
+        (_, sign1), (_, sign2) = ops.CAPTURE_RELU
+    finally:
+        ops.CAPTURE_RELU = None
+    out.backward(dout.to(DEV))
+    # float64 reference
+    ref = {k: v.double().requires_grad_(True) for k, v in prm.items()}
+    hr = h.double().requires_grad_(True)
+    p = drop_p if training else 0.0
+    mask1 = ops.dropout_mask(rows, 128, p, seed, DEV).cpu().double()
+    mask2 = ops.dropout_mask(rows, 64, p, seed + 1, DEV).cpu().double()
+
+    def relu_as_device(pre, sign):  # same piecewise-linear function on both sides; disagreements must be rounding-level
+        sign = sign.cpu()
+        bad = (pre.detach() > 0) != sign
+        assert not bool(bad.any()) or float(pre.detach()[bad].abs().max()) <= 1e-4
+        return pre * sign.double()
+
+    z1 = hr @ ref["w1"].t() + ref["b1"]
+    mu1, va1 = (z1.mean(0), z1.var(0, unbiased=False)) if training else (run["m1"].double(), run["v1"].double())
+    a1 = relu_as_device((z1 - mu1) / torch.sqrt(va1 + eps) * ref["g1"] + ref["be1"], sign1) * mask1
+    z2 = (torch.einsum("rki,kji->rkj", a1.view(rows, 4, 32), ref["w2"]) + ref["b2"]).reshape(rows, 64)
+    mu2, va2 = (z2.mean(0), z2.var(0, unbiased=False)) if training else (run["m2"].double(), run["v2"].double())
+    a2 = relu_as_device((z2 - mu2) / torch.sqrt(va2 + eps) * ref["g2"] + ref["be2"], sign2) * mask2
+    want = torch.einsum("rkj,kj->rk", a2.view(rows, 4, 16), ref["w3"]) + ref["b3"]
+    if sigmoid:
+        want = torch.sigmoid(want)
+    want.backward(dout.double())
+    ok, worst = close(out.detach().cpu(), want.detach(), 1e-4, 1e-5)
+    assert ok, f"out {worst}"
+    if training:
+        for got, w_, name in ((m1, mu1, "mean1"), (v1, va1, "var1"), (m2, mu2, "mean2"), (v2, va2, "var2")):
+            ok, worst = close(got.cpu(), w_.detach(), 1e-4, 1e-5)
+            assert ok, f"{name} {worst}"
+    ok, worst = close(hd.grad.cpu(), hr.grad, 1e-3, 1e-4)
+    assert ok, f"dh {worst}"
+    gmax = max(float(v.grad.abs().max()) for v in ref.values())
+    for k in prm:
+        if training and k in ("b1", "b2"):  # a bias in front of a train-mode BatchNorm: true gradient 0, rounding noise only
+            assert float(dev[k].grad.abs().max()) <= 1e-3 * gmax, k
+            continue
+        ok, worst = close(dev[k].grad.cpu(), ref[k].grad, 1e-3, 1e-4)
+        assert ok, f"d{k} {worst}"
+
+
 # ---- BN + dropout + act + residual ----------------------------------------------------------------------------
 
 @pytest.mark.parametrize("cols", [64, 128])
