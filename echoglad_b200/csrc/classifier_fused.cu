@@ -6,12 +6,15 @@
 //             z2 = blockdiag(W2) act1(z1) + b2 (+ stats)  clf_mid_act_fwd_kernel                           1.5 U
 //             out = blockdiag(W3) act2(z2) + b3           clf_tail_fwd_kernel                              0.5 U
 //   backward  BN2 sums, dW3, db3 from (z2, dout)          clf_tail_bwd_kernel (reduction only)             0.5 U
-//             dz2 (registers / shared memory only) -> dW2, db2, g1 = mask1 * (W2^T dz2), BN1 sums
-//                                                         clf_mid_act_bwd_kernel (reads z1, z2; writes g1) 2.5 U
+//             dz2 = BN2-backward(mask2 * dout W3)         clf_tail_dz2_kernel (reads z2; writes dz2)       1   U
+//             dW2, db2, g1 = mask1 * (W2^T dz2), BN1 sums clf_mid_act_bwd_kernel (reads z1, dz2; writes g1) 2.5 U
 //             dz1 = BN1-backward(g1, z1), in place        bn_bwd_apply (bn.cu)                             3   U
 //             dh = dz1 W1, dW1 = dz1^T h, db1             eg::launch_linear_tc / eg::launch_wgrad_tc       4   U
-// with U = rows * 128 * 4 bytes: 4 U forward + 10 U backward, against 7 U + 15 U for the r01 chain of separate
+// with U = rows * 128 * 4 bytes: 4 U forward + 11 U backward, against 7 U + 15 U for the r01 chain of separate
 // linear / BatchNorm-activation / layer kernels (which wrote and re-read a1, a2, da2, dz2, da1).
+// (r02f/h: forming dz2 inside clf_mid_act_bwd_kernel -- one column per lane, exchanged through the warp's ring slot,
+// software-pipelined one row ahead -- saves that 1 U but made the kernel instruction-bound: 3.2-3.6 ms against
+// 1.4 ms for the r01 kernel; the dropout hash and the index arithmetic are integer work at half the FP32 rate.)
 // act(z) = relu(drop(gamma (z - mean) rsqrt(var + eps) + beta)) with the arithmetic of bn.cu, so the sign pattern
 // and the dropout masks are bit-identical to eg_bn_act_fwd on the same inputs.
 #include "common.cuh"
@@ -200,28 +203,39 @@ clf_tail_fwd_kernel(long long rows, const float* __restrict__ Z2, const Act act,
   for (int e = 0; e < 4; ++e) col[e] = load_col(act, q * 4 + e);
   const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long r0 = warp_id * 2; r0 < rows; r0 += nwarps * 2) {  // warp-uniform trip count
-    const long long r = r0 + half;
-    const bool valid = r < rows;
-    const float4 z = valid ? ldg4(Z2 + r * 64 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint32_t keep = act.thr ? drop_keep4(act.seed, (uint64_t)(r * 16 + q), act.thr) : 0xfu;
-    bool pass;
-    float p = act_fwd(z.x, col[0], keep & 1u, act.keep_scale, pass) * w.x;
-    p = fmaf(act_fwd(z.y, col[1], keep & 2u, act.keep_scale, pass), w.y, p);
-    p = fmaf(act_fwd(z.z, col[2], keep & 4u, act.keep_scale, pass), w.z, p);
-    p = fmaf(act_fwd(z.w, col[3], keep & 8u, act.keep_scale, pass), w.w, p);
-    p += __shfl_xor_sync(0xffffffffu, p, 1);
-    p += __shfl_xor_sync(0xffffffffu, p, 2);
-    const int base = half * 16;  // first lane of this half warp
-    float l0 = __shfl_sync(0xffffffffu, p, base + 0), l1 = __shfl_sync(0xffffffffu, p, base + 4);
-    float l2 = __shfl_sync(0xffffffffu, p, base + 8), l3 = __shfl_sync(0xffffffffu, p, base + 12);
-    if (q == 0 && valid) {
-      float4 o = make_float4(l0 + b.x, l1 + b.y, l2 + b.z, l3 + b.w);
-      if (sigmoid) {
-        o.x = 1.f / (1.f + expf(-o.x)); o.y = 1.f / (1.f + expf(-o.y));
-        o.z = 1.f / (1.f + expf(-o.z)); o.w = 1.f / (1.f + expf(-o.w));
+  constexpr int kU = 4;  // row pairs in flight per warp: one 128-bit load per thread and row is not enough to cover the
+                         // DRAM latency (one pair per iteration ran at 2.9 TB/s)
+  for (long long r0 = warp_id * 2; r0 < rows; r0 += nwarps * 2 * kU) {  // warp-uniform trip count
+    float4 z[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long r = r0 + u * nwarps * 2 + half;
+      z[u] = r < rows ? ldg4(Z2 + r * 64 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long r = r0 + u * nwarps * 2 + half;
+      if (r0 + u * nwarps * 2 >= rows) break;  // warp-uniform
+      const bool valid = r < rows;
+      const uint32_t keep = act.thr ? drop_keep4(act.seed, (uint64_t)(r * 16 + q), act.thr) : 0xfu;
+      bool pass;
+      float p = act_fwd(z[u].x, col[0], keep & 1u, act.keep_scale, pass) * w.x;
+      p = fmaf(act_fwd(z[u].y, col[1], keep & 2u, act.keep_scale, pass), w.y, p);
+      p = fmaf(act_fwd(z[u].z, col[2], keep & 4u, act.keep_scale, pass), w.z, p);
+      p = fmaf(act_fwd(z[u].w, col[3], keep & 8u, act.keep_scale, pass), w.w, p);
+      p += __shfl_xor_sync(0xffffffffu, p, 1);
+      p += __shfl_xor_sync(0xffffffffu, p, 2);
+      const int base = half * 16;  // first lane of this half warp
+      float l0 = __shfl_sync(0xffffffffu, p, base + 0), l1 = __shfl_sync(0xffffffffu, p, base + 4);
+      float l2 = __shfl_sync(0xffffffffu, p, base + 8), l3 = __shfl_sync(0xffffffffu, p, base + 12);
+      if (q == 0 && valid) {
+        float4 o = make_float4(l0 + b.x, l1 + b.y, l2 + b.z, l3 + b.w);
+        if (sigmoid) {
+          o.x = 1.f / (1.f + expf(-o.x)); o.y = 1.f / (1.f + expf(-o.y));
+          o.z = 1.f / (1.f + expf(-o.z)); o.w = 1.f / (1.f + expf(-o.w));
+        }
+        st4(out + r * 4, o);
       }
-      st4(out + r * 4, o);
     }
   }
 }
@@ -231,7 +245,7 @@ clf_tail_fwd_kernel(long long rows, const float* __restrict__ Z2, const Act act,
 // head), a2 = act2(z2), dA = pass ? dz W3 keep_scale : 0.  Nothing of rows x 64 is written.
 // Block = 16 column groups x 16 row lanes.  Partial layout: [64 dW3][4 db3][64 s1][64 s2].
 constexpr int kTailPart = 64 + 4 + 64 + 64;
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 clf_tail_bwd_kernel(long long rows, const float* __restrict__ Z2, const Act act, const float* __restrict__ W3,
                     const float* __restrict__ out, const float* __restrict__ dout, int sigmoid,
                     float* __restrict__ parts) {
@@ -246,26 +260,41 @@ clf_tail_bwd_kernel(long long rows, const float* __restrict__ Z2, const Act act,
   float sw[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, sb = 0.f;
   float tw[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f}, tb = 0.f;
   int run = 0;
-  for (long long r = (long long)blockIdx.x * 16 + ty; r < rows; r += (long long)gridDim.x * 16) {
-    float dz = __ldg(dout + r * 4 + k);
-    if (sigmoid) {
-      const float s = __ldg(out + r * 4 + k);
-      dz *= s * (1.f - s);
-    }
-    const float4 z4 = ldg4(Z2 + r * 64 + tx * 4);
-    const float z[4] = {z4.x, z4.y, z4.z, z4.w};
-    const uint32_t keep = act.thr ? drop_keep4(act.seed, (uint64_t)(r * 16 + tx), act.thr) : 0xfu;
+  constexpr int kU = 4;  // rows in flight per thread (memory-level parallelism: the loop is a dependent load -> math chain)
+  const long long rstep = (long long)gridDim.x * 16;
+  for (long long r0 = (long long)blockIdx.x * 16 + ty; r0 < rows; r0 += rstep * kU) {
+    float4 z4[kU];
+    float dzu[kU];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      bool pass;
-      const float a2 = act_fwd(z[e], col[e], (keep >> e) & 1u, act.keep_scale, pass);
-      const float dA = pass ? dz * w[e] * act.keep_scale : 0.f;
-      sw[e] = fmaf(dz, a2, sw[e]);
-      s1[e] += dA;
-      s2[e] = fmaf(dA, (z[e] - col[e].mean) * col[e].invstd, s2[e]);
+    for (int u = 0; u < kU; ++u) {
+      const long long r = r0 + u * rstep;
+      const bool ok = r < rows;
+      z4[u] = ok ? ldg4(Z2 + r * 64 + tx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dzu[u] = ok ? __ldg(dout + r * 4 + k) : 0.f;
+      if (sigmoid && ok) {
+        const float s = __ldg(out + r * 4 + k);
+        dzu[u] *= s * (1.f - s);
+      }
     }
-    sb += dz;
-    if (++run == 64) {  // bounded fp32 runs
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long r = r0 + u * rstep;
+      if (r >= rows) break;
+      const float dz = dzu[u];
+      const float z[4] = {z4[u].x, z4[u].y, z4[u].z, z4[u].w};
+      const uint32_t keep = act.thr ? drop_keep4(act.seed, (uint64_t)(r * 16 + tx), act.thr) : 0xfu;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        bool pass;
+        const float a2 = act_fwd(z[e], col[e], (keep >> e) & 1u, act.keep_scale, pass);
+        const float dA = pass ? dz * w[e] * act.keep_scale : 0.f;
+        sw[e] = fmaf(dz, a2, sw[e]);
+        s1[e] += dA;
+        s2[e] = fmaf(dA, (z[e] - col[e].mean) * col[e].invstd, s2[e]);
+      }
+      sb += dz;
+    }
+    if (++run == 16) {  // bounded fp32 runs (64 rows)
 #pragma unroll
       for (int e = 0; e < 4; ++e) { tw[e] += sw[e]; t1[e] += s1[e]; t2[e] += s2[e]; sw[e] = s1[e] = s2[e] = 0.f; }
       tb += sb;
@@ -299,6 +328,56 @@ clf_tail_bwd_kernel(long long rows, const float* __restrict__ Z2, const Act act,
   }
 }
 
+// dz2[r][c] = sc2[c] (dA - c1[c] - xhat c2[c]),  dA = pass2 ? dout[r][head] (* s (1 - s)) W3[c] keep_scale : 0: the
+// BatchNorm-2 backward applied to the masked layer-8 gradient, written once ([rows,64]) for clf_mid_act_bwd_kernel.
+__global__ void __launch_bounds__(256)
+clf_tail_dz2_kernel(long long rows, const float* __restrict__ Z2, const Act act, const float* __restrict__ W3,
+                    const float* __restrict__ out, const float* __restrict__ dout, int sigmoid,
+                    const float* __restrict__ coef, float* __restrict__ dZ2) {
+  const int tx = threadIdx.x & 15, k = tx >> 2;  // 256 % 16 == 0 and the stride is a multiple of 16: one column group per thread
+  const float4 w4 = ldg4(W3 + tx * 4);
+  const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+  Col col[4];
+  float c1[4], c2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    col[e] = load_col(act, tx * 4 + e);
+    c1[e] = __ldg(coef + tx * 4 + e);
+    c2[e] = __ldg(coef + 64 + tx * 4 + e);
+  }
+  const long long total = rows * 16, step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * step) {
+    const bool two = i + step < total;
+    const long long i2 = two ? i + step : i;
+    const float4 za = ldg4(Z2 + i * 4), zb = ldg4(Z2 + i2 * 4);
+    float da = __ldg(dout + (i >> 4) * 4 + k), db = __ldg(dout + (i2 >> 4) * 4 + k);
+    if (sigmoid) {
+      const float sa = __ldg(out + (i >> 4) * 4 + k), sb = __ldg(out + (i2 >> 4) * 4 + k);
+      da *= sa * (1.f - sa);
+      db *= sb * (1.f - sb);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const long long iu = u ? i2 : i;
+      const float4 z4 = u ? zb : za;
+      const float dz = u ? db : da;
+      const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+      float o[4];
+      const uint32_t keep = act.thr ? drop_keep4(act.seed, (uint64_t)iu, act.thr) : 0xfu;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float xc = z[e] - col[e].mean;
+        const float bn = fmaf(xc, col[e].sc, col[e].beta);
+        const bool pass = ((keep >> e) & 1u) && bn > 0.f;
+        const float dA = pass ? dz * w[e] * act.keep_scale : 0.f;
+        o[e] = col[e].sc * (dA - c1[e] - xc * col[e].invstd * c2[e]);
+      }
+      st4(dZ2 + iu * 4, make_float4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
 // Sums per-block float partials in double (fixed order): out_a[0..n_a), out_b[0..n_b) from the first n_a + n_b
 // entries; the next `cols` entries are BatchNorm sums s1 and the `cols` after them s2: dbeta = s1, dgamma = s2,
 // coef = (s1 / rows, s2 / rows) for a train-mode BatchNorm, zeros for an eval-mode one (dz = sc * dA).
@@ -327,32 +406,19 @@ __global__ void clf_parts_finalize_kernel(int nparts, int width, const float* __
 
 // ---- backward, layer 4 ---------------------------------------------------------------------------------------------
 // Per half row (heads 2h, 2h+1; a warp owns half rows, as classifier.cu's clf_mid_bwd_kernel):
-//   dz2[c]  = BN2-backward of dA2[c] = pass2 ? dout[head] W3[c] keep_scale : 0       (lane = column 32h + lane of Z2)
 //   a1[i]   = act1(z1)[i], mask pass1[i]                                             (lane = inputs 2c, 2c+1 of its head)
 //   dW2    += dz2 (x) a1,  db2 += dz2,  da1 = W2^T dz2,  g1 = pass1 ? da1 keep_scale : 0   (written, [rows,128])
 //   BN1 sums s1 += g1, s2 += g1 xhat1
-// The 32 dz2 values of the half row are formed by the 32 lanes (one column each), exchanged through the warp's
-// shared-memory slot (they overwrite the staged z2 values) and then read back as the 16 values of the lane's head.
-// Slot: [256 B z1 half row][128 B z2 half row][16 B dout row][16 B out row (sigmoid head only)].
+// Slot of the per-warp cp.async ring: [256 B z1 half row][128 B dz2 half row].
 constexpr int kMidDepth = 8;
-constexpr int kMidSlotBytes = 256 + 128 + 16 + 16;
+constexpr int kMidSlotBytes = 256 + 128;
 constexpr int kMidHalfPart = 1024 + 32 + 64 + 64;  // dW2 of 2 heads, db2 of 32 columns, s1 / s2 of 64 columns
 constexpr int kMidPart = 2 * kMidHalfPart;         // [2048 dW2][64 db2][128 s1][128 s2]
 static_assert((size_t)kMidGrid * kMidPart * sizeof(float) <= kWgradBytes, "clf_mid_act_bwd partials fit the workspace");
-struct MidBwd {
-  const float* Z1;
-  const float* Z2;
-  const float* out;    // sigmoid head only
-  const float* dout;
-  const float* W2;
-  const float* W3;
-  const float* coef2;  // [128]: c1[64], c2[64] of BatchNorm 2 (zeros for eval-mode statistics)
-  float* G1;
-  float* parts;
-  int sigmoid;
-};
 __global__ void __launch_bounds__(kMidBwdThreads, kMidBwdBlocks)
-clf_mid_act_bwd_kernel(long long rows, const MidBwd p, const Act act1, const Act act2) {
+clf_mid_act_bwd_kernel(long long rows, const float* __restrict__ Z1, const float* __restrict__ dZ2,
+                       const float* __restrict__ W2, const Act act1, float* __restrict__ G1,
+                       float* __restrict__ parts) {
   constexpr int kWarps = kMidBwdThreads / 32;
   constexpr int kRingFloats = kWarps * kMidDepth * kMidSlotBytes / 4, kRedFloats = kWarps * kMidHalfPart;
   __shared__ __align__(16) float smem[kRedFloats > kRingFloats ? kRedFloats : kRingFloats];  // rings, then the block reduction
@@ -361,19 +427,15 @@ clf_mid_act_bwd_kernel(long long rows, const MidBwd p, const Act act1, const Act
   P2 wq[8][2];  // wq[m][e] = (W2[head][2m][2c+e], W2[head][2m+1][2c+e])
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
-    const float2 w0 = __ldg(reinterpret_cast<const float2*>(p.W2 + (head * 16 + 2 * m) * 32 + 2 * c));
-    const float2 w1 = __ldg(reinterpret_cast<const float2*>(p.W2 + (head * 16 + 2 * m + 1) * 32 + 2 * c));
+    const float2 w0 = __ldg(reinterpret_cast<const float2*>(W2 + (head * 16 + 2 * m) * 32 + 2 * c));
+    const float2 w1 = __ldg(reinterpret_cast<const float2*>(W2 + (head * 16 + 2 * m + 1) * 32 + 2 * c));
     wq[m][0] = p2(w0.x, w1.x);
     wq[m][1] = p2(w0.y, w1.y);
   }
   P2 wacc[8][2];  // (dW2[head][2m][2c+e], dW2[head][2m+1][2c+e])
 #pragma unroll
   for (int m = 0; m < 8; ++m) wacc[m][0] = wacc[m][1] = p2(0.f, 0.f);
-  // this lane as the owner of column 32h + lane of Z2 / dz2
-  const int c2i = 32 * h + lane;
-  const Col col2 = load_col(act2, c2i);
-  const float w3 = __ldg(p.W3 + c2i), cf1 = __ldg(p.coef2 + c2i), cf2 = __ldg(p.coef2 + 64 + c2i);
-  // this lane as the owner of columns 64h + 2 lane, + 1 of Z1 / g1 (= inputs 2c, 2c+1 of its head)
+  // this lane owns columns 64h + 2 lane, + 1 of Z1 / g1 (= inputs 2c, 2c+1 of its head) and column 32h + lane of dz2 (db2)
   const int c1i = 64 * h + 2 * lane;
   const Col col1a = load_col(act1, c1i), col1b = load_col(act1, c1i + 1);
   float bacc = 0.f, s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;       // current fp32 runs
@@ -382,22 +444,12 @@ clf_mid_act_bwd_kernel(long long rows, const MidBwd p, const Act act1, const Act
   const long long wid = (long long)blockIdx.x * (kWarps / 2) + (warp >> 1), nw = (long long)gridDim.x * (kWarps / 2);
   float* ringf = smem + warp * (kMidDepth * kMidSlotBytes / 4);
   const uint32_t ring = (uint32_t)__cvta_generic_to_shared(ringf);
-  // lanes 0-15 copy z1, lanes 16-23 z2, lane 24 the dout row, lane 25 the out row; 16 bytes each
-  const float* src0;
-  long long src_stride;
-  uint32_t dst0;
-  bool copies;
-  if (lane < 16) {
-    src0 = p.Z1 + 64 * h + lane * 4, src_stride = 128, dst0 = ring + lane * 16, copies = true;
-  } else if (lane < 24) {
-    src0 = p.Z2 + 32 * h + (lane - 16) * 4, src_stride = 64, dst0 = ring + 256 + (lane - 16) * 16, copies = true;
-  } else if (lane == 24) {
-    src0 = p.dout, src_stride = 4, dst0 = ring + 384, copies = true;
-  } else {
-    src0 = p.out, src_stride = 4, dst0 = ring + 400, copies = lane == 25 && p.sigmoid;
-  }
+  // lanes 0-15 copy z1, lanes 16-23 dz2; 16 bytes each
+  const float* src0 = lane < 16 ? Z1 + 64 * h + lane * 4 : dZ2 + 32 * h + (lane - 16) * 4;
+  const long long src_stride = lane < 16 ? 128 : 64;
+  const uint32_t dst0 = ring + (lane < 16 ? lane * 16 : 256 + (lane - 16) * 16);
   auto issue = [&](long long r, int slot) {
-    if (r < rows && copies)
+    if (r < rows && lane < 24)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + slot * kMidSlotBytes), "l"(src0 + r * src_stride) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -407,36 +459,21 @@ clf_mid_act_bwd_kernel(long long rows, const MidBwd p, const Act act1, const Act
   for (long long r = wid; r < rows; r += nw) {
     asm volatile("cp.async.wait_group %0;" ::"n"(kMidDepth - 2) : "memory");
     __syncwarp();
-    float* row = ringf + slot * (kMidSlotBytes / 4);
-    // (1) dz2 of column 32h + lane
-    float dzo = row[96 + head];
-    if (p.sigmoid) {
-      const float s = row[100 + head];
-      dzo *= s * (1.f - s);
-    }
-    const float z2 = row[64 + lane];
-    const uint32_t keep2 = act2.thr ? drop_keep4(act2.seed, (uint64_t)(r * 16 + 8 * h + (lane >> 2)), act2.thr) : 0xfu;
-    const float xc2 = z2 - col2.mean;
-    const float bn2 = fmaf(xc2, col2.sc, col2.beta);
-    const bool pass2 = ((keep2 >> (lane & 3)) & 1u) && bn2 > 0.f;
-    const float dA2 = pass2 ? dzo * w3 * act2.keep_scale : 0.f;
-    const float dz2 = col2.sc * (dA2 - cf1 - xc2 * col2.invstd * cf2);
-    // (2) a1 of inputs 2c, 2c+1 (columns 64h + 2 lane, + 1 of Z1)
+    const float* row = ringf + slot * (kMidSlotBytes / 4);
     const float2 z1 = *reinterpret_cast<const float2*>(row + lane * 2);
-    const uint32_t keep1 = act1.thr ? drop_keep4(act1.seed, (uint64_t)(r * 32 + 16 * h + (lane >> 1)), act1.thr) : 0xfu;
-    bool pass1a, pass1b;
-    const float a1a = act_fwd(z1.x, col1a, (keep1 >> ((lane & 1) * 2)) & 1u, act1.keep_scale, pass1a);
-    const float a1b = act_fwd(z1.y, col1b, (keep1 >> ((lane & 1) * 2 + 1)) & 1u, act1.keep_scale, pass1b);
-    __syncwarp();            // every lane has read its z2 value and the dout / out rows
-    row[64 + lane] = dz2;    // exchange: the slot now holds the half row of dz2
-    __syncwarp();
     const float4 g0 = *reinterpret_cast<const float4*>(row + 64 + kk * 16),
                  g1 = *reinterpret_cast<const float4*>(row + 64 + kk * 16 + 4),
                  g2 = *reinterpret_cast<const float4*>(row + 64 + kk * 16 + 8),
                  g3 = *reinterpret_cast<const float4*>(row + 64 + kk * 16 + 12);
+    const float dz_own = row[64 + lane];
     __syncwarp();  // every lane has read the slot: refill it with the row kMidDepth - 1 ahead
     issue(r + (long long)(kMidDepth - 1) * nw, (slot + kMidDepth - 1) % kMidDepth);
     slot = (slot + 1) % kMidDepth;
+    // a1 of inputs 2c, 2c+1 (columns 64h + 2 lane, + 1 of Z1)
+    const uint32_t keep1 = act1.thr ? drop_keep4(act1.seed, (uint64_t)(r * 32 + 16 * h + (lane >> 1)), act1.thr) : 0xfu;
+    bool pass1a, pass1b;
+    const float a1a = act_fwd(z1.x, col1a, (keep1 >> ((lane & 1) * 2)) & 1u, act1.keep_scale, pass1a);
+    const float a1b = act_fwd(z1.y, col1b, (keep1 >> ((lane & 1) * 2 + 1)) & 1u, act1.keep_scale, pass1b);
     const P2 dz[8] = {p2(g0.x, g0.y), p2(g0.z, g0.w), p2(g1.x, g1.y), p2(g1.z, g1.w),
                       p2(g2.x, g2.y), p2(g2.z, g2.w), p2(g3.x, g3.y), p2(g3.z, g3.w)};
     const P2 a0 = p2(a1a, a1a), a1 = p2(a1b, a1b);
@@ -457,8 +494,8 @@ clf_mid_act_bwd_kernel(long long rows, const MidBwd p, const Act act1, const Act
     o1 = p2_add(o1, o3);
     const float ga = pass1a ? (p2_lo(o0) + p2_hi(o0)) * act1.keep_scale : 0.f;
     const float gb = pass1b ? (p2_lo(o1) + p2_hi(o1)) * act1.keep_scale : 0.f;
-    *reinterpret_cast<float2*>(p.G1 + r * 128 + c1i) = make_float2(ga, gb);
-    bacc += dz2;
+    *reinterpret_cast<float2*>(G1 + r * 128 + c1i) = make_float2(ga, gb);
+    bacc += dz_own;
     s1a += ga;
     s1b += gb;
     s2a = fmaf(ga, (z1.x - col1a.mean) * col1a.invstd, s2a);
@@ -483,7 +520,7 @@ clf_mid_act_bwd_kernel(long long rows, const MidBwd p, const Act act1, const Act
   *reinterpret_cast<float2*>(red + 1120 + 2 * lane) = make_float2(t2a + s2a, t2b + s2b);
   __syncthreads();
   // block partial, warps of a half combined in fixed order.  Layout: [2048 dW2][64 db2][128 s1][128 s2]
-  float* P = p.parts + (size_t)blockIdx.x * kMidPart;
+  float* P = parts + (size_t)blockIdx.x * kMidPart;
   for (int i = tid; i < 2 * kMidHalfPart; i += kMidBwdThreads) {
     const int hh = i / kMidHalfPart, q = i - hh * kMidHalfPart;
     float t = 0.f;
@@ -579,7 +616,8 @@ int eg_classifier_bwd(int64_t rows, const float* h, const eg_classifier_params* 
   float* coef2 = coef1 + 256;                                                                        // [128]
   {
     long long blocks = (rows + 15) / 16;
-    const int grid = (int)(blocks < kMaxParts ? blocks : kMaxParts);
+    const int cap = num_sms() * 2;  // __launch_bounds__(256, 2): one resident wave
+    const int grid = (int)(blocks < cap ? blocks : cap);
     ProfileScope prof("clf_tail_bwd", s);
     clf_tail_bwd_kernel<<<grid, 256, 0, s>>>(rows, z2, act2, p->w3, out, dout, p->sigmoid, parts);
     EG_LAUNCH_CHECK();
@@ -589,14 +627,21 @@ int eg_classifier_bwd(int64_t rows, const float* h, const eg_classifier_params* 
     EG_LAUNCH_CHECK();
   }
   {
+    float* dz2 = scratch + (size_t)rows * 128;  // scratch = [rows,128] g1 / dz1 followed by [rows,64] dz2
+    const long long groups = rows * 16;
+    long long blocks = (groups + 255) / 256;
+    const long long capb = (long long)num_sms() * 16;
+    const int grid_e = (int)(blocks < capb ? (blocks < 1 ? 1 : blocks) : capb);
+    {
+      ProfileScope prof("clf_tail_dz2", s);
+      clf_tail_dz2_kernel<<<grid_e, 256, 0, s>>>(rows, z2, act2, p->w3, out, dout, p->sigmoid, coef2, dz2);
+      EG_LAUNCH_CHECK();
+    }
     const long long want = (rows + 15) / 16;
     const int cap = num_sms() * kMidBwdBlocks;
     const int grid = (int)(want < cap ? want : cap);
-    MidBwd m;
-    m.Z1 = z1, m.Z2 = z2, m.out = out, m.dout = dout, m.W2 = p->w2, m.W3 = p->w3, m.coef2 = coef2, m.G1 = scratch;
-    m.parts = parts, m.sigmoid = p->sigmoid;
     ProfileScope prof("clf_mid_act_bwd", s);
-    clf_mid_act_bwd_kernel<<<grid, kMidBwdThreads, 0, s>>>(rows, m, act1, act2);
+    clf_mid_act_bwd_kernel<<<grid, kMidBwdThreads, 0, s>>>(rows, z1, dz2, p->w2, act1, scratch, parts);
     EG_LAUNCH_CHECK();
     clf_parts_finalize_kernel<<<(kMidPart + 127) / 128, 128, 0, s>>>(grid, kMidPart, parts, 2048, 64, 128, rows,
                                                                      p->batch_stats, g->dw2, g->db2, g->dg1, g->dbe1,

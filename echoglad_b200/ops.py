@@ -397,7 +397,7 @@ class ClassifierHeads(torch.autograd.Function):
         cp = ClassifierHeads._params(w1, b1, g1, be1, w2, b2, g2, be2, w3, b3, eps, p, seed, training, sigmoid)
         grads = [torch.empty_like(t) for t in (w1, b1, g1, be1, w2, b2, g2, be2, w3, b3)]
         cg = ClassifierGrads(*[t.data_ptr() for t in grads])
-        scratch = torch.empty(rows, F, device=dev)
+        scratch = torch.empty(rows * (F + 64), device=dev)  # [rows,128] g1 -> dz1, then [rows,64] dz2
         dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
         ws = _ws(dev)
         check(lib.eg_classifier_bwd(rows, h.data_ptr(), C.byref(cp), m1.data_ptr(), v1.data_ptr(), m2.data_ptr(),

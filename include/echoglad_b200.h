@@ -249,7 +249,8 @@ typedef struct eg_classifier_grads {  /* all required; same shapes as the parame
 int eg_classifier_fwd(int64_t rows, const float* h, const eg_classifier_params* p, float* mean1, float* var1,
                       float* mean2, float* var2, float* z1, float* z2, float* out, void* ws, size_t ws_bytes,
                       void* stream);
-/* Backward from dout float[rows,4].  scratch: float[rows,128] (overwritten: masked layer-1 gradient, then dz1);
+/* Backward from dout float[rows,4].  scratch: float[rows * 192] (overwritten: [rows,128] masked layer-1 gradient, then
+ * dz1 in place; followed by [rows,64] dz2);
  * dh (optional): float[rows,128] gradient with respect to h; `out` is read for the sigmoid head only. */
 int eg_classifier_bwd(int64_t rows, const float* h, const eg_classifier_params* p, const float* mean1,
                       const float* var1, const float* mean2, const float* var2, const float* z1, const float* z2,
