@@ -43,7 +43,7 @@ def workload_config(batch: int, world: int, cudnn_tf32: bool = False) -> dict:
                         "(embedder + UNet + GNN stack + classifiers + both losses, fwd+bwd, Adam)",
             "frame_size": 224, "num_aux_graphs": 7, "num_gnn_layers": 3, "batch_per_gpu": batch,
             "global_batch": batch * world, "nodes_per_step": batch * world * N_NODES,
-            "parallelism": f"dp{world} (frames sharded, flat-bucket NCCL grad all-reduce)",
+            "parallelism": f"dp{world} (frames sharded; flat gradient buffer, 3 groups all-reduced over NCCL from autograd hooks on a side stream)",
             "l2": "working set (2.36 GB per node tensor) >> 126 MB L2, no flush",
             "precision": "fp32 storage; 3xTF32 tensor-core transforms with fp32 accumulate; "
                          f"cuDNN TF32 {'on' if cudnn_tf32 else 'off'}"}
@@ -192,7 +192,12 @@ def run_native(args):
     torch.backends.cudnn.allow_tf32 = bool(args.cudnn_tf32)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
-    B = args.batch
+    if args.scaling == "strong":
+        if args.batch % world:
+            raise SystemExit(f"--scaling strong: global batch {args.batch} does not divide over {world} ranks")
+        B = args.batch // world   # the GLOBAL batch is fixed; every rank takes its shard of frames
+    else:
+        B = args.batch            # weak: --batch frames per GPU
 
     torch.manual_seed(200)
     embedder = eg.CNN(out_channels=[4], kernel_sizes=[3], pool_sizes=[1], cnn_dropout_p=0.1).to(dev)
@@ -201,40 +206,48 @@ def run_native(args):
                                              **LANDMARK_KW).to(dev)
     embedder.train(); landmark.train()
     params = list(embedder.parameters()) + list(landmark.parameters())
-    bucket = egdist.FlatGradBucket(params)
+    # gradient groups in backward order; with more than one rank each group's all-reduce is launched from autograd
+    # hooks on a side stream as soon as its gradients exist (overlaps the rest of the backward)
+    bucket = egdist.FlatGradBucket(params, groups=egdist.backward_order_groups(embedder, landmark))
     opt = torch.optim.Adam(params, lr=1e-3, weight_decay=1e-4, fused=True)
     bce = eg.WeightedBCEWithLogitsLoss(reduction='none', ones_weight=9000, loss_weight=1)
-    elm = eg.ExpectedLandmarkMSE(loss_weight=10, batch_size=B, frame_size=224, num_aux_graphs=7,
-                                 use_main_graph_only=False, num_output_channels=4)
     spec = landmark.graph_spec
     graph = eg.DeviceGraph.get(spec, dev)
     assert graph.meta.num_nodes == N_NODES
 
-    frames_h, coords_h = synthetic.host_batch(B, 224, seed=200 + rank)
-    frames_d, coords_d = frames_h.to(dev), coords_h.to(dev)
-    y_d, valid_d = synthetic.device_labels(coords_d, spec)
-    loss_h = torch.empty((), pin_memory=True)
+    def build_steps(B):
+        """(step_resident, step_e2e, frames_h, coords_h) for B frames per rank."""
+        elm = eg.ExpectedLandmarkMSE(loss_weight=10, batch_size=B, frame_size=224, num_aux_graphs=7,
+                                     use_main_graph_only=False, num_output_channels=4)
+        frames_h, coords_h = synthetic.host_batch(B, 224, seed=200 + rank)
+        frames_d, coords_d = frames_h.to(dev), coords_h.to(dev)
+        y_d, valid_d = synthetic.device_labels(coords_d, spec)
+        loss_h = torch.empty((), pin_memory=True)
 
-    def fwd_bwd(frames, y, valid):
-        bucket.zero()
-        logits, _ = landmark(x=embedder(frames))
-        pv, yv = logits.view(B, -1, 4), y.view(B, -1, 4)
-        loss = bce.compute(pv, yv, valid) + elm.compute(pv, yv, valid)
-        loss.backward()
-        bucket.all_reduce_mean()
-        opt.step()
-        return loss
+        def fwd_bwd(frames, y, valid):
+            bucket.zero()
+            logits, _ = landmark(x=embedder(frames))
+            pv, yv = logits.view(B, -1, 4), y.view(B, -1, 4)
+            loss = bce.compute(pv, yv, valid) + elm.compute(pv, yv, valid)
+            loss.backward()
+            bucket.all_reduce_mean()
+            opt.step()
+            return loss
 
-    def step_resident():
-        return fwd_bwd(frames_d, y_d, valid_d)
+        def step_resident():
+            return fwd_bwd(frames_d, y_d, valid_d)
 
-    def step_e2e():
-        frames_d.copy_(frames_h, non_blocking=True)
-        coords_d.copy_(coords_h, non_blocking=True)
-        y, valid = synthetic.device_labels(coords_d, spec)
-        loss = fwd_bwd(frames_d, y, valid)
-        loss_h.copy_(loss.detach(), non_blocking=False)  # D2H read of the step's result (synchronises)
-        return loss_h
+        def step_e2e():
+            frames_d.copy_(frames_h, non_blocking=True)
+            coords_d.copy_(coords_h, non_blocking=True)
+            y, valid = synthetic.device_labels(coords_d, spec)
+            loss = fwd_bwd(frames_d, y, valid)
+            loss_h.copy_(loss.detach(), non_blocking=False)  # D2H read of the step's result (synchronises)
+            return loss_h
+
+        return step_resident, step_e2e, frames_h, coords_h
+
+    step_resident, step_e2e, frames_h, coords_h = build_steps(B)
 
     def barrier():
         if world > 1:
@@ -296,6 +309,23 @@ def run_native(args):
         ms_tf32 = timed(step_resident, args.steps)
         torch.backends.cudnn.allow_tf32 = False
 
+    # second regime on more than one rank (informational, same JSON line): STRONG scaling of the same step, the global
+    # batch fixed at --batch and sharded over the ranks
+    strong = None
+    if world > 1 and args.scaling == "weak" and args.batch % world == 0 and not args.no_strong:
+        Bs = args.batch // world
+        s_res, _, _, _ = build_steps(Bs)
+        for _ in range(3):
+            s_res()
+        _lib.profile_enable(True)
+        ms_s = timed(s_res, args.steps)
+        prof_s = _lib.profile_report()
+        _lib.profile_enable(False)
+        strong = {"global_batch": args.batch, "batch_per_gpu": Bs, "ms_per_step": ms_s / args.steps,
+                  "frames_per_s": args.batch * args.steps / (ms_s / 1e3),
+                  "native_kernel_ms_per_step_rank0": sum(v[0] for v in prof_s.values()) / args.steps,
+                  "kernels_ms_per_step_rank0": {k: v[0] / args.steps for k, v in prof_s.items()}}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -334,7 +364,7 @@ def run_native(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(B, world, bool(args.cudnn_tf32)),
         "clocks": clocks,
@@ -351,6 +381,7 @@ def run_native(args):
                                            "algorithmic_bytes_per_launch": a_bwd, "launches_per_step": bwd_n / args.steps,
                                            "avg_launch_ms": (bwd_ms / bwd_n) if bwd_n else None}},
         "cpu_baseline": cpu_baseline,
+        "strong_scaling": strong,
         "kernels": kernels,
         "native_kernel_ms_per_step": native_ms,
         "alt": {"note": "informational: same step with cudnn.allow_tf32=True (PyTorch default) for the UNet/embedder convolutions",
@@ -367,7 +398,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=64, help="frames per GPU (weak scaling)")
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU (weak scaling) / global batch (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's scaling run): --batch frames per GPU; strong: --batch frames in "
+                         "total, sharded over the ranks.  A weak multi-rank run also reports the strong regime under "
+                         "`strong_scaling`")
+    ap.add_argument("--no-strong", action="store_true", help="skip the informational strong-scaling leg of a weak run")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cudnn-tf32", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

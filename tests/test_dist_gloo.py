@@ -23,7 +23,10 @@ def _worker(rank, world, port, out_dir):
     assert (r, w) == (rank, world)
     torch.manual_seed(0)  # identical replicas
     model = torch.nn.Sequential(torch.nn.Linear(16, 8), torch.nn.Tanh(), torch.nn.Linear(8, 1))
-    bucket = egdist.FlatGradBucket(model.parameters())
+    # two groups in backward order (last layer first): each is all-reduced from its post-accumulate hooks as soon as
+    # its gradients exist (overlap path), the rest in all_reduce_mean()
+    bucket = egdist.FlatGradBucket(model.parameters(), groups=[list(model[2].parameters()), list(model[0].parameters())])
+    assert bucket.overlap
     frames = torch.randn(8, 16, generator=torch.Generator().manual_seed(1))  # the global batch, same on all ranks
     mine = egdist.shard_range(frames.shape[0], r, w)
     bucket.zero()
@@ -32,6 +35,11 @@ def _worker(rank, world, port, out_dir):
     bucket.all_reduce_mean()
     for p, v in zip(bucket.params, bucket.views):  # after the exchange every .grad IS its view of the flat buffer
         assert p.grad.data_ptr() == v.data_ptr()
+    assert all(bucket._launched)
+    # uneven loss normalisers: rank r holds V_r = r + 1 valid entries; scaled per-rank losses average to the global one
+    v = torch.tensor(float(rank + 1))
+    scale = egdist.global_normaliser_scale(v)
+    assert abs(float(scale) - world * (rank + 1) / sum(range(1, world + 1))) < 1e-6
     torch.save({"flat": bucket.flat.clone(), "range": (mine.start, mine.stop)}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -47,7 +55,8 @@ def test_flat_bucket_allreduce_equals_global_batch_gradient(tmp_path):
     # equal shards => mean of per-rank mean-losses == global mean loss => same gradient as one rank on 8 frames
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(16, 8), torch.nn.Tanh(), torch.nn.Linear(8, 1))
-    bucket = egdist.FlatGradBucket(model.parameters())
+    bucket = egdist.FlatGradBucket(model.parameters(), groups=[list(model[2].parameters()), list(model[0].parameters())])
+    assert not bucket.overlap  # single process: no hooks, one gather at the end
     frames = torch.randn(8, 16, generator=torch.Generator().manual_seed(1))
     bucket.zero()
     model(frames).square().mean().backward()
