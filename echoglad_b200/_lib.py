@@ -34,6 +34,13 @@ class ClassifierParams(C.Structure):
                 ("sigmoid", C.c_int32)]
 
 
+class CoordMlpParams(C.Structure):
+    """eg_coord_mlp_params."""
+    _fields_ = [(n, C.c_void_p) for n in ("w1", "b1", "g1", "be1", "w2", "b2", "g2", "be2", "w3", "b3")] + \
+               [("eps", C.c_float), ("drop_p", C.c_float), ("seed", C.c_uint64), ("batch_stats", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class ClassifierGrads(C.Structure):
     """eg_classifier_grads."""
     _fields_ = [(n, C.c_void_p) for n in ("dw1", "db1", "dg1", "dbe1", "dw2", "db2", "dg2", "dbe2", "dw3", "db3")]
@@ -83,6 +90,12 @@ SIGNATURES = {
     "eg_classifier_fwd": (_I, [_L, _P, C.POINTER(ClassifierParams), _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "eg_classifier_bwd": (_I, [_L, _P, C.POINTER(ClassifierParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                C.POINTER(ClassifierGrads), _P, _SZ, _P]),
+    "eg_coord_sample_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "eg_coord_sample_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "eg_coord_update_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, C.POINTER(CoordMlpParams)] + [_P] * 10),
+    "eg_coord_update_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, C.POINTER(CoordMlpParams)] + [_P] * 9 +
+                            [_P, C.POINTER(ClassifierGrads), _P, _P]),
+    "eg_mae": (_I, [_L, _P, _P, _F, _P, _P, _P]),
     "eg_bce_multilevel": (_I, [_L, _P, _P, _P, _F, _F, _P, _P, _P, _SZ, _P]),
     "eg_expected_landmark_mse": (_I, [_I, _I, _I, C.POINTER(C.c_int32), _P, _P, _P, _F, _P, _P, _P, _SZ, _P]),
     "eg_node_labels": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int32), _P, _P, _P, _P]),

@@ -48,11 +48,12 @@ class ExpectedLandmarkMSE(object):
 
 class MAE(object):
     """CRITERIA['mae'] = the 'coordinate' loss of `use_coordinate_graph` (src/core/criterion.py:52-64,
-    src/builders/criterion_builder.py:40-41): loss_weight * mean |pred - y| over the [4B, 2] coordinates.  Eight
-    numbers per frame: plain torch on the device tensors (nothing to fuse)."""
+    src/builders/criterion_builder.py:40-41): loss_weight * mean |pred - y| over the [4B, 2] coordinates
+    (eg_mae: loss and gradient in one launch)."""
 
     def __init__(self, loss_weight=1):
         self.loss_weight = loss_weight
 
     def compute(self, pred_y, y):
-        return self.loss_weight * (pred_y - y.to(pred_y.dtype)).abs().mean()
+        with ops.device_of(pred_y):
+            return ops.MAELoss.apply(pred_y, y.to(pred_y.device), float(self.loss_weight))

@@ -80,8 +80,7 @@ int run(const eg_graph* g, int batch, float* const* maps, float* head, float* ta
     rows_copy_kernel<<<64, 256, 0, s>>>(batch, info.num_nodes, 0, info.first_pixel_node, F, head, X, to_nodes);
     EG_LAUNCH_CHECK();
   }
-  if (info.num_coord_nodes > 0) {
-    EG_CHECK_ARG(tail, "pack: graph has coordinate nodes but tail rows are NULL");
+  if (info.num_coord_nodes > 0 && tail) {  // tail == NULL: the caller fills them (eg_coord_sample_fwd) / has consumed them
     rows_copy_kernel<<<64, 256, 0, s>>>(batch, info.num_nodes, info.num_nodes - info.num_coord_nodes,
                                         info.num_coord_nodes, F, tail, X, to_nodes);
     EG_LAUNCH_CHECK();

@@ -70,23 +70,6 @@ def _update_running(bn: nn.BatchNorm1d, mean: torch.Tensor, var: torch.Tensor, n
 # landmark model
 # ---------------------------------------------------------------------------------------------------------
 
-class _GatherRows(torch.autograd.Function):
-    """rows[idx] for a handful of rows of a large [R, C] tensor.  Unlike torch.gather / index_select it saves only
-    the indices, so the source may be updated in place afterwards (the coordinate rows of the same tensor are,
-    src/core/models.py:473)."""
-
-    @staticmethod
-    def forward(ctx, rows, idx):
-        ctx.save_for_backward(idx)
-        ctx.shape = rows.shape
-        return rows.index_select(0, idx)
-
-    @staticmethod
-    def backward(ctx, g):
-        (idx,) = ctx.saved_tensors
-        return torch.zeros(ctx.shape, dtype=g.dtype, device=g.device).index_add_(0, idx, g), None
-
-
 class HierarchicalPatchModel(nn.Module):
     """Base landmark model: average-pooled pyramid of the embedder output as node features."""
 
@@ -177,34 +160,19 @@ class HierarchicalPatchModel(nn.Module):
         """[B, naux+1, 128]: the frame mean repeated (base variant, src/core/models.py:531-534)."""
         return maps[-1].mean(dim=(2, 3)).unsqueeze(1).repeat(1, self.num_aux_graphs + 1, 1)
 
-    def bilinear_rows(self, coords: torch.Tensor, rows: torch.Tensor, frame_stride: int, offset: int) -> torch.Tensor:
-        """`bilinear_interpolation` (src/core/models.py:539-553) on node-major features: coords [B,4,2] (h, w);
-        rows [R, C] holds the row-major main grid of frame b at rows [b*frame_stride + offset, + S*S) -> [B,4,C].
-        The reference multiplies a dense [4,S,S] tent-weight map into the [C,S,S] frame; the tent
-        `relu(1 - |c - g|)` is non-zero on at most two grid lines per axis, so only those 4 taps are gathered (same
-        weights, same sub-gradient at the kinks: they come from the same formula through autograd)."""
-        s = self.frame_size
-        b = coords.shape[0]
-        base = torch.floor(coords.detach()).clamp_(0, s - 1)                  # [B,4,2] first grid line per axis
-        lines = torch.stack((base, (base + 1).clamp_(max=s - 1)), dim=-1)      # [B,4,2(axis),2(tap)]
-        w = TF.relu(1 - (coords.unsqueeze(-1) - lines).abs())                   # tent weights of the taps
-        # when the second tap was clamped onto the first (coordinate exactly S-1) it duplicates it: drop it
-        w = w * torch.stack((torch.ones_like(base), (base + 1 <= s - 1).to(w.dtype)), dim=-1)
-        idx = (lines[:, :, 0, :, None] * s + lines[:, :, 1, None, :]).long().view(b, 16)    # [B, 4 landmarks x 4 taps]
-        idx = idx + (torch.arange(b, device=idx.device) * frame_stride + offset).unsqueeze(1)
-        taps = _GatherRows.apply(rows, idx.reshape(-1)).view(b, 4, 4, -1)
-        wt = (w[:, :, 0, :, None] * w[:, :, 1, None, :]).view(b, 4, 4, 1)
-        return (taps * wt).sum(dim=2)
-
     def create_node_pixels(self, x: torch.Tensor, graph: DeviceGraph, node_coords=None) -> torch.Tensor:
         maps = self.pyramid(x)
         head = self.connection_rows(maps) if graph.meta.first_pixel_node else None
-        tail = None
-        if self.use_coordinate_graph:  # coordinate nodes start as the interpolated main-level features (:526-527)
-            m = maps[-1]
-            s2 = m.shape[2] * m.shape[3]
-            tail = self.bilinear_rows(node_coords, m.permute(0, 2, 3, 1).reshape(-1, m.shape[1]), s2, 0)
-        return ops.PackNodes.apply(graph, head, tail, *maps)
+        feats = ops.PackNodes.apply(graph, head, None, *maps)
+        return self.sample_coordinate_rows(feats, graph, node_coords)
+
+    def sample_coordinate_rows(self, feats: torch.Tensor, graph: DeviceGraph, node_coords) -> torch.Tensor:
+        """Coordinate nodes start as the bilinear sample of the frame's main-level features at the initial
+        coordinates (src/core/models.py:526-527, 743-744): written into the packed tensor in place."""
+        if not self.use_coordinate_graph:
+            return feats
+        batch = feats.shape[0] // graph.meta.num_nodes
+        return ops.CoordSample.apply(feats, node_coords, graph, batch, self.frame_size)
 
     # -- forward ---------------------------------------------------------------------------------------------
     def forward(self, data_batch=None, x: torch.Tensor = None, node_coords: torch.Tensor = None,
@@ -273,20 +241,21 @@ class HierarchicalPatchModel(nn.Module):
         return (self.dropout_seed * 0x9E3779B1 + self._stream_id() + self._step * 1000003 + salt * 7919) & 0x7FFFFFFFFFFFFFFF
 
     def update_coordinates(self, i: int, y: torch.Tensor, coords: torch.Tensor, graph: DeviceGraph, batch: int):
-        """Coordinate update after GNN layer i (src/core/models.py:438-473): relative-position features + the
-        coordinate nodes' embeddings -> MLP -> delta; clamp; the coordinate nodes' embeddings are re-sampled from the
-        main-level rows of `y` at the new coordinates and written back in place (4 rows per frame)."""
-        meta = graph.meta
-        s = self.frame_size
-        yv = y.view(batch, meta.num_nodes, F)
-        c0 = meta.num_nodes - meta.num_coord_nodes
-        m0 = meta.first_pixel_node + meta.num_pixel_nodes - s * s
-        rel = -(coords.unsqueeze(2) - coords.unsqueeze(1)).reshape(batch * 4, 8)
-        delta = self.node_coordinate_mlp[i](torch.cat((yv[:, c0:, :].reshape(batch * 4, F), rel), dim=1))
-        coords = torch.clamp(coords + delta.view(batch, 4, 2), min=0, max=s - 1)
-        new = self.bilinear_rows(coords, y, meta.num_nodes, m0)
-        yv[:, c0:, :] = new
-        return y, coords
+        """Coordinate update after GNN layer i (src/core/models.py:438-473), one kernel (eg_coord_update_fwd):
+        relative-position features + the coordinate nodes' embeddings -> node_coordinate_mlp[i] -> delta; clamp; the
+        coordinate nodes' embeddings are re-sampled from the main-level rows of `y` at the new coordinates and
+        written back in place (4 rows per frame).  No host sync (the reference does three np.where per layer)."""
+        mlp = self.node_coordinate_mlp[i]
+        bn1, bn2 = mlp[1], mlp[5]
+        y, new, m1, v1, m2, v2 = ops.CoordUpdate.apply(
+            y, coords, graph, batch, self.frame_size, mlp[0].weight, mlp[0].bias, bn1.weight, bn1.bias,
+            bn1.running_mean, bn1.running_var, mlp[4].weight, mlp[4].bias, bn2.weight, bn2.bias, bn2.running_mean,
+            bn2.running_var, mlp[8].weight, mlp[8].bias, self.training, bn1.eps,
+            self.classifier_dropout_p if self.training else 0.0, self._seed(201 + 2 * i))
+        if self.training:
+            _update_running(bn1, m1, v1, 4 * batch)
+            _update_running(bn2, m2, v2, 4 * batch)
+        return y, new.view(batch, 4, 2)
 
     def gnn_stack(self, feats: torch.Tensor, graph: DeviceGraph, batch: int, coords: torch.Tensor = None):
         hidden = [feats]
@@ -454,10 +423,10 @@ class UNETHierarchicalPatchModel(HierarchicalPatchModel):
         return [TF.relu(self.linears[i](feats[i])) for i in used]
 
     def create_node_pixels(self, x: torch.Tensor, graph: DeviceGraph, node_coords=None) -> torch.Tensor:
-        """Fused route (default.yml: no connection / coordinate nodes): the narrow decoder maps of the big levels
+        """Fused route (no connection nodes): the narrow decoder maps of the big levels
         go straight into eg_level_embed (1x1 conv + ReLU + packing in one pass)."""
         meta = graph.meta
-        if meta.first_pixel_node or meta.num_coord_nodes or not self.fuse_level_embed:
+        if meta.first_pixel_node or not self.fuse_level_embed:
             return super().create_node_pixels(x, graph, node_coords)
         feats, used = self.decoder_features(x)
         fused, args = [], []
@@ -468,7 +437,7 @@ class UNETHierarchicalPatchModel(HierarchicalPatchModel):
                 args += [f, lin.weight, lin.bias]
             else:
                 args += [TF.relu(lin(f)), None, None]
-        return ops.EmbedPackNodes.apply(graph, tuple(fused), *args)
+        return self.sample_coordinate_rows(ops.EmbedPackNodes.apply(graph, tuple(fused), *args), graph, node_coords)
 
     def connection_rows(self, maps: List[torch.Tensor]) -> torch.Tensor:
         """One connection node per used level = its spatial mean (src/core/models.py:735-752)."""

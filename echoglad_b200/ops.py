@@ -460,3 +460,141 @@ class ExpectedLandmarkMSEFn(torch.autograd.Function):
     def backward(ctx, dloss):
         (grad,) = ctx.saved_tensors
         return (grad * dloss).view(ctx.shape), None, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# coordinate-graph branch (use_coordinate_graph): in-place Functions over the node tensor
+# ---------------------------------------------------------------------------------------------------------
+
+def _coord_geom(graph: DeviceGraph, frame_size: int):
+    """(nodes per frame, first coordinate row, first main-lattice row) inside a frame."""
+    meta = graph.meta
+    if meta.num_coord_nodes != 4:
+        raise EchogladError("the graph has no coordinate nodes (use_coordinate_graph=False)")
+    return (meta.num_nodes, meta.num_nodes - meta.num_coord_nodes,
+            meta.first_pixel_node + meta.num_pixel_nodes - frame_size * frame_size)
+
+
+def _own_grad(dy: torch.Tensor) -> torch.Tensor:
+    """The backward kernels rewrite the incoming gradient of the node tensor in place (4 + 16 rows per frame of a
+    multi-GB tensor).  COORD_INPLACE_GRAD = False clones it first (one extra pass; for callers that keep a
+    reference to that gradient, e.g. retain_grad() on the updated tensor)."""
+    dy = _f32(dy, "dy")
+    return dy if COORD_INPLACE_GRAD else dy.clone()
+
+
+COORD_INPLACE_GRAD = True
+
+
+class CoordSample(torch.autograd.Function):
+    """Initial coordinate-node features: rows of the 4 coordinate nodes = bilinear sample of the frame's main-level
+    rows at `coords` [4B,2] (src/core/models.py:526-527, 743-744, 539-553).  In place on x (eg_coord_sample_fwd)."""
+
+    @staticmethod
+    def forward(ctx, x, coords, graph: DeviceGraph, batch: int, frame_size: int):
+        x = _f32(x, "x")
+        coords = _f32(coords.reshape(-1, 2), "node_coords")
+        n, c0, m0 = _coord_geom(graph, frame_size)
+        if x.shape != (batch * n, F) or coords.shape[0] != 4 * batch:
+            raise EchogladError(f"CoordSample: x {tuple(x.shape)} / coords {tuple(coords.shape)} for batch {batch}")
+        check(lib.eg_coord_sample_fwd(x.data_ptr(), batch, n, c0, m0, frame_size, coords.data_ptr(), _stream(x)),
+              "eg_coord_sample_fwd")
+        ctx.mark_dirty(x)
+        ctx.save_for_backward(x, coords)
+        ctx.cfg = (batch, n, c0, m0, frame_size)
+        return x
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, coords = ctx.saved_tensors
+        batch, n, c0, m0, s = ctx.cfg
+        dy = _own_grad(dy)
+        dc = torch.empty_like(coords) if ctx.needs_input_grad[1] else None
+        check(lib.eg_coord_sample_bwd(dy.data_ptr(), x.data_ptr(), batch, n, c0, m0, s, coords.data_ptr(), _ptr(dc),
+                                      _stream(dy)), "eg_coord_sample_bwd")
+        return dy, dc, None, None, None
+
+
+class CoordUpdate(torch.autograd.Function):
+    """Coordinate update after a GNN layer (src/core/models.py:438-473) as one kernel per direction: relative
+    positions + coordinate-node embeddings -> node_coordinate_mlp[i] -> clamp -> re-sample -> coordinate rows of y
+    overwritten in place.  Returns (y, new coords [4B,2], mean1, var1, mean2, var2)."""
+
+    @staticmethod
+    def forward(ctx, y, coords, graph: DeviceGraph, batch: int, frame_size: int, w1, b1, g1, be1, m1_in, v1_in,
+                w2, b2, g2, be2, m2_in, v2_in, w3, b3, training: bool, eps: float, drop_p: float, seed: int):
+        from ._lib import CoordMlpParams
+        y = _f32(y, "y")
+        coords = _f32(coords.reshape(-1, 2), "node_coords")
+        n, c0, m0 = _coord_geom(graph, frame_size)
+        r, dev = 4 * batch, y.device
+        if y.shape != (batch * n, F) or coords.shape[0] != r:
+            raise EchogladError(f"CoordUpdate: y {tuple(y.shape)} / coords {tuple(coords.shape)} for batch {batch}")
+        prm = [_f32(t, "coordinate MLP parameter") for t in (w1, b1, g1, be1, w2, b2, g2, be2, w3, b3)]
+        if tuple(prm[0].shape) != (32, F + 8) or tuple(prm[4].shape) != (16, 32) or tuple(prm[8].shape) != (2, 16):
+            raise EchogladError("CoordUpdate: node_coordinate_mlp must be Linear(136,32) / (32,16) / (16,2) "
+                                "(classifier_hidden_dim == 32)")
+        p = float(drop_p) if training else 0.0
+        if training:
+            m1, v1, m2, v2 = (torch.empty(k, device=dev) for k in (32, 32, 16, 16))
+        else:
+            m1, v1, m2, v2 = (_f32(t, "running statistics") for t in (m1_in, v1_in, m2_in, v2_in))
+        feat_in = torch.empty(r, F, device=dev)
+        z1, z2 = torch.empty(r, 32, device=dev), torch.empty(r, 16, device=dev)
+        pre, out = torch.empty(r, 2, device=dev), torch.empty(r, 2, device=dev)
+        cp = CoordMlpParams(*[t.data_ptr() for t in prm], float(eps), p, int(seed), int(training), 0)
+        check(lib.eg_coord_update_fwd(y.data_ptr(), batch, n, c0, m0, frame_size, coords.data_ptr(), C.byref(cp),
+                                      m1.data_ptr(), v1.data_ptr(), m2.data_ptr(), v2.data_ptr(), feat_in.data_ptr(),
+                                      z1.data_ptr(), z2.data_ptr(), pre.data_ptr(), out.data_ptr(), _stream(y)),
+              "eg_coord_update_fwd")
+        ctx.mark_dirty(y)
+        ctx.mark_non_differentiable(m1, v1, m2, v2)
+        ctx.save_for_backward(y, coords, *prm, m1, v1, m2, v2, feat_in, z1, z2, pre, out)
+        ctx.cfg = (batch, n, c0, m0, frame_size, training, eps, p, seed)
+        return y, out, m1, v1, m2, v2
+
+    @staticmethod
+    def backward(ctx, dy, dcoords, *_):
+        from ._lib import ClassifierGrads, CoordMlpParams
+        y, coords, *rest = ctx.saved_tensors
+        prm, (m1, v1, m2, v2, feat_in, z1, z2, pre, out) = rest[:10], rest[10:]
+        batch, n, c0, m0, s, training, eps, p, seed = ctx.cfg
+        dy = _own_grad(dy)
+        dcoords = None if dcoords is None else _f32(dcoords.reshape(-1, 2), "dcoords")
+        dev = dy.device
+        grads = [torch.empty_like(t) for t in prm]
+        cg = ClassifierGrads(*[t.data_ptr() for t in grads])  # same ten pointers as eg_coord_mlp_grads
+        cp = CoordMlpParams(*[t.data_ptr() for t in prm], float(eps), p, int(seed), int(training), 0)
+        scratch = torch.empty(4 * batch * 64, device=dev)
+        dc_in = torch.empty_like(coords) if ctx.needs_input_grad[1] else None
+        check(lib.eg_coord_update_bwd(dy.data_ptr(), _ptr(dcoords), y.data_ptr(), batch, n, c0, m0, s,
+                                      coords.data_ptr(), C.byref(cp), m1.data_ptr(), v1.data_ptr(), m2.data_ptr(),
+                                      v2.data_ptr(), feat_in.data_ptr(), z1.data_ptr(), z2.data_ptr(), pre.data_ptr(),
+                                      out.data_ptr(), scratch.data_ptr(), C.byref(cg), _ptr(dc_in), _stream(dy)),
+              "eg_coord_update_bwd")
+        dw1, db1, dg1, dbe1, dw2, db2, dg2, dbe2, dw3, db3 = grads
+        return (dy, dc_in, None, None, None, dw1, db1, dg1, dbe1, None, None, dw2, db2, dg2, dbe2, None, None,
+                dw3, db3, None, None, None, None)
+
+
+class MAELoss(torch.autograd.Function):
+    """loss_weight * mean |pred - y|  (reference src/core/criterion.py:52-64), loss and gradient in one launch."""
+
+    @staticmethod
+    def forward(ctx, pred, y, loss_weight: float):
+        p = _f32(pred, "pred")
+        y = _f32(y.to(torch.float32), "y")
+        if p.numel() != y.numel() or p.numel() == 0:
+            raise EchogladError("MAE: pred / y element counts differ")
+        loss = torch.empty((), device=p.device)
+        grad = torch.empty_like(p) if pred.requires_grad else None
+        check(lib.eg_mae(p.numel(), p.data_ptr(), y.data_ptr(), float(loss_weight), loss.data_ptr(), _ptr(grad),
+                         _stream(p)), "eg_mae")
+        ctx.save_for_backward(grad)
+        ctx.shape = pred.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return (grad * dloss).view(ctx.shape), None, None

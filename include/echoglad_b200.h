@@ -103,8 +103,9 @@ int eg_graph_check_edge_index(const eg_graph* g, int batch, const int64_t* edge_
 /* ---- node-feature packing: replaces the per-frame permute/reshape/cat loop --------------------------
  * (src/core/models.py:722-756).  maps[l] = DEVICE float[batch, F, s_l, s_l] (NCHW) for lattice level l;
  * `maps` itself is a HOST array of num_levels pointers.  head = float[batch, first_pixel_node, F]
- * (connection-node rows) or NULL; tail = float[batch, num_coord_nodes, F] or NULL.  A NULL maps[l] skips
- * level l (its rows are written by eg_level_embed_fwd).
+ * (connection-node rows) or NULL; tail = float[batch, num_coord_nodes, F] or NULL (coordinate rows left to
+ * eg_coord_sample_fwd / already consumed by eg_coord_sample_bwd).  A NULL maps[l] skips level l (its rows are
+ * written by eg_level_embed_fwd).
  * X = float[batch*N, F] node-major.  The _grad form scatters dX back (d_maps etc. are outputs). */
 int eg_pack_nodes(const eg_graph* g, int batch, const float* const* maps, const float* head,
                   const float* tail, float* X, void* stream);
@@ -256,6 +257,65 @@ int eg_classifier_bwd(int64_t rows, const float* h, const eg_classifier_params* 
                       const float* var1, const float* mean2, const float* var2, const float* z1, const float* z2,
                       const float* out, const float* dout, float* scratch, float* dh,
                       const eg_classifier_grads* g, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- coordinate-graph branch (`use_coordinate_graph`; replaces the per-layer coordinate update of
+ * HierarchicalPatchModel.forward, src/core/models.py:438-473, `bilinear_interpolation`, :539-553, the initial
+ * coordinate-node features of create_node_pixels, :526-527 / :743-744, and their autograd) ---------------------------
+ * Geometry of the node tensor Y float[batch * nodes_per_frame, 128]: the 4 coordinate nodes of frame b are rows
+ * b*nodes_per_frame + coord_row0 + {0..3}; its row-major frame_size x frame_size main lattice starts at row
+ * b*nodes_per_frame + main_row0.  coords: float[4*batch, 2] = (h, w) per landmark, the layout of the reference's
+ * `node_coords`.  The bilinear map gathers the <= 4 taps whose tent weight relu(1 - |c - g|) is non-zero (the
+ * reference multiplies a dense [4,S,S] weight map into the frame: same weights, same sub-gradients).
+ *
+ * eg_coord_sample_fwd: Y[coordinate rows] = bilinear sample of the main rows at `coords` (in place).
+ * eg_coord_sample_bwd: turns dY (gradient of the tensor AFTER the sample) in place into the gradient of the tensor
+ *   before it: tap rows += weight * dY[coordinate row], coordinate rows = 0; dcoords (optional) float[4*batch,2]. */
+int eg_coord_sample_fwd(float* Y, int batch, int nodes_per_frame, int coord_row0, int main_row0, int frame_size,
+                        const float* coords, void* stream);
+int eg_coord_sample_bwd(float* dY, const float* Y, int batch, int nodes_per_frame, int coord_row0, int main_row0,
+                        int frame_size, const float* coords, float* dcoords, void* stream);
+
+/* node_coordinate_mlp[i] (src/core/models.py:337-350): Linear(136,32) BN ReLU Dropout Linear(32,16) BN ReLU Dropout
+ * Linear(16,2).  w1 float[32,136], w2 float[16,32], w3 float[2,16]; batch_stats / drop_p / seed as
+ * eg_classifier_params (dropout stream `seed` for layer 1, `seed + 1` for layer 2, element index row*width + col). */
+typedef struct eg_coord_mlp_params {
+  const float *w1, *b1, *g1, *be1;
+  const float *w2, *b2, *g2, *be2;
+  const float *w3, *b3;
+  float eps;
+  float drop_p;
+  uint64_t seed;
+  int32_t batch_stats;
+  int32_t reserved;
+} eg_coord_mlp_params;
+typedef struct eg_coord_mlp_grads { /* all required; same shapes as the parameters */
+  float *dw1, *db1, *dg1, *dbe1;
+  float *dw2, *db2, *dg2, *dbe2;
+  float *dw3, *db3;
+} eg_coord_mlp_grads;
+/* One coordinate update after a GNN layer, one kernel: relative-position features + coordinate-node embeddings ->
+ * MLP -> coords_out = clamp(coords_in + delta, 0, frame_size-1) -> the coordinate rows of Y are re-sampled at
+ * coords_out and overwritten IN PLACE.  mean1/var1 float[32], mean2/var2 float[16]: outputs when batch_stats != 0
+ * (train-mode BatchNorm), inputs (running statistics) otherwise.  Saved for the backward (all outputs): feat_in
+ * float[4*batch,128] (the coordinate rows before the overwrite), z1 float[4*batch,32], z2 float[4*batch,16]
+ * (pre-activations), pre float[4*batch,2] (coordinates before the clamp), coords_out float[4*batch,2]. */
+int eg_coord_update_fwd(float* Y, int batch, int nodes_per_frame, int coord_row0, int main_row0, int frame_size,
+                        const float* coords_in, const eg_coord_mlp_params* p, float* mean1, float* var1, float* mean2,
+                        float* var2, float* feat_in, float* z1, float* z2, float* pre, float* coords_out,
+                        void* stream);
+/* Backward: dY float[batch*nodes_per_frame,128] = gradient of the UPDATED tensor, turned in place into the gradient
+ * of the layer output (tap rows += weight * d(new row); coordinate rows = MLP input gradient); dcoords_out (optional)
+ * = gradient of coords_out; Y = the updated tensor (its main rows are read); scratch float[4*batch*64];
+ * dcoords_in (optional) float[4*batch,2]. */
+int eg_coord_update_bwd(float* dY, const float* dcoords_out, const float* Y, int batch, int nodes_per_frame,
+                        int coord_row0, int main_row0, int frame_size, const float* coords_in,
+                        const eg_coord_mlp_params* p, const float* mean1, const float* var1, const float* mean2,
+                        const float* var2, const float* feat_in, const float* z1, const float* z2, const float* pre,
+                        const float* coords_out, float* scratch, const eg_coord_mlp_grads* g, float* dcoords_in,
+                        void* stream);
+/* CRITERIA['mae'] = the 'coordinate' loss (src/core/criterion.py:52-64, src/builders/criterion_builder.py:40-41):
+ * loss[0] = loss_weight * mean |pred - y| over n values; grad (optional) float[n] = d loss / d pred. */
+int eg_mae(int64_t n, const float* pred, const float* y, float loss_weight, float* loss, float* grad, void* stream);
 
 /* ---- measurement hooks (no reference counterpart) ---------------------------------------------------
  * eg_profile_enable(1) clears and starts recording CUDA-event spans around every launch helper on the

@@ -367,15 +367,29 @@ def pack_nodes(cfg: Cfg, maps: List[Tensor], node_coords: Optional[Tensor] = Non
     return torch.cat(rows, dim=0)
 
 
-def coordinate_mlp(sd, cfg: Cfg, i: int, feats: Tensor, training: bool) -> Tensor:
+def coordinate_mlp(sd, cfg: Cfg, i: int, feats: Tensor, training: bool, masks=None) -> Tensor:
     """node_coordinate_mlp[i] (src/core/models.py:337-350): Linear(136,32)-BN-ReLU-Drop-Linear(32,16)-BN-ReLU-Drop-
-    Linear(16,2)."""
+    Linear(16,2).  masks (optional): externally supplied keep-masks `cmlp{i}a` [R,32] / `cmlp{i}b` [R,16]."""
     p = f"node_coordinate_mlp.{i}."
     z = F.linear(feats, sd[p + "0.weight"], sd[p + "0.bias"])
-    z = F.dropout(F.relu(_bn(sd, p + "1.", z, training)), cfg.classifier_dropout_p, training)
+    z = _drop(F.relu(_bn(sd, p + "1.", z, training)), cfg.classifier_dropout_p, training, masks, f"cmlp{i}a")
     z = F.linear(z, sd[p + "4.weight"], sd[p + "4.bias"])
-    z = F.dropout(F.relu(_bn(sd, p + "5.", z, training)), cfg.classifier_dropout_p, training)
+    z = _drop(F.relu(_bn(sd, p + "5.", z, training)), cfg.classifier_dropout_p, training, masks, f"cmlp{i}b")
     return F.linear(z, sd[p + "8.weight"], sd[p + "8.bias"])
+
+
+def coordinate_update(sd, cfg: Cfg, i: int, h: Tensor, coords: Tensor, coord_rows: Tensor, pixel_rows: Tensor,
+                      training: bool, masks=None):
+    """The coordinate update after GNN layer i (src/core/models.py:438-473): h [Nt,F], coords [B,4,2] ->
+    (h with the coordinate rows re-sampled, new coords)."""
+    B, S = coords.shape[0], cfg.frame_size
+    rel = -(coords.unsqueeze(2) - coords.unsqueeze(1))          # [B,4,4,2]: -(c_j - c_k) per frame (:441-444)
+    shape_feats = rel.reshape(B * 4, 8)
+    delta = coordinate_mlp(sd, cfg, i, torch.cat((h[coord_rows], shape_feats), dim=1), training, masks)
+    coords = torch.clamp(coords + delta.view(B, 4, 2), min=0, max=S - 1)
+    main = h[pixel_rows].view(B, -1, h.shape[1])[:, -S * S:, :].permute(0, 2, 1).reshape(B, -1, S, S)
+    new = torch.cat([bilinear_tent(coords[b], main[b]) for b in range(B)], dim=0)
+    return h.index_copy(0, coord_rows, new), coords
 
 
 def gnn_stack(sd, cfg: Cfg, feats: Tensor, edge_index: Tensor, training: bool, masks=None,
@@ -392,7 +406,6 @@ def gnn_stack(sd, cfg: Cfg, feats: Tensor, edge_index: Tensor, training: bool, m
         nt = torch.as_tensor(np.asarray(node_type))
         coord_rows = torch.nonzero(nt == 1).squeeze(1)
         pixel_rows = torch.nonzero(nt == 0).squeeze(1)
-        B, S = coords.shape[0], cfg.frame_size
     for i in range(L):
         p = f"gnn_layers.{i}."
         h = gcn_conv(hidden[i], edge_index, sd[p + "module_0.lin.weight"], sd[p + "module_0.bias"])
@@ -403,13 +416,7 @@ def gnn_stack(sd, cfg: Cfg, feats: Tensor, edge_index: Tensor, training: bool, m
         if cfg.residual and h.shape[1] == hidden[i].shape[1]:
             h = h + hidden[i]
         if cfg.use_coordinate_graph:
-            rel = -(coords.unsqueeze(2) - coords.unsqueeze(1))          # [B,4,4,2]: -(c_j - c_k) per frame (:441-444)
-            shape_feats = rel.reshape(B * 4, 8)
-            delta = coordinate_mlp(sd, cfg, i, torch.cat((h[coord_rows], shape_feats), dim=1), training)
-            coords = torch.clamp(coords + delta.view(B, 4, 2), min=0, max=S - 1)
-            main = h[pixel_rows].view(B, -1, h.shape[1])[:, -S * S:, :].permute(0, 2, 1).reshape(B, -1, S, S)
-            new = torch.cat([bilinear_tent(coords[b], main[b]) for b in range(B)], dim=0)
-            h = h.index_copy(0, coord_rows, new)
+            h, coords = coordinate_update(sd, cfg, i, h, coords, coord_rows, pixel_rows, training, masks)
         hidden.append(h)
     if cfg.gnn_jk_mode == "max":
         out = torch.stack(hidden, dim=-1).max(dim=-1)[0]

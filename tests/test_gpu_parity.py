@@ -762,6 +762,137 @@ def test_coordinate_graph_module_matches_reference_golden():
     assert not bad, bad
 
 
+def _coord_setup(frame, naux, batch, seed, p_drop):
+    cfg = R.Cfg(variant="avgpool", frame_size=frame, num_aux_graphs=naux, gnn_dropout_p=0.0,
+                classifier_dropout_p=p_drop, use_coordinate_graph=True)
+    sd = R.init_landmark_state(cfg, seed=seed)
+    g = eg.DeviceGraph.get(eg.HierGraphSpec(frame_size=frame, num_aux_graphs=naux, use_coordinate_graph=True), DEV)
+    nt = np.tile(R.build_edge_index(frame, naux, coord=True)[1], batch)
+    coord_rows = torch.nonzero(torch.as_tensor(nt) == 1).squeeze(1)
+    pixel_rows = torch.nonzero(torch.as_tensor(nt) == 0).squeeze(1)
+    gen = torch.Generator().manual_seed(seed + 1)
+    h = torch.randn(batch * g.meta.num_nodes, 128, generator=gen)
+    coords = torch.rand(batch, 4, 2, generator=gen) * (frame - 1)
+    coords[0, 1] = coords[0, 0]            # two landmarks on the same taps: the scatter must accumulate
+    coords[-1, 2] = torch.tensor([0.0, float(frame - 1)])  # on the lattice: the kinks of the tent
+    coords[0, 3] = torch.tensor([frame - 1.2, 0.2])        # next to two borders (the update test pushes it across)
+    return cfg, sd, g, coord_rows, pixel_rows, gen, h, coords
+
+
+@pytest.mark.parametrize("frame,naux,batch,p_drop,training", [
+    (12, 3, 2, 0.0, True), (28, 4, 5, 0.5, True), (16, 3, 3, 0.0, False), (224, 7, 2, 0.5, True)])
+def test_coordinate_update_entry_points_against_oracle(frame, naux, batch, p_drop, training):
+    """eg_coord_update_fwd / _bwd (relative positions + coordinate-node embeddings -> MLP -> clamp -> 4-tap re-sample,
+    coordinate rows rewritten in place) against the oracle's restatement of src/core/models.py:438-473 on the same
+    inputs, same dropout masks: new coordinates, the rewritten rows, BatchNorm statistics, and the gradients with
+    respect to the layer output, the incoming coordinates and all ten MLP parameters."""
+    i, seed = 1, 4321
+    cfg, sd, g, coord_rows, pixel_rows, gen, h, coords = _coord_setup(frame, naux, batch, 60 + batch, p_drop)
+    pfx = f"node_coordinate_mlp.{i}."
+    sd[pfx + "8.bias"] = torch.tensor([2.5, -2.5])  # pushes the landmarks near two borders through the clamp
+    names = ["0.weight", "0.bias", "1.weight", "1.bias", "4.weight", "4.bias", "5.weight", "5.bias", "8.weight", "8.bias"]
+    r = 4 * batch
+    w_h, w_c = torch.randn(h.shape, generator=gen), torch.randn(batch, 4, 2, generator=gen)
+
+    # device
+    prm = [sd[pfx + k].to(DEV).requires_grad_(True) for k in names]
+    stats = [sd[pfx + k].to(DEV).clone() for k in ("1.running_mean", "1.running_var", "5.running_mean", "5.running_var")]
+    h_leaf = h.to(DEV).requires_grad_(True)
+    c_leaf = coords.to(DEV).requires_grad_(True)
+    y, c_out, m1, v1, m2, v2 = ops.CoordUpdate.apply(
+        h_leaf * 1.0, c_leaf, g, batch, frame, prm[0], prm[1], prm[2], prm[3], stats[0], stats[1], prm[4], prm[5],
+        prm[6], prm[7], stats[2], stats[3], prm[8], prm[9], training, 1e-5, p_drop, seed)
+    ((y * w_h.to(DEV)).sum() + (c_out.view(batch, 4, 2) * w_c.to(DEV)).sum()).backward()
+
+    # oracle, same masks
+    masks = None
+    if training and p_drop > 0:
+        masks = {f"cmlp{i}a": ops.dropout_mask(r, 32, p_drop, seed, DEV).cpu(),
+                 f"cmlp{i}b": ops.dropout_mask(r, 16, p_drop, seed + 1, DEV).cpu()}
+        assert 0.3 < float((masks[f"cmlp{i}a"] > 0).float().mean()) < 0.7
+    osd = R.clone_state(sd, requires_grad=True)
+    ho, co = h.clone().requires_grad_(True), coords.clone().requires_grad_(True)
+    yo, c_o = R.coordinate_update(osd, cfg, i, ho, co, coord_rows, pixel_rows, training, masks)
+    ((yo * w_h).sum() + (c_o * w_c).sum()).backward()
+
+    clamped = int(((c_o.detach() == 0) | (c_o.detach() == frame - 1)).sum())
+    assert 0 < clamped < 2 * r, clamped  # both branches of the clamp are exercised
+    ok, worst = close(c_out.detach().cpu().view(batch, 4, 2), c_o.detach(), 1e-4, 1e-5)
+    assert ok, f"coords {worst}"
+    ok, worst = close(y.detach().cpu()[coord_rows], yo.detach()[coord_rows], 1e-4, 1e-5)
+    assert ok, f"re-sampled rows {worst}"
+    assert torch.equal(y.detach().cpu()[pixel_rows], h[pixel_rows])  # nothing else is touched
+    if training:
+        z1 = torch.nn.functional.linear(torch.cat((h[coord_rows], (-(coords.unsqueeze(2) - coords.unsqueeze(1))).reshape(r, 8)), 1),
+                                        sd[pfx + "0.weight"], sd[pfx + "0.bias"])
+        assert torch.allclose(m1.cpu(), z1.mean(0), rtol=1e-4, atol=1e-5)
+        assert torch.allclose(v1.cpu(), z1.var(0, unbiased=False), rtol=1e-4, atol=1e-6)
+    ok, worst = close(h_leaf.grad.cpu(), ho.grad, 1e-3, 1e-4)
+    assert ok, f"d layer output {worst}"
+    ok, worst = close(c_leaf.grad.cpu(), co.grad, 1e-3, 1e-4)
+    assert ok, f"d coords {worst}"
+    bad = grads_close({k: t.grad.cpu() for k, t in zip(names, prm)}, {k: osd[pfx + k].grad for k in names},
+                      rtol=1e-3, atol_frac=1e-4)
+    assert not bad, bad
+
+
+def test_coordinate_sample_and_mae_against_oracle():
+    """eg_coord_sample_fwd / _bwd (initial coordinate-node features, src/core/models.py:526-527) against the dense
+    tent-weight formula, incl. coordinates outside [0, S-1] (not clamped at this point of the reference), and eg_mae."""
+    frame, naux, batch = 20, 4, 3
+    cfg, sd, g, coord_rows, pixel_rows, gen, h, coords = _coord_setup(frame, naux, batch, 77, 0.0)
+    coords[1, 0] = torch.tensor([-0.4, frame - 0.3])  # outside the lattice
+    w_h = torch.randn(h.shape, generator=gen)
+    h_leaf, c_leaf = h.to(DEV).requires_grad_(True), coords.to(DEV).requires_grad_(True)
+    y = ops.CoordSample.apply(h_leaf * 1.0, c_leaf, g, batch, frame)
+    (y * w_h.to(DEV)).sum().backward()
+    ho, co = h.clone().requires_grad_(True), coords.clone().requires_grad_(True)
+    main = ho[pixel_rows].view(batch, -1, 128)[:, -frame * frame:, :].permute(0, 2, 1).reshape(batch, -1, frame, frame)
+    yo = ho.index_copy(0, coord_rows, torch.cat([R.bilinear_tent(co[b], main[b]) for b in range(batch)], dim=0))
+    (yo * w_h).sum().backward()
+    ok, worst = close(y.detach().cpu(), yo.detach(), 1e-4, 1e-5)
+    assert ok, f"sampled rows {worst}"
+    ok, worst = close(h_leaf.grad.cpu(), ho.grad, 1e-3, 1e-4)
+    assert ok, f"d features {worst}"
+    ok, worst = close(c_leaf.grad.cpu(), co.grad, 1e-3, 1e-4)
+    assert ok, f"d coords {worst}"
+
+    pred = (torch.rand(4 * batch, 2, generator=gen) * frame)
+    tgt = torch.randint(0, frame, (4 * batch, 2), generator=gen)
+    pred[0] = tgt[0].float()  # |0|: sub-gradient 0
+    pd = pred.to(DEV).requires_grad_(True)
+    got = eg.MAE(loss_weight=3.0).compute(pd, tgt.to(DEV))
+    got.backward()
+    po = pred.clone().requires_grad_(True)
+    want = R.mae_loss(po, tgt.float(), 3.0)
+    want.backward()
+    assert abs(got.item() - want.item()) <= 1e-6 * abs(want.item())
+    assert torch.allclose(pd.grad.cpu(), po.grad, rtol=1e-6, atol=0)
+
+
+def test_coordinate_branch_default_size_batch_runs_on_kernels_only():
+    """default.yml + use_coordinate_graph (BASELINE configs[0] variant C1'): one training step of the module at
+    224 px launches only library kernels for the coordinate branch (no eager fallback): the launch counter advances
+    by the 1 + 3 forward and 3 + 1 backward coordinate kernels on top of the plain model's launches."""
+    batch = 2
+    kw = dict(frame_size=224, gnn_dropout_p=0.5, classifier_dropout_p=0.5, node_embedding_dim=128, node_hidden_dim=128,
+              num_output_channels=4, num_gnn_layers=3, num_aux_graphs=7, gnn_jk_mode='last', classifier_hidden_dim=32,
+              residual=True, output_activation='logit')
+    x = torch.randn(batch, 128, 224, 224, device=DEV, requires_grad=True)
+    counts = {}
+    for flag in (False, True):
+        model = eg.HierarchicalPatchModel(use_coordinate_graph=flag, **kw).to(DEV).train()
+        coords = (torch.rand(4 * batch, 2, device=DEV) * 223) if flag else None
+        before = ops.lib.eg_launch_count()
+        logits, out = model(x=x, node_coords=coords)
+        loss = logits.sum() if not flag else logits.sum() + eg.MAE().compute(out, torch.zeros_like(out))
+        loss.backward()
+        torch.cuda.synchronize()
+        counts[flag] = ops.lib.eg_launch_count() - before
+        assert torch.isfinite(logits).all()
+    assert counts[True] - counts[False] == 1 + 3 + 3 + 1 + 1, counts  # sample, 3 updates, their backwards, MAE
+
+
 def test_unet_variant_with_coordinate_graph_against_oracle():
     """UNet variant + `use_coordinate_graph`: coordinate nodes start from the bilinear sample of the main-level
     decoder map (src/core/models.py:743-744).  Oracle on identical weights; the PyTorch pyramid runs on both sides,
