@@ -493,6 +493,7 @@ class CoordSample(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, coords, graph: DeviceGraph, batch: int, frame_size: int):
         x = _f32(x, "x")
+        ctx.coords_shape = coords.shape
         coords = _f32(coords.reshape(-1, 2), "node_coords")
         n, c0, m0 = _coord_geom(graph, frame_size)
         if x.shape != (batch * n, F) or coords.shape[0] != 4 * batch:
@@ -512,7 +513,7 @@ class CoordSample(torch.autograd.Function):
         dc = torch.empty_like(coords) if ctx.needs_input_grad[1] else None
         check(lib.eg_coord_sample_bwd(dy.data_ptr(), x.data_ptr(), batch, n, c0, m0, s, coords.data_ptr(), _ptr(dc),
                                       _stream(dy)), "eg_coord_sample_bwd")
-        return dy, dc, None, None, None
+        return dy, (None if dc is None else dc.view(ctx.coords_shape)), None, None, None
 
 
 class CoordUpdate(torch.autograd.Function):
@@ -525,6 +526,7 @@ class CoordUpdate(torch.autograd.Function):
                 w2, b2, g2, be2, m2_in, v2_in, w3, b3, training: bool, eps: float, drop_p: float, seed: int):
         from ._lib import CoordMlpParams
         y = _f32(y, "y")
+        ctx.coords_shape = coords.shape
         coords = _f32(coords.reshape(-1, 2), "node_coords")
         n, c0, m0 = _coord_geom(graph, frame_size)
         r, dev = 4 * batch, y.device
@@ -573,7 +575,7 @@ class CoordUpdate(torch.autograd.Function):
                                       out.data_ptr(), scratch.data_ptr(), C.byref(cg), _ptr(dc_in), _stream(dy)),
               "eg_coord_update_bwd")
         dw1, db1, dg1, dbe1, dw2, db2, dg2, dbe2, dw3, db3 = grads
-        return (dy, dc_in, None, None, None, dw1, db1, dg1, dbe1, None, None, dw2, db2, dg2, dbe2, None, None,
+        return (dy, None if dc_in is None else dc_in.view(ctx.coords_shape), None, None, None, dw1, db1, dg1, dbe1, None, None, dw2, db2, dg2, dbe2, None, None,
                 dw3, db3, None, None, None, None)
 
 
