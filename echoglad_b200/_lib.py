@@ -41,6 +41,12 @@ class CoordMlpParams(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class View(C.Structure):
+    """eg_view: element (r, c) = base[(r // frame_rows) * frame_stride + (r % frame_rows) * row_stride + c * col_stride]."""
+    _fields_ = [("base", C.c_void_p), ("frame_rows", C.c_int64), ("frame_stride", C.c_int64),
+                ("row_stride", C.c_int64), ("col_stride", C.c_int64)]
+
+
 class ClassifierGrads(C.Structure):
     """eg_classifier_grads."""
     _fields_ = [(n, C.c_void_p) for n in ("dw1", "db1", "dg1", "dbe1", "dw2", "db2", "dg2", "dbe2", "dw3", "db3")]
@@ -96,6 +102,9 @@ SIGNATURES = {
     "eg_coord_update_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, C.POINTER(CoordMlpParams)] + [_P] * 9 +
                             [_P, C.POINTER(ClassifierGrads), _P, _P]),
     "eg_mae": (_I, [_L, _P, _P, _F, _P, _P, _P]),
+    "eg_linear_fwd": (_I, [_L, _I, _I, C.POINTER(View), C.POINTER(View), _P, _I, _P, C.POINTER(View), _I,
+                           C.POINTER(View), _P]),
+    "eg_linear_wgrad": (_I, [_L, _I, _I, C.POINTER(View), C.POINTER(View), C.POINTER(View), _P, _P, _P, _SZ, _P]),
     "eg_bce_multilevel": (_I, [_L, _P, _P, _P, _F, _F, _P, _P, _P, _SZ, _P]),
     "eg_expected_landmark_mse": (_I, [_I, _I, _I, C.POINTER(C.c_int32), _P, _P, _P, _F, _P, _P, _P, _SZ, _P]),
     "eg_node_labels": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int32), _P, _P, _P, _P]),

@@ -1,6 +1,6 @@
 // Coordinate-graph branch (`use_coordinate_graph`): the per-layer coordinate update of
-// src/core/models.py:438-473 and `bilinear_interpolation` (:539-553) as ONE kernel per direction, and the `MAE`
-// coordinate criterion (src/core/criterion.py:52-64).
+// src/core/models.py:438-473 and `bilinear_interpolation` (:539-553) as three launches forward (gather the 4 rows
+// per frame, MLP, re-sample) and two backward, and the `MAE` coordinate criterion (src/core/criterion.py:52-64).
 //
 // After GNN layer i the reference (a) builds relative-position features of the 4 landmark coordinates of a frame,
 // (b) feeds [coordinate-node embedding (128) | relative positions (8)] through node_coordinate_mlp[i]
@@ -9,12 +9,14 @@
 // of the layer output with a tent-weight bilinear map and writes them back in place.  It does so with ~30 eager
 // ops, a dense [4,S,S] weight map per frame and three device->host syncs per layer (np.where on node_type).
 //
-// Here: R = 4*batch rows in total, so the whole update is one CTA (the train-mode BatchNorm statistics couple all
-// rows; a single CTA needs no grid barrier), 16 warps, a warp per row; the bilinear map is the 4 taps where the
-// tent `relu(1 - |c - g|)` is non-zero (same weights and sub-gradients as the dense formula).  The backward
-// kernel turns the gradient of the updated node tensor IN PLACE into the gradient of the layer output: the 4 tap
-// rows of each landmark receive `weight * d(new row)`, the coordinate rows receive the MLP's input gradient.
-// Everything is fixed-order (no atomics): bit-reproducible.
+// Here: R = 4*batch rows in total, so the MLP with its train-mode BatchNorm statistics (which couple all rows) is
+// one CTA (no grid barrier), 16 warps, a warp per row; the row gathers / scatters around it, whose cost is the
+// latency of cold rows of a multi-GB tensor, are multi-CTA launches with a warp per row / frame and all of a
+// landmark's row reads in flight at once (r02k: one CTA doing everything took 85 us forward / 310 us backward at
+// batch 64).  The bilinear map is the 4 taps where the tent `relu(1 - |c - g|)` is non-zero (same weights and
+// sub-gradients as the dense formula).  The backward turns the gradient of the updated node tensor IN PLACE into
+// the gradient of the layer output: the 4 tap rows of each landmark receive `weight * d(new row)`, the coordinate
+// rows receive the MLP's input gradient.  Everything is fixed-order (no atomics): bit-reproducible.
 #include "common.cuh"
 
 using namespace eg;
@@ -216,38 +218,45 @@ __device__ __forceinline__ void sample_bwd_frame(float* dY, const float* Y, int 
     tent(coords[2 * r], S, lh, wh, dh);
     tent(coords[2 * r + 1], S, lw, ww, dw);
     float gh = 0.f, gw = 0.f;
+    long long off[4];
+    float4 v[4], gacc[4];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int i = 0; i < 4; ++i) {  // the landmark's 4 + 4 row reads are independent: all in flight at once
+      off[i] = ((long long)lh[i >> 1] * S + lw[i & 1]) * EG_F + lane * 4;
+      v[i] = *reinterpret_cast<const float4*>(Ymain + off[i]);
+      gacc[i] = *reinterpret_cast<const float4*>(dmain + off[i]);
+    }
 #pragma unroll
-      for (int bb = 0; bb < 2; ++bb) {
-        const long long off = ((long long)lh[a] * S + lw[bb]) * EG_F + lane * 4;
-        const float4 v = *reinterpret_cast<const float4*>(Ymain + off);
-        const float dot = warp_sum(dn.x * v.x + dn.y * v.y + dn.z * v.z + dn.w * v.w);
-        gh = fmaf(dot, dh[a] * ww[bb], gh);
-        gw = fmaf(dot, wh[a] * dw[bb], gw);
-        const float w = wh[a] * ww[bb];
-        if (w != 0.f) {  // warp-uniform
-          float4 g = *reinterpret_cast<float4*>(dmain + off);
-          g.x = fmaf(w, dn.x, g.x);
-          g.y = fmaf(w, dn.y, g.y);
-          g.z = fmaf(w, dn.z, g.z);
-          g.w = fmaf(w, dn.w, g.w);
-          *reinterpret_cast<float4*>(dmain + off) = g;
-        }
+    for (int i = 0; i < 4; ++i) {
+      const int a = i >> 1, bb = i & 1;
+      const float dot = warp_sum(dn.x * v[i].x + dn.y * v[i].y + dn.z * v[i].z + dn.w * v[i].w);
+      gh = fmaf(dot, dh[a] * ww[bb], gh);
+      gw = fmaf(dot, wh[a] * dw[bb], gw);
+      const float w = wh[a] * ww[bb];
+      if (w != 0.f) {  // warp-uniform; taps with a non-zero weight are 4 different rows
+        float4 g = gacc[i];
+        g.x = fmaf(w, dn.x, g.x);
+        g.y = fmaf(w, dn.y, g.y);
+        g.z = fmaf(w, dn.z, g.z);
+        g.w = fmaf(w, dn.w, g.w);
+        *reinterpret_cast<float4*>(dmain + off[i]) = g;
       }
+    }
     dch[k] = gh;
     dcw[k] = gw;
     if (zero_rows) *reinterpret_cast<float4*>(drow) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
+// ZERO: the coordinate rows of dY are cleared (initial sample); otherwise they are left for the MLP backward
+template <bool ZERO>
 __global__ void __launch_bounds__(kThreads, 1) coord_sample_bwd_kernel(float* dY, const float* Y, int batch, int N,
                                                                          int c0, int m0, int S, const float* coords,
                                                                          float* dcoords) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int b = blockIdx.x * kWarps + warp; b < batch; b += gridDim.x * kWarps) {
     float dch[4], dcw[4];
-    sample_bwd_frame(dY, Y, b, N, c0, m0, S, coords, lane, dch, dcw, true);
+    sample_bwd_frame(dY, Y, b, N, c0, m0, S, coords, lane, dch, dcw, ZERO);
     if (dcoords && lane == 0) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -272,11 +281,13 @@ __global__ void __launch_bounds__(kThreads, 1) coord_update_fwd_kernel(const Arg
   load_weights(sm, p);
   __syncthreads();
   // ---- layer 1: z1 = [embedding | relative positions] W1^T + b1 -------------------------------------------------
+  float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (warp < R) nxt = *reinterpret_cast<const float4*>(a.feat_in + (long long)warp * EG_F + lane * 4);
   for (int r = warp; r < R; r += kWarps) {
-    const int b = r >> 2, k = r & 3;
-    const float4 v = *reinterpret_cast<const float4*>(a.Y + ((long long)b * a.N + a.c0 + k) * EG_F + lane * 4);
-    *reinterpret_cast<float4*>(a.feat_in + (long long)r * EG_F + lane * 4) = v;
-    *reinterpret_cast<float4*>(&sm.in[warp][lane * 4]) = v;
+    const int b = r >> 2;
+    *reinterpret_cast<float4*>(&sm.in[warp][lane * 4]) = nxt;
+    if (r + kWarps < R)  // next row of this warp: in flight during the 136-step dot products
+      nxt = *reinterpret_cast<const float4*>(a.feat_in + (long long)(r + kWarps) * EG_F + lane * 4);
     if (lane < 8) {  // -(c_k - c_j) for j = 0..3, (h, w)   (src/core/models.py:441-444)
       const int j = lane >> 1, d = lane & 1;
       sm.in[warp][EG_F + lane] = a.coords_in[2 * (4 * b + j) + d] - a.coords_in[2 * r + d];
@@ -301,9 +312,8 @@ __global__ void __launch_bounds__(kThreads, 1) coord_update_fwd_kernel(const Arg
   }
   __syncthreads();
   layer_stats<kH2>(sm, R, a.z2, a.mean2, a.var2, p.g2, p.be2, p.eps, p.batch_stats, sm.sc2, sm.sh2, sm.mu2, sm.inv2);
-  // ---- layer 3, clamp, re-sample ----------------------------------------------------------------------------------
+  // ---- layer 3, clamp (the re-sampling at coords_out is the next launch: coord_sample_fwd_kernel) ------------------
   for (int r = warp; r < R; r += kWarps) {
-    const int b = r >> 2, k = r & 3;
     float a2 = 0.f;
     if (lane < kH2) {
       const long long e = (long long)r * kH2 + lane;
@@ -320,13 +330,22 @@ __global__ void __launch_bounds__(kThreads, 1) coord_update_fwd_kernel(const Arg
       a.coords_out[2 * r] = ch;
       a.coords_out[2 * r + 1] = cw;
     }
-    const float* Ymain = a.Y + ((long long)b * a.N + a.m0) * EG_F;
-    const float4 v = sample_row(Ymain, a.S, ch, cw, lane);
-    *reinterpret_cast<float4*>(a.Y + ((long long)b * a.N + a.c0 + k) * EG_F + lane * 4) = v;
   }
 }
 
-// scratch layout (floats): ddelta [R,2] | g2 -> dz2 [R,16] | g1 -> dz1 [R,32] | drel [R,8]
+// feat_in[r] = Y[coordinate row r]: the MLP's inputs, kept for the backward (the rows are overwritten afterwards)
+__global__ void __launch_bounds__(kThreads) coord_gather_kernel(const float* Y, int batch, int N, int c0,
+                                                                float* feat_in) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = 4 * batch;
+  for (int r = blockIdx.x * kWarps + warp; r < R; r += gridDim.x * kWarps) {
+    const int b = r >> 2, k = r & 3;
+    *reinterpret_cast<float4*>(feat_in + (long long)r * EG_F + lane * 4) =
+        *reinterpret_cast<const float4*>(Y + ((long long)b * N + c0 + k) * EG_F + lane * 4);
+  }
+}
+
+// scratch layout (floats): ddelta [R,2] | g2 -> dz2 [R,16] | g1 -> dz1 [R,32] | drel [R,8] | dsample [R,2]
 __global__ void __launch_bounds__(kThreads, 1) coord_update_bwd_kernel(const BwdArgs q) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -340,6 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) coord_update_bwd_kernel(const Bwd
   float* dz2 = ddelta + (long long)R * 2;
   float* dz1 = dz2 + (long long)R * kH2;
   float* drel = dz1 + (long long)R * kH1;
+  const float* dsample = drel + (long long)R * 8;
   load_weights(sm, p);
   if (t < kH1) {
     bn_consts(a.mean1[t], a.var1[t], __ldg(p.g1 + t), __ldg(p.be1 + t), p.eps, sm.sc1[t], sm.sh1[t], sm.inv1[t]);
@@ -350,20 +370,12 @@ __global__ void __launch_bounds__(kThreads, 1) coord_update_bwd_kernel(const Bwd
     sm.mu2[t] = a.mean2[t];
   }
   __syncthreads();
-  // ---- re-sampling backward (tap rows of dY, d coords), clamp backward -> d delta -------------------------------
-  for (int b = warp; b < a.batch; b += kWarps) {
-    float dch[4], dcw[4];
-    sample_bwd_frame(q.dY, a.Y, b, a.N, a.c0, a.m0, a.S, a.coords_out, lane, dch, dcw, false);
-    if (lane < 8) {
-      const int k = lane >> 1, d = lane & 1, r = 4 * b + k;
-      float g = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        if (kk == k) g = d ? dcw[kk] : dch[kk];
-      if (q.dcoords_out) g += q.dcoords_out[2 * r + d];
-      const float pr = a.pre[2 * r + d];
-      ddelta[2 * r + d] = (pr >= 0.f && pr <= (float)(a.S - 1)) ? g : 0.f;  // torch.clamp passes the bounds
-    }
+  // ---- clamp backward -> d delta (the re-sampling backward ran as the previous launch: its d coords are in dsample) --
+  for (int i = t; i < R * 2; i += kThreads) {
+    float g = dsample[i];
+    if (q.dcoords_out) g += q.dcoords_out[i];
+    const float pr = a.pre[i];
+    ddelta[i] = (pr >= 0.f && pr <= (float)(a.S - 1)) ? g : 0.f;  // torch.clamp passes the bounds
   }
   __syncthreads();
   // ---- layer 3 backward: g2 = d a2 through Dropout / ReLU ------------------------------------------------------------
@@ -569,8 +581,8 @@ int eg_coord_sample_bwd(float* dY, const float* Y, int batch, int nodes_per_fram
   cudaStream_t s = as_stream(stream);
   ProfileScope prof("coord_sample_bwd", s);
   const int grid = (batch + kWarps - 1) / kWarps;
-  coord_sample_bwd_kernel<<<grid < 148 ? grid : 148, kThreads, 0, s>>>(dY, Y, batch, nodes_per_frame, coord_row0,
-                                                                      main_row0, frame_size, coords, dcoords);
+  coord_sample_bwd_kernel<true><<<grid < 148 ? grid : 148, kThreads, 0, s>>>(dY, Y, batch, nodes_per_frame, coord_row0,
+                                                                            main_row0, frame_size, coords, dcoords);
   EG_LAUNCH_CHECK();
   return EG_OK;
 }
@@ -589,7 +601,13 @@ int eg_coord_update_fwd(float* Y, int batch, int nodes_per_frame, int coord_row0
          feat_in, z1, z2, pre, coords_out};
   cudaStream_t s = as_stream(stream);
   ProfileScope prof("coord_update_fwd", s);
+  const int grid = (4 * batch + kWarps - 1) / kWarps;
+  coord_gather_kernel<<<grid < 148 ? grid : 148, kThreads, 0, s>>>(Y, batch, nodes_per_frame, coord_row0, feat_in);
+  EG_LAUNCH_CHECK();
   coord_update_fwd_kernel<<<1, kThreads, sizeof(Smem), s>>>(a);
+  EG_LAUNCH_CHECK();
+  coord_sample_fwd_kernel<<<grid < 148 ? grid : 148, kThreads, 0, s>>>(Y, batch, nodes_per_frame, coord_row0,
+                                                                      main_row0, frame_size, coords_out);
   EG_LAUNCH_CHECK();
   return EG_OK;
 }
@@ -620,6 +638,10 @@ int eg_coord_update_bwd(float* dY, const float* dcoords_out, const float* Y, int
   q.dcoords_in = dcoords_in;
   cudaStream_t s = as_stream(stream);
   ProfileScope prof("coord_update_bwd", s);
+  const int grid = (batch + kWarps - 1) / kWarps;
+  coord_sample_bwd_kernel<false><<<grid < 148 ? grid : 148, kThreads, 0, s>>>(
+      dY, Y, batch, nodes_per_frame, coord_row0, main_row0, frame_size, coords_out, scratch + (size_t)4 * batch * 58);
+  EG_LAUNCH_CHECK();
   coord_update_bwd_kernel<<<1, kThreads, sizeof(Smem), s>>>(q);
   EG_LAUNCH_CHECK();
   return EG_OK;

@@ -423,20 +423,17 @@ class UNETHierarchicalPatchModel(HierarchicalPatchModel):
         return [TF.relu(self.linears[i](feats[i])) for i in used]
 
     def create_node_pixels(self, x: torch.Tensor, graph: DeviceGraph, node_coords=None) -> torch.Tensor:
-        """Fused route (no connection nodes): the narrow decoder maps of the big levels
-        go straight into eg_level_embed (1x1 conv + ReLU + packing in one pass)."""
+        """Fused route (no connection nodes): the raw decoder maps of ALL levels go through 1x1 conv + ReLU + packing
+        in one pass per level (eg_level_embed for the two big levels, eg_linear_fwd for the small ones; SURVEY.md
+        §8(f) row 1); no [B,128,s,s] map is materialised."""
         meta = graph.meta
         if meta.first_pixel_node or not self.fuse_level_embed:
             return super().create_node_pixels(x, graph, node_coords)
         feats, used = self.decoder_features(x)
-        fused, args = [], []
-        for l, i in enumerate(used):
-            lin, f = self.linears[i], feats[i]
-            if ops.lib.eg_level_embed_supported(graph.handle, l, f.shape[1]):
-                fused.append(l)
-                args += [f, lin.weight, lin.bias]
-            else:
-                args += [TF.relu(lin(f)), None, None]
+        args = []
+        for i in used:  # every level: raw decoder map + its 1x1 conv (tensor-core-free kernels pick by cin)
+            args += [feats[i], self.linears[i].weight, self.linears[i].bias]
+        fused = range(len(used))
         return self.sample_coordinate_rows(ops.EmbedPackNodes.apply(graph, tuple(fused), *args), graph, node_coords)
 
     def connection_rows(self, maps: List[torch.Tensor]) -> torch.Tensor:

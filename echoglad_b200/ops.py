@@ -194,11 +194,47 @@ class PackNodes(torch.autograd.Function):
         return (None, d_head if need[1] else None, d_tail if need[2] else None, *d_maps)
 
 
+def _view_rows(t: torch.Tensor):
+    """eg_view of a contiguous row-major [rows, C] tensor."""
+    from ._lib import View
+    return View(t.data_ptr(), max(int(t.shape[0]), 1), 0, int(t.shape[1]), 1)
+
+
+def _view_level(x: torch.Tensor, graph: DeviceGraph, level: int):
+    """eg_view of lattice level `level` inside the node tensor x [B*N, F]."""
+    from ._lib import View
+    meta = graph.meta
+    f = int(x.shape[1])
+    s = meta.level_size[level]
+    return View(x.data_ptr() + meta.level_offset[level] * f * 4, s * s, meta.num_nodes * f, f, 1)
+
+
+def _view_nchw(m: torch.Tensor):
+    """eg_view of a contiguous NCHW map [B, C, s, s] seen as [B*s*s, C]."""
+    from ._lib import View
+    p = int(m.shape[2] * m.shape[3])
+    return View(m.data_ptr(), p, int(m.shape[1]) * p, 1, p)
+
+
+def linear_generic(rows, k, n, a, w, trans_w, y, bias=None, gate=None, addend=None, relu=False, stream=None):
+    """y = act(a_eff op(w) + bias + addend) over eg_views (see include/echoglad_b200.h: eg_linear_fwd)."""
+    ref = lambda v: None if v is None else C.byref(v)  # noqa: E731
+    check(lib.eg_linear_fwd(rows, k, n, C.byref(a), ref(gate), w.data_ptr(), int(trans_w), _ptr(bias), ref(addend),
+                            int(relu), C.byref(y), stream), "eg_linear_fwd")
+
+
+def linear_generic_wgrad(rows, k, n, g, a, dw, db, ws, gate=None, stream=None):
+    check(lib.eg_linear_wgrad(rows, k, n, C.byref(g), None if gate is None else C.byref(gate), C.byref(a),
+                              dw.data_ptr(), _ptr(db), ws.data_ptr(), WORKSPACE_BYTES, stream), "eg_linear_wgrad")
+
+
 class EmbedPackNodes(torch.autograd.Function):
     """Node features of the UNet variant: per lattice level `relu(conv1x1(feature map))` packed node-major
-    (reference src/core/models.py:708-710,722-756).  Levels whose raw map is narrow (cin 4 / 8: the main grid
-    and the 128x128 level, 92 % of the nodes) run the fused eg_level_embed kernels straight from the raw UNet
-    map; the remaining (tiny) levels arrive already embedded and go through eg_pack_nodes.
+    (reference src/core/models.py:708-710,722-756), no intermediate [B,128,s,s] map.  Levels whose raw map is narrow
+    (cin 4 / 8: the main grid and the 128x128 level, 92 % of the nodes) run the eg_level_embed kernels; the small
+    levels (cin 16..512) run the generic strided transform eg_linear_fwd straight from the NCHW map into the level's
+    node rows (backward: eg_linear_fwd with the ReLU gate for d_in, eg_linear_wgrad).  A level NOT listed in
+    fused_levels arrives already embedded ([B,128,s,s]) and goes through eg_pack_nodes.
 
     args: graph, fused_levels (tuple of level indices), then for every level l either
           (raw_map [B,cin,s,s], weight [128,cin,1,1], bias [128]) if l is fused, or (map [B,128,s,s], None, None)."""
@@ -222,20 +258,30 @@ class EmbedPackNodes(torch.autograd.Function):
             if tuple(maps[l].shape) != (batch, F, s_l, s_l):
                 raise EchogladError(f"level {l} map has shape {tuple(maps[l].shape)}, expected {(batch, F, s_l, s_l)}")
             plain.append(maps[l])
-        arr = (C.c_void_p * len(plain))(*[_ptr(m) for m in plain])
-        check(lib.eg_pack_nodes(graph.handle, batch, arr, None, None, x.data_ptr(), st), "eg_pack_nodes")
-        saved = []
+        if any(m is not None for m in plain) or meta.first_pixel_node:
+            arr = (C.c_void_p * len(plain))(*[_ptr(m) for m in plain])
+            check(lib.eg_pack_nodes(graph.handle, batch, arr, None, None, x.data_ptr(), st), "eg_pack_nodes")
+        saved, kinds = [], []
         for l in sorted(fused):
             w, b = _f32(args[3 * l + 1], "weight"), _f32(args[3 * l + 2], "bias")
-            cin = maps[l].shape[1]
-            if tuple(maps[l].shape) != (batch, cin, meta.level_size[l], meta.level_size[l]) or w.numel() != F * cin:
+            cin, s_l = maps[l].shape[1], meta.level_size[l]
+            if tuple(maps[l].shape) != (batch, cin, s_l, s_l) or w.numel() != F * cin:
                 raise EchogladError(f"level {l}: raw map {tuple(maps[l].shape)} / weight {tuple(w.shape)} mismatch")
-            check(lib.eg_level_embed_fwd(graph.handle, batch, l, cin, maps[l].data_ptr(), w.data_ptr(), b.data_ptr(),
-                                         x.data_ptr(), st), "eg_level_embed_fwd")
+            tc = bool(lib.eg_level_embed_supported(graph.handle, l, cin))
+            if tc:
+                check(lib.eg_level_embed_fwd(graph.handle, batch, l, cin, maps[l].data_ptr(), w.data_ptr(),
+                                             b.data_ptr(), x.data_ptr(), st), "eg_level_embed_fwd")
+            else:
+                linear_generic(batch * s_l * s_l, cin, F, _view_nchw(maps[l]), w, True, _view_level(x, graph, l),
+                               bias=b, relu=True, stream=st)
+            kinds.append(tc)
             saved += [maps[l], w, b]
         ctx.save_for_backward(*saved)
-        ctx.graph, ctx.batch, ctx.fused = graph, batch, sorted(fused)
+        ctx.graph, ctx.batch, ctx.fused, ctx.kinds = graph, batch, sorted(fused), kinds
         ctx.shapes = [m.shape for m in maps]
+        # the generic levels' ReLU mask is read from the output rows themselves.  Not through save_for_backward: the
+        # coordinate rows of x may be rewritten in place afterwards (CoordSample), which never touches a level's rows.
+        ctx.x_nodes = x.detach() if not all(kinds) else None
         return x
 
     @staticmethod
@@ -252,18 +298,26 @@ class EmbedPackNodes(torch.autograd.Function):
             else:
                 grads[3 * l] = torch.empty(ctx.shapes[l], device=dx.device)
                 d_plain.append(grads[3 * l])
-        arr = (C.c_void_p * len(d_plain))(*[_ptr(m) for m in d_plain])
-        check(lib.eg_pack_nodes_grad(ctx.graph.handle, ctx.batch, dx.data_ptr(), arr, None, None, st),
-              "eg_pack_nodes_grad")
+        if any(m is not None for m in d_plain):
+            arr = (C.c_void_p * len(d_plain))(*[_ptr(m) for m in d_plain])
+            check(lib.eg_pack_nodes_grad(ctx.graph.handle, ctx.batch, dx.data_ptr(), arr, None, None, st),
+                  "eg_pack_nodes_grad")
         ws = _ws(dx.device)
         for k, l in enumerate(ctx.fused):
             raw, w, b = ctx.saved_tensors[3 * k:3 * k + 3]
-            cin = raw.shape[1]
+            cin, s_l = raw.shape[1], meta.level_size[l]
             d_raw = torch.empty_like(raw) if need[2 + 3 * l] else None
             dw, db = torch.empty_like(w), torch.empty_like(b)
-            check(lib.eg_level_embed_bwd(ctx.graph.handle, ctx.batch, l, cin, raw.data_ptr(), w.data_ptr(),
-                                         b.data_ptr(), dx.data_ptr(), _ptr(d_raw), dw.data_ptr(), db.data_ptr(),
-                                         ws.data_ptr(), WORKSPACE_BYTES, st), "eg_level_embed_bwd")
+            if ctx.kinds[k]:
+                check(lib.eg_level_embed_bwd(ctx.graph.handle, ctx.batch, l, cin, raw.data_ptr(), w.data_ptr(),
+                                             b.data_ptr(), dx.data_ptr(), _ptr(d_raw), dw.data_ptr(), db.data_ptr(),
+                                             ws.data_ptr(), WORKSPACE_BYTES, st), "eg_level_embed_bwd")
+            else:
+                rows = ctx.batch * s_l * s_l
+                g, gate = _view_level(dx, ctx.graph, l), _view_level(ctx.x_nodes, ctx.graph, l)
+                if d_raw is not None:  # d_in = (dX masked by the ReLU) W, written straight into the NCHW layout
+                    linear_generic(rows, F, cin, g, w, False, _view_nchw(d_raw), gate=gate, stream=st)
+                linear_generic_wgrad(rows, cin, F, g, _view_nchw(raw), dw, db, ws, gate=gate, stream=st)
             grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = d_raw, dw, db
         return (None, None, *grads)
 

@@ -276,8 +276,9 @@ int eg_coord_sample_bwd(float* dY, const float* Y, int batch, int nodes_per_fram
                         int frame_size, const float* coords, float* dcoords, void* stream);
 
 /* node_coordinate_mlp[i] (src/core/models.py:337-350): Linear(136,32) BN ReLU Dropout Linear(32,16) BN ReLU Dropout
- * Linear(16,2).  w1 float[32,136], w2 float[16,32], w3 float[2,16]; batch_stats / drop_p / seed as
- * eg_classifier_params (dropout stream `seed` for layer 1, `seed + 1` for layer 2, element index row*width + col). */
+ * Linear(16,2).  w1 float[32,136], w2 float[16,32], w3 float[2,16]; batch_stats / drop_p / seed as in
+ * the classifier parameter block: dropout stream `seed` for layer 1, `seed + 1` for layer 2, element index
+ * row*width + col. */
 typedef struct eg_coord_mlp_params {
   const float *w1, *b1, *g1, *be1;
   const float *w2, *b2, *g2, *be2;
@@ -293,7 +294,7 @@ typedef struct eg_coord_mlp_grads { /* all required; same shapes as the paramete
   float *dw2, *db2, *dg2, *dbe2;
   float *dw3, *db3;
 } eg_coord_mlp_grads;
-/* One coordinate update after a GNN layer, one kernel: relative-position features + coordinate-node embeddings ->
+/* One coordinate update after a GNN layer (row gather, one-CTA MLP, re-sampling): relative-position features + coordinate-node embeddings ->
  * MLP -> coords_out = clamp(coords_in + delta, 0, frame_size-1) -> the coordinate rows of Y are re-sampled at
  * coords_out and overwritten IN PLACE.  mean1/var1 float[32], mean2/var2 float[16]: outputs when batch_stats != 0
  * (train-mode BatchNorm), inputs (running statistics) otherwise.  Saved for the backward (all outputs): feat_in
@@ -316,6 +317,27 @@ int eg_coord_update_bwd(float* dY, const float* dcoords_out, const float* Y, int
 /* CRITERIA['mae'] = the 'coordinate' loss (src/core/criterion.py:52-64, src/builders/criterion_builder.py:40-41):
  * loss[0] = loss_weight * mean |pred - y| over n values; grad (optional) float[n] = d loss / d pred. */
 int eg_mae(int64_t n, const float* pred, const float* y, float loss_weight, float* loss, float* grad, void* stream);
+
+/* ---- generic-width dense transforms over strided views (fp32 FMA; any width) -----------------------------------
+ * Element (r, c) of a view = base[(r / frame_rows) * frame_stride + (r % frame_rows) * row_stride + c * col_stride]
+ * (strides in elements): a row-major [rows, F] tensor is {p, rows, 0, F, 1}; lattice level l inside the node tensor
+ * is {X + off_l * F, s_l^2, N * F, F, 1}; an NCHW map [B, C, s, s] seen as [B * s^2, C] is {p, s^2, C * s^2, 1, s^2}.
+ * Replaces (a) `F.relu(self.linears[l](features[l]))` + that level's packing for the SMALL pyramid levels
+ * (src/core/models.py:708-710,728-741; the two big levels go through eg_level_embed_*), (b) nn.Linear / GCNConv.lin
+ * of models whose widths are not 128 / 32 (constructor defaults 64 / 16, src/core/models.py:290-296).
+ * eg_linear_fwd: y = act(a_eff op(w) + bias + addend); w = float[n, k] with trans_w != 0 (nn.Linear forward),
+ *   float[k, n] with trans_w == 0 (the input gradient of a Linear whose weight is [k, n]); a_eff = a where
+ *   gate > 0, else 0 (gate optional: the ReLU mask of a forward output); bias, addend optional; relu != 0: ReLU.
+ * eg_linear_wgrad: dw float[n, k] = g_eff^T a, db (optional) float[n] = column sums of g_eff; ws as everywhere. */
+typedef struct eg_view {
+  float* base;
+  int64_t frame_rows;
+  int64_t frame_stride, row_stride, col_stride;
+} eg_view;
+int eg_linear_fwd(int64_t rows, int k, int n, const eg_view* a, const eg_view* gate, const float* w, int trans_w,
+                  const float* bias, const eg_view* addend, int relu, const eg_view* y, void* stream);
+int eg_linear_wgrad(int64_t rows, int k, int n, const eg_view* g, const eg_view* gate, const eg_view* a, float* dw,
+                    float* db, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- measurement hooks (no reference counterpart) ---------------------------------------------------
  * eg_profile_enable(1) clears and starts recording CUDA-event spans around every launch helper on the

@@ -531,17 +531,17 @@ def test_level_embed_fused_matches_conv_relu_pack(frame, naux, batch):
     cfg = R.Cfg(frame_size=frame, num_aux_graphs=naux)
     gen = torch.Generator().manual_seed(frame)
     sizes = list(g.meta.level_size)
-    # narrow raw maps for the levels the fused kernel supports (cin 8 for the finest aux level that is a multiple
-    # of 64 positions, cin 4 for the main grid), ready 128-channel maps for the others
-    cins = [128] * len(sizes)
-    cins[-1] = 4
-    cins[-2] = 8
+    # raw decoder maps with the UNet's channel counts (..., 64, 32, 16 | 8 | 4): cin 4 / 8 on the two finest levels run
+    # the eg_level_embed kernels, the small levels the generic strided transform (eg_linear_fwd / _wgrad); level 0
+    # arrives as a ready 128-channel map and goes through eg_pack_nodes
+    cins = ([512, 256, 128, 64, 32, 16, 8, 4])[-len(sizes):]
+    cins[0] = 128
     raws = [torch.randn(batch, c, s, s, generator=gen) for c, s in zip(cins, sizes)]
-    ws = [torch.randn(128, c, 1, 1, generator=gen) * 0.5 for c in cins]
+    ws = [torch.randn(128, c, 1, 1, generator=gen) * (0.5 / (c / 4) ** 0.5) for c in cins]
     bs = [torch.randn(128, generator=gen) * 0.1 for _ in cins]
-    fused = [l for l, (c, s) in enumerate(zip(cins, sizes)) if c != 128 and
-             ops.lib.eg_level_embed_supported(g.handle, l, c)]
-    assert len(sizes) - 1 in fused and (frame != 224 or len(fused) == 2)
+    fused = list(range(1, len(sizes)))
+    tc = [l for l in fused if ops.lib.eg_level_embed_supported(g.handle, l, cins[l])]
+    assert len(sizes) - 1 in tc and (frame != 224 or len(tc) == 2) and len(tc) < len(fused)
 
     def leaf(t, dev):
         return t.to(dev).clone().requires_grad_(True)
@@ -873,7 +873,8 @@ def test_coordinate_sample_and_mae_against_oracle():
 def test_coordinate_branch_default_size_batch_runs_on_kernels_only():
     """default.yml + use_coordinate_graph (BASELINE configs[0] variant C1'): one training step of the module at
     224 px launches only library kernels for the coordinate branch (no eager fallback): the launch counter advances
-    by the 1 + 3 forward and 3 + 1 backward coordinate kernels on top of the plain model's launches."""
+    by the coordinate launches (initial sample 1, per layer 3 forward + 2 backward, sample backward 1, MAE 1) on top
+    of the plain model's launches."""
     batch = 2
     kw = dict(frame_size=224, gnn_dropout_p=0.5, classifier_dropout_p=0.5, node_embedding_dim=128, node_hidden_dim=128,
               num_output_channels=4, num_gnn_layers=3, num_aux_graphs=7, gnn_jk_mode='last', classifier_hidden_dim=32,
@@ -890,7 +891,7 @@ def test_coordinate_branch_default_size_batch_runs_on_kernels_only():
         torch.cuda.synchronize()
         counts[flag] = ops.lib.eg_launch_count() - before
         assert torch.isfinite(logits).all()
-    assert counts[True] - counts[False] == 1 + 3 + 3 + 1 + 1, counts  # sample, 3 updates, their backwards, MAE
+    assert counts[True] - counts[False] == 1 + 3 * 3 + 3 * 2 + 1 + 1, counts
 
 
 def test_unet_variant_with_coordinate_graph_against_oracle():
