@@ -577,6 +577,67 @@ def test_level_embed_fused_matches_conv_relu_pack(frame, naux, batch):
             assert ok, f"db[{l}] {worst}"
 
 
+@pytest.mark.parametrize("rows,k,n,layout", [(1000, 37, 50, "rows"), (3 * 49, 24, 130, "nchw_in"),
+                                             (5 * 64, 128, 16, "nchw_out"), (70001, 16, 128, "rows"),
+                                             (2 * 4096, 64, 64, "nchw_in")])
+def test_generic_strided_transforms_entry_points(rows, k, n, layout):
+    """eg_linear_fwd / eg_linear_wgrad over eg_view (generic widths, strided sources / destinations) against the
+    float64 evaluation of the same formula: y = relu((a masked by gate > 0) op(W) + bias + addend), dW = g_eff^T a,
+    db = column sums of g_eff.  Covers ragged tile edges (rows, k, n not multiples of 64 / 16), the NCHW source
+    (1x1 convolution read in place) and the NCHW destination (input gradient written in place)."""
+    gen = torch.Generator().manual_seed(rows + k)
+    st = torch.cuda.current_stream().cuda_stream
+    w = (torch.randn(n, k, generator=gen) * 0.2).to(DEV)
+    bias = torch.randn(n, generator=gen).to(DEV)
+    if layout == "nchw_in":
+        side = 7 if rows == 3 * 49 else 64
+        b = rows // (side * side)
+        a_map = torch.randn(b, k, side, side, generator=gen).to(DEV)
+        a_rows = a_map.permute(0, 2, 3, 1).reshape(rows, k)
+        a_view = ops._view_nchw(a_map)
+    else:
+        a_rows = torch.randn(rows, k, generator=gen).to(DEV)
+        a_view = ops._view_rows(a_rows)
+    gate = torch.randn(rows, k, generator=gen).to(DEV)
+    addend = torch.randn(rows, n, generator=gen).to(DEV)
+    for use_gate, use_add, relu, trans in [(False, False, True, True), (True, True, False, True), (True, False, False, False)]:
+        if use_gate and layout == "nchw_in":
+            continue
+        wt = w if trans else w.t().contiguous()
+        a_eff = a_rows.double() * ((gate > 0).double() if use_gate else 1.0)
+        want = a_eff @ w.double().t() + bias.double() + (addend.double() if use_add else 0.0)
+        if relu:
+            want = want.clamp_min(0)
+        if layout == "nchw_out" and not use_add:
+            side = 8
+            y_map = torch.full((rows // 64, n, side, side), float("nan"), device=DEV)
+            y_view = ops._view_nchw(y_map)
+        else:
+            y_map = None
+            y = torch.full((rows, n), float("nan"), device=DEV)
+            y_view = ops._view_rows(y)
+        ops.linear_generic(rows, k, n, a_view, wt, trans, y_view, bias=bias,
+                           gate=ops._view_rows(gate) if use_gate else None,
+                           addend=ops._view_rows(addend) if use_add else None, relu=relu, stream=st)
+        got = y_map.permute(0, 2, 3, 1).reshape(rows, n) if y_map is not None else y
+        ok, worst = close(got.cpu().double(), want.cpu(), 1e-5, 1e-6)
+        assert ok, f"y ({layout}, gate={use_gate}, add={use_add}, trans={trans}) {worst}"
+    # weight gradient: g [rows, n] masked by gate_g > 0, a [rows, k]
+    g = torch.randn(rows, n, generator=gen).to(DEV)
+    gate_g = torch.randn(rows, n, generator=gen).to(DEV)
+    ws = ops._ws(DEV)
+    for use_gate in (False, True):
+        dw = torch.full((n, k), float("nan"), device=DEV)
+        db = torch.full((n,), float("nan"), device=DEV)
+        ops.linear_generic_wgrad(rows, k, n, ops._view_rows(g), a_view, dw, db, ws,
+                                 gate=ops._view_rows(gate_g) if use_gate else None, stream=st)
+        g_eff = g.double() * ((gate_g > 0).double() if use_gate else 1.0)
+        ok, worst = close(dw.cpu().double(), (g_eff.t() @ a_rows.double()).cpu(), 1e-5, 1e-6)
+        assert ok, f"dW ({layout}, gate={use_gate}) {worst}"
+        ok, worst = close(db.cpu().double(), g_eff.sum(0).cpu(), 1e-5, 1e-6)
+        assert ok, f"db ({layout}, gate={use_gate}) {worst}"
+
+
 def test_unet_module_fused_embed_equals_unfused_route():
     """The drop-in module with the fused level embedding gives the same logits and parameter gradients as its own
     PyTorch conv1x1 + ReLU + eg_pack_nodes route (fuse_level_embed = False)."""
