@@ -88,6 +88,35 @@ struct TilePlan {
   const PlanRow* rows;  // [tiles][128]
 };
 
+// ---- patch plan of the fused kernel's TMA path (gcn_tc.cu, MODE = patch; built in graph.cu) -----------------
+// A regular 4-neighbour lattice level whose side is a multiple of 16 is cut into 8 x 16 patches (the tile table).
+// Per K chunk a patch tile stages, with one TMA box copy each,
+//   P: the haloed patch, [10][18] lattice positions x 128 B (out-of-lattice positions arrive as zeros),
+//   Q: the [4][8] parents of the patch (coarser level),
+//   C: (patches with children only) four sub-stages of [4][32] child positions = the children of two patch rows.
+// A compute half-warp owns a 2 x 2 block of the patch; its 4 x 6 lattice weights (up, left, right, down, parent, self;
+// 0 = no such edge) and 4 x 4 child weights are gcn_norm's dis[v] * dis[u], precomputed per block.
+constexpr int kPatchPRows = 10 * 18, kPatchQRows = 4 * 8, kPatchCRows = 4 * 32;
+struct alignas(16) PatchTile {  // 48 bytes
+  int32_t cls;              // 0 = patch, 1 = patch with children, 2 = CSR tile (rows summed from the device CSR)
+  int32_t level;            // lattice level of the patch
+  int32_t y0, x0;           // patch origin inside the level
+  int32_t qlevel, qy, qx;   // parents: level (-1 = none) and origin of the 4 x 8 box
+  int32_t clevel, cy, cx;   // children: level (-1 = none) and origin of the 16 x 32 box (may lie partly outside)
+  int32_t node0, side;      // frame-local node id of lattice position (0, 0) and side of the level
+};
+static_assert(sizeof(PatchTile) == 48, "PatchTile layout");
+struct alignas(16) PatchBlockW {  // 160 bytes
+  float wl[4][6];  // node (a, b, c, d) = ((0,0), (0,1), (1,0), (1,1)) of the block x (up, left, right, down, parent, self)
+  float wc[4][4];  // node x child (2 ny + i, 2 nx + j) -> [i * 2 + j]
+};
+static_assert(sizeof(PatchBlockW) == 160, "PatchBlockW layout");
+struct PatchPlan {
+  int ok;                      // 0: the graph has tiles this path cannot run (diagonal lattices, hubs): use the gather plan
+  const PatchTile* tiles;      // [tiles_per_frame]
+  const PatchBlockW* blocks;   // [tiles_per_frame][32]
+};
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ---- counter-based dropout RNG: one 64-bit mix per group of 4 consecutive elements -----------------

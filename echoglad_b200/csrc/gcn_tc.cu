@@ -39,6 +39,11 @@
 // A/B driver tools/gpu_ab.sh): EG_TC_TIMING adds per-role wait-cycle counters (eg_tc_debug_read, printed by
 // tools/kernel_bench.py); EG_DBG_NOGATHER / NOEMIT / NOFENCE / NOCOMPUTE / NOLOAD / NOMMA / NOSTORE / NOEPI /
 // SMALLOUT each remove one piece of work (WRONG results, timing only: the knock-out table of DESIGN.md 4.1).
+#include <cuda.h>  // CUtensorMap (the encode function is fetched through cudaGetDriverEntryPoint: no -lcuda)
+
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -52,6 +57,7 @@ const int32_t* graph_tile_nodes(const eg_graph* g);
 const int32_t* graph_tile_groups(const eg_graph* g);
 int graph_tiles_per_frame(const eg_graph* g);
 const TilePlan& graph_plan(const eg_graph* g);
+const PatchPlan& graph_patch_plan(const eg_graph* g);
 int launch_stats_finalize(int nparts, int cols, int stride, long long rows, const double* parts, float* mean,
                           float* var, cudaStream_t s);
 }  // namespace eg
@@ -76,7 +82,6 @@ using namespace eg::tc;
 namespace {
 
 constexpr int kStages = 3;                 // operand ring (hi + lo tiles)
-constexpr int kRawStages = 3;              // raw source-row ring
 constexpr int kProdWarps = 16;             // compute warps: 8 tile rows per warp and stage
 constexpr int kRowsPerProd = 128 / kProdWarps;
 constexpr int kEpiWarps = 4;
@@ -92,25 +97,43 @@ constexpr int kRegsCompute = 88, kRegsEpi = 72, kRegsLoad = 56;
 static_assert(4 * 32 * (kRegsEpi + kRegsLoad) + kProdWarps * 32 * kRegsCompute <= kThreads * 80, "register pool of the CTA");
 constexpr int kTileBytes = 128 * 128;      // one [128 rows x 32 tf32] operand tile
 constexpr uint32_t kABytes = kStages * 2 * kTileBytes;
-constexpr int kRawRows = kPlanSrc;         // 216 >= 128 (linear mode stages the tile's own rows)
-constexpr uint32_t kRawBytes = kRawRows * 128;
-constexpr uint32_t kPlanWarpBytes = kRowsPerProd * sizeof(PlanRow) + 16;  // a compute warp's 8 plan rows + tile header
-constexpr uint32_t kPlanBytes = kProdWarps * 2 * kPlanWarpBytes;           // double-buffered per warp
-constexpr uint32_t kSmemBytes = kABytes + kRawStages * kRawBytes + kPlanBytes + 256 /*barriers*/ + 1024 /*align*/;
-// shared-memory map, byte offsets from the 1024-byte aligned base
-constexpr uint32_t kOffRaw = kABytes;
-constexpr uint32_t kOffPlan = kOffRaw + kRawStages * kRawBytes;
-constexpr uint32_t kOffBars = kOffPlan + kPlanBytes;
-constexpr uint32_t kOffFull = kOffBars, kOffEmpty = kOffFull + 8 * kStages, kOffRawFull = kOffEmpty + 8 * kStages,
-                   kOffRawEmpty = kOffRawFull + 8 * kRawStages;
+// Kernel modes: plain per-node transform / gather plan (any graph: cp.async row copies, per-row slot plan) / patch plan
+// (regular lattices: TMA box copies, one 2 x 2 node block per half-warp; see PatchTile in common.cuh).
+constexpr int kLinear = 0, kGather = 1, kPatch = 2;
+template <int MODE>
+struct Lay {
+  static constexpr int kRawStages = MODE == kPatch ? 4 : 3;
+  // gather / linear: kPlanSrc staged rows (linear mode stages the tile's own 128 rows); patch: P + Q boxes (a C sub-stage
+  // of 128 child rows reuses the front of a slot)
+  static constexpr int kRawRows = MODE == kPatch ? kPatchPRows + kPatchQRows : kPlanSrc;
+  static constexpr uint32_t kRawBytes = kRawRows * 128;
+  // per compute warp and tile: gather: 8 plan rows + tile header; patch: its two blocks' weights + the tile descriptor
+  static constexpr uint32_t kPlanWarpBytes =
+      MODE == kPatch ? 2 * sizeof(PatchBlockW) + sizeof(PatchTile) : kRowsPerProd * sizeof(PlanRow) + 16;
+  static constexpr uint32_t kPlanBytes = kProdWarps * 2 * kPlanWarpBytes;  // double-buffered per warp
+  static constexpr uint32_t kSmemBytes = kABytes + kRawStages * kRawBytes + kPlanBytes + 256 /*barriers*/ + 1024 /*align*/;
+  // shared-memory map, byte offsets from the 1024-byte aligned base
+  static constexpr uint32_t kOffRaw = kABytes;
+  static constexpr uint32_t kOffPlan = kOffRaw + kRawStages * kRawBytes;
+  static constexpr uint32_t kOffBars = kOffPlan + kPlanBytes;
+  static constexpr uint32_t kOffFull = kOffBars, kOffEmpty = kOffFull + 8 * kStages, kOffRawFull = kOffEmpty + 8 * kStages,
+                            kOffRawEmpty = kOffRawFull + 8 * kRawStages;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory of one CTA");
+};
+static_assert(kPatchCRows * 128 <= Lay<kPatch>::kRawBytes && kPatchPRows * 128 % 128 == 0, "patch slot layout");
 constexpr int kTmemCols = 512;             // [0,128) W hi, [128,256) W lo, [256,384) / [384,512) accumulators
 constexpr uint32_t kTmemAcc = 256;
 static_assert(kPlanSrc % (kLoadWarps * 4) == 0 && kPlanSrc >= 128, "loader mapping");
 
+struct PatchMaps {  // tensor maps of the node tensor, per lattice level: [3 l + 0 / 1 / 2] = P / Q / C box (see PatchTile)
+  CUtensorMap m[3 * EG_MAX_LEVELS];
+};
+
 struct TcParams {
   const int32_t* tile_nodes;   // GATHER: [tiles_per_frame][128]
   const int32_t* tile_groups;  // GATHER: [tiles_per_frame][16] first node / rows of each 16-row group
-  TilePlan plan;               // GATHER: per-tile staged sources and per-row edges
+  TilePlan plan;               // gather mode: per-tile staged sources and per-row edges
+  PatchPlan patch;             // patch mode: tile descriptors and per-block weights
   int tiles_per_frame;
   int nodes_per_frame;
   int num_tiles;              // < 2^31 / 128 (rows < 2^31, checked by the launchers)
@@ -168,6 +191,25 @@ __device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
   return r;
 }
 
+// acc += w * x on a packed pair (FFMA2 with the scalar weight broadcast)
+__device__ __forceinline__ void fma2(F2& acc, float w, F2 x) {
+  const unsigned long long w2 = ((unsigned long long)__float_as_uint(w) << 32) | __float_as_uint(w);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.u) : "l"(w2), "l"(x.u));
+}
+__device__ __forceinline__ F2 lds_f2(uint32_t addr) {
+  F2 v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v.u) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts2(uint32_t addr, uint2 v) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ F2 ldg_f2(const float* p) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return f2_pack(v.x, v.y);
+}
+__device__ __forceinline__ void st_f2(float* p, F2 v) { *reinterpret_cast<float2*>(p) = make_float2(f2_lo(v), f2_hi(v)); }
+
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
   acc.x = fmaf(w, x.x, acc.x);
   acc.y = fmaf(w, x.y, acc.y);
@@ -195,8 +237,15 @@ __device__ __forceinline__ void fma4_x2(float4& acc, float w, const float4& x) {
 // the 203 KB of shared memory (ld.global.cg; measured -1 % against ld.global.nc, L1::no_allocate +4 %).
 __device__ __forceinline__ float4 ld_far(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
-template <bool GATHER>
-__global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
+template <int MODE>
+__device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) {
+  constexpr bool GATHER = MODE != kLinear;
+  using L = Lay<MODE>;
+  constexpr int kRawStages = L::kRawStages, kRawRows = L::kRawRows;
+  constexpr uint32_t kRawBytes = L::kRawBytes, kPlanWarpBytes = L::kPlanWarpBytes, kPlanBytes = L::kPlanBytes;
+  constexpr uint32_t kOffRaw = L::kOffRaw, kOffPlan = L::kOffPlan, kOffFull = L::kOffFull, kOffEmpty = L::kOffEmpty,
+                     kOffRawFull = L::kOffRawFull, kOffRawEmpty = L::kOffRawEmpty;
+  (void)kRawRows, (void)kOffPlan, (void)kPlanWarpBytes, (void)pm;
 #ifdef EG_TC_TIMING
   long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long dbg_n = 0;
@@ -236,7 +285,8 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < kRawStages; ++s) {
-      mbar_init(&raw_full[s], kLoadWarps * 32);  // one cp.async.mbarrier.arrive.noinc per loader thread
+      // gather / linear: one cp.async.mbarrier.arrive.noinc per loader thread; patch: the producer's expect_tx arrival
+      mbar_init(&raw_full[s], MODE == kPatch ? 1 : kLoadWarps * 32);
       mbar_init(&raw_empty[s], kProdWarps);
     }
     for (int b = 0; b < 2; ++b) {
@@ -267,6 +317,17 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
       tmem_st32(ta + 128, lo);
     }
     tmem_st_wait();
+  }
+  if constexpr (MODE == kPatch) {
+    // The parent region of a slot is only written by tiles that have parents; its weights are zero otherwise, but
+    // 0 x (uninitialised shared memory) may be NaN: start from zeros (from then on it holds zeros or finite rows).
+    if (warp >= kProdWarp0) {
+      for (int i = tid - kProdWarp0 * 32; i < kRawStages * kPatchQRows * 8; i += kProdWarps * 32) {
+        const int slot = i / (kPatchQRows * 8), o = i % (kPatchQRows * 8);
+        sts4(sm + kOffRaw + slot * kRawBytes + kPatchPRows * 128 + o * 16, make_uint4(0, 0, 0, 0));
+      }
+      fence_proxy_async_smem();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -362,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
       sts4(a_hi + kTileBytes + soff[i], lo);
     };
 
-    if (!GATHER) {
+    if constexpr (MODE == kLinear) {
       // linear mode: raw slot r = tile row r (rows past the end were not copied: zero them)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < 4; ++kc) {
@@ -378,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
           release();
         }
       }
-    } else {
+    } else if constexpr (MODE == kGather) {
       const bool agg_out = p.AggOut != nullptr;
       uint32_t pbuf = 0;
       prefetch_plan(blockIdx.x, 0);
@@ -555,6 +616,260 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
           if (agg_out) {
 #pragma unroll
             for (int i = 0; i < kIters; ++i) store_agg(i, coff, aggv[i]);
+          }
+        }
+      }
+    } else {
+      // ===== patch mode: a half-warp owns a 2 x 2 node block of the 8 x 16 patch, a lane 2 of the chunk's 32 features.
+      // Per chunk: 12 haloed-patch rows + 1 parent row (13 LDS.64, immediate offsets from one base) feed the four sums
+      // (24 FFMA2); patches with children add 16 child rows when the sub-stage of their block row arrives.
+      const int h = lane >> 4, l16 = lane & 15;
+      const int q = pw * 2 + h, by = q >> 3, bx = q & 7;
+      auto op_off = [&](int r) {  // this lane's 8 bytes of tile row r inside a K-major SWIZZLE_128B operand tile
+        return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((l16 >> 1) ^ (r & 7)) << 4) + (l16 & 1) * 8);
+      };
+      const int r_a = 32 * by + 2 * bx;  // tile rows of the block: a = r_a, b = r_a + 1, c = r_a + 16, d = r_a + 17
+      uint32_t so_a = op_off(r_a), so_b = op_off(r_a + 1);
+      asm volatile("" : "+r"(so_a), "+r"(so_b));
+      const uint32_t pb = sm + kOffRaw + (2 * by * 18 + 2 * bx) * 128 + l16 * 8;  // P[0][0] of the block's 4 x 4 window
+      const uint32_t qb = sm + kOffRaw + kPatchPRows * 128 + (by * 8 + bx) * 128 + l16 * 8;
+      const uint32_t cb = sm + kOffRaw + 4 * bx * 128 + l16 * 8;  // children window inside a C sub-stage ([4][32] rows)
+      const bool agg_out = p.AggOut != nullptr;
+      auto prefetch_patch = [&](int tile, uint32_t buf) {
+        if (tile >= p.num_tiles) return;
+        const int t = tile % p.tiles_per_frame;
+        const uint32_t dst = plan_u + buf * kPlanWarpBytes;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.patch.blocks + (size_t)t * 32 + pw * 2);
+        const uint8_t* tsrc = reinterpret_cast<const uint8_t*>(p.patch.tiles + t);
+        if (lane < 20) cp_async16(dst + lane * 16, wsrc + lane * 16);
+        else if (lane < 23) cp_async16(dst + lane * 16, tsrc + (lane - 20) * 16);
+      };
+      uint32_t use = 0;  // raw-slot uses so far (the producer counts the same sequence)
+      auto wait_raw = [&]() -> uint32_t {
+        const uint32_t rs = use % kRawStages, rphase = (use / kRawStages) & 1u;
+#ifdef EG_TC_TIMING
+        const long long _t = clock64();
+        mbar_wait_a(sm + kOffRawFull + rs * 8, rphase);
+        dbg_acc[1] += clock64() - _t;
+#else
+        mbar_wait_a(sm + kOffRawFull + rs * 8, rphase);
+#endif
+        return rs * kRawBytes;
+      };
+      auto release_raw = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(sm + kOffRawEmpty + (use % kRawStages) * 8);
+        ++use;
+      };
+      auto wait_op = [&]() -> uint32_t {
+        const uint32_t stage = chunk % kStages, phase = (chunk / kStages) & 1u;
+#ifdef EG_TC_TIMING
+        const long long _t = clock64();
+        mbar_wait_a(sm + kOffEmpty + stage * 8, phase ^ 1u);
+        dbg_acc[0] += clock64() - _t;
+        ++dbg_n;
+#else
+        mbar_wait_a(sm + kOffEmpty + stage * 8, phase ^ 1u);
+#endif
+        return sm + stage * 2 * kTileBytes;
+      };
+      auto release_op = [&]() {
+#ifdef EG_TC_TIMING
+        const long long _t = clock64();
+        fence_proxy_async_smem();
+        dbg_acc[2] += clock64() - _t;
+#else
+        fence_proxy_async_smem();
+#endif
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(sm + kOffFull + (chunk % kStages) * 8);
+        ++chunk;
+      };
+      auto emit2 = [&](uint32_t a_hi, uint32_t off, F2 v) {
+#ifdef EG_DBG_NOEMIT
+        if (f2_lo(v) == 123.456f) sts2(a_hi + off, make_uint2(0, 0));
+        return;
+#endif
+        uint2 hi, lo;
+        split_tf32_op(f2_lo(v), hi.x, lo.x);
+        split_tf32_op(f2_hi(v), hi.y, lo.y);
+        sts2(a_hi + off, hi);
+        sts2(a_hi + kTileBytes + off, lo);
+      };
+      uint32_t pbuf = 0;
+      prefetch_patch(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, pbuf ^= 1u) {
+        const int b = tile / p.tiles_per_frame;
+        const int t = tile - b * p.tiles_per_frame;
+        const long long frow0 = (long long)b * p.nodes_per_frame;
+        cp_async_wait_all();  // this tile's weights and descriptor (prefetched one tile ahead)
+        __syncwarp();
+        const uint32_t pl = plan_u + pbuf * kPlanWarpBytes;
+        const float4 d0 = lds4(pl + 320), d2 = lds4(pl + 352);
+        const int cls = __float_as_int(d0.x), y0 = __float_as_int(d0.z), x0 = __float_as_int(d0.w);
+        const int node0 = __float_as_int(d2.z), side = __float_as_int(d2.w);
+        if (cls == 2) {
+          // ---- CSR tile (ragged small lattices, coordinate nodes): rows summed straight from the device CSR
+          prefetch_patch(tile + gridDim.x, pbuf ^ 1u);
+          const float* fbase = p.X + frow0 * 128 + l16 * 2;
+#pragma unroll 1
+          for (int kc = 0; kc < 4; ++kc) {
+            const uint32_t a_hi = wait_op();
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+              const int r = pw * 8 + h * 4 + i;
+              const int node = __ldg(p.tile_nodes + t * 128 + r);
+              F2 acc = f2_pack(0.f, 0.f);
+              if (node >= 0) {
+                const int e1 = __ldg(p.rowptr + node + 1);
+                for (int e = __ldg(p.rowptr + node); e < e1; ++e)  // sources ascending, self loop last
+                  fma2(acc, __ldg(p.w + e), ldg_f2(fbase + (long long)__ldg(p.col + e) * 128 + kc * 32));
+                if (agg_out) st_f2(p.AggOut + (frow0 + node) * 128 + kc * 32 + l16 * 2, acc);
+              }
+              emit2(a_hi, op_off(r), acc);
+            }
+            release_op();
+          }
+          continue;
+        }
+        float wl[24];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const float4 v = lds4(pl + h * 160 + i * 16);
+          wl[4 * i] = v.x, wl[4 * i + 1] = v.y, wl[4 * i + 2] = v.z, wl[4 * i + 3] = v.w;
+        }
+        prefetch_patch(tile + gridDim.x, pbuf ^ 1u);
+        float* agg_a = agg_out ? p.AggOut + (frow0 + node0 + (long long)(y0 + 2 * by) * side + x0 + 2 * bx) * 128 + l16 * 2
+                               : nullptr;
+#pragma unroll 1
+        for (int kc = 0; kc < 4; ++kc) {
+          uint32_t ro = wait_raw();
+          const uint32_t pa = pb + ro;
+#ifdef EG_PD_NOGATHER
+#define lds_f2x(a) f2_pack(1.f, 2.f)
+#else
+#define lds_f2x(a) lds_f2(a)
+#endif
+          const F2 p01 = lds_f2x(pa + (0 * 18 + 1) * 128), p02 = lds_f2x(pa + (0 * 18 + 2) * 128);
+          const F2 p10 = lds_f2x(pa + (1 * 18 + 0) * 128), p11 = lds_f2(pa + (1 * 18 + 1) * 128);
+          const F2 p12 = lds_f2x(pa + (1 * 18 + 2) * 128), p13 = lds_f2x(pa + (1 * 18 + 3) * 128);
+          const F2 p20 = lds_f2x(pa + (2 * 18 + 0) * 128), p21 = lds_f2x(pa + (2 * 18 + 1) * 128);
+          const F2 p22 = lds_f2x(pa + (2 * 18 + 2) * 128), p23 = lds_f2x(pa + (2 * 18 + 3) * 128);
+          const F2 p31 = lds_f2x(pa + (3 * 18 + 1) * 128), p32 = lds_f2x(pa + (3 * 18 + 2) * 128);
+          const F2 pq = lds_f2x(qb + ro);
+          F2 aa = f2_pack(0.f, 0.f), ab = aa, ac = aa, ad = aa;
+          // order: up, left, right, down, parent, self (then the children)
+          fma2(aa, wl[0], p01), fma2(aa, wl[1], p10), fma2(aa, wl[2], p12), fma2(aa, wl[3], p21), fma2(aa, wl[4], pq), fma2(aa, wl[5], p11);
+          fma2(ab, wl[6], p02), fma2(ab, wl[7], p11), fma2(ab, wl[8], p13), fma2(ab, wl[9], p22), fma2(ab, wl[10], pq), fma2(ab, wl[11], p12);
+          fma2(ac, wl[12], p11), fma2(ac, wl[13], p20), fma2(ac, wl[14], p22), fma2(ac, wl[15], p31), fma2(ac, wl[16], pq), fma2(ac, wl[17], p21);
+          fma2(ad, wl[18], p12), fma2(ad, wl[19], p21), fma2(ad, wl[20], p23), fma2(ad, wl[21], p32), fma2(ad, wl[22], pq), fma2(ad, wl[23], p22);
+          asm volatile("" : "+l"(aa.u), "+l"(ab.u), "+l"(ac.u), "+l"(ad.u) : : "memory");  // the slot's loads have landed
+          release_raw();
+#ifdef EG_PD_PLAINAUX
+          if (false) {
+#else
+          if (cls == 1) {
+#endif
+#pragma unroll 1
+            for (int sub = 0; sub < 4; ++sub) {  // sub-stage `sub` = children of patch rows 2 sub, 2 sub + 1
+              ro = wait_raw();
+#ifdef EG_PD_NOCHILD
+              if (false) {
+#else
+              if (sub == by) {
+#endif
+                const uint32_t ca = cb + ro;
+                const uint32_t wcu = pl + h * 160 + 96;
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {  // node n = (ny, nx): children rows 2 ny + i, columns 2 nx + j of the window
+                  const int ny = n >> 1, nx = n & 1;
+                  const float4 wc = lds4(wcu + n * 16);
+                  const F2 c0 = lds_f2(ca + ((2 * ny) * 32 + 2 * nx) * 128), c1 = lds_f2(ca + ((2 * ny) * 32 + 2 * nx + 1) * 128);
+                  const F2 c2 = lds_f2(ca + ((2 * ny + 1) * 32 + 2 * nx) * 128), c3 = lds_f2(ca + ((2 * ny + 1) * 32 + 2 * nx + 1) * 128);
+                  F2& acc = n == 0 ? aa : n == 1 ? ab : n == 2 ? ac : ad;
+                  fma2(acc, wc.x, c0), fma2(acc, wc.y, c1), fma2(acc, wc.z, c2), fma2(acc, wc.w, c3);
+                }
+                asm volatile("" : "+l"(aa.u), "+l"(ab.u), "+l"(ac.u), "+l"(ad.u) : : "memory");
+              }
+              release_raw();
+            }
+          }
+          const uint32_t a_hi = wait_op();
+          emit2(a_hi, so_a, aa);
+          emit2(a_hi, so_b, ab);
+          emit2(a_hi, so_a + 2048, ac);
+          emit2(a_hi, so_b + 2048, ad);
+          release_op();
+          if (agg_out) {  // A_hat dH side output: stored after the chunk is handed to the MMA
+            float* o = agg_a + kc * 32;
+            st_f2(o, aa);
+            st_f2(o + 128, ab);
+            st_f2(o + (long long)side * 128, ac);
+            st_f2(o + (long long)side * 128 + 128, ad);
+          }
+        }
+      }
+    }
+  } else if (MODE == kPatch && warp >= kLoadWarp0) {
+    // ===== patch mode producer: ONE thread issues the TMA box copies of every slot use (the other loader lanes idle)
+    if constexpr (MODE == kPatch) {
+      if (warp == kLoadWarp0 && lane == 0) {
+        const uint32_t bar_raw_full = sm + kOffRawFull, bar_raw_empty = sm + kOffRawEmpty;
+        uint32_t use = 0;
+        auto slot_acquire = [&](uint32_t bytes, uint32_t& dst, uint32_t& bar) {
+          const uint32_t rs = use % kRawStages, rphase = (use / kRawStages) & 1u;
+#ifdef EG_TC_TIMING
+          const long long _t = clock64();
+          mbar_wait_a(bar_raw_empty + rs * 8, rphase ^ 1u);
+          dbg_acc[0] += clock64() - _t;
+#else
+          mbar_wait_a(bar_raw_empty + rs * 8, rphase ^ 1u);
+#endif
+          bar = bar_raw_full + rs * 8;
+          dst = sm + kOffRaw + rs * kRawBytes;
+#ifdef EG_PD_NOTMA
+          mbar_arrive_a(bar);
+#else
+          mbar_arrive_expect_tx_a(bar, bytes);
+#endif
+          ++use;
+        };
+        auto load_desc = [&](int tile, int4& a, int4& b4, int4& c) {
+          if (tile >= p.num_tiles) return;
+          const int4* d = reinterpret_cast<const int4*>(p.patch.tiles + tile % p.tiles_per_frame);
+          a = __ldg(d), b4 = __ldg(d + 1), c = __ldg(d + 2);
+        };
+        int4 na = make_int4(2, 0, 0, 0), nb = na, nc = na;
+        load_desc(blockIdx.x, na, nb, nc);
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          const int4 ta = na, tb = nb, tcd = nc;  // {cls, level, y0, x0} {qlevel, qy, qx, clevel} {cy, cx, node0, side}
+          load_desc(tile + gridDim.x, na, nb, nc);
+          if (ta.x == 2) continue;
+          const int b = tile / p.tiles_per_frame;
+          const CUtensorMap* mp = &pm->m[3 * ta.y];
+          const CUtensorMap* mq = tb.x >= 0 ? &pm->m[3 * tb.x + 1] : nullptr;
+          const CUtensorMap* mc = tb.w >= 0 ? &pm->m[3 * tb.w + 2] : nullptr;
+#pragma unroll 1
+          for (int kc = 0; kc < 4; ++kc) {
+            uint32_t dst, bar;
+            slot_acquire(kPatchPRows * 128 + (mq ? kPatchQRows * 128 : 0), dst, bar);
+#ifndef EG_PD_NOTMA
+            tma_load_4d(dst, mp, kc * 32, ta.w - 1, ta.z - 1, b, bar);
+            if (mq) tma_load_4d(dst + kPatchPRows * 128, mq, kc * 32, tb.z, tb.y, b, bar);
+#endif
+#ifdef EG_PD_PLAINAUX
+            if (false) {
+#else
+            if (ta.x == 1) {
+#endif
+#pragma unroll 1
+              for (int sub = 0; sub < 4; ++sub) {
+                slot_acquire(kPatchCRows * 128, dst, bar);
+#ifndef EG_PD_NOTMA
+                tma_load_4d(dst, mc, kc * 32, tcd.y, tcd.x + 4 * sub, b, bar);
+#endif
+              }
+            }
           }
         }
       }
@@ -841,27 +1156,97 @@ __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
   }
 }
 
-template <bool GATHER>
-int launch(const TcParams& p, float* mean, float* var, void* ws, size_t ws_bytes, const char* name, cudaStream_t s) {
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
+  tc_body<MODE>(p, nullptr);
+}
+__global__ void __launch_bounds__(kThreads, 1) gcn_patch_kernel(const TcParams p, const __grid_constant__ PatchMaps pm) {
+  tc_body<kPatch>(p, &pm);
+}
+
+template <int MODE>
+int launch(const TcParams& p, const PatchMaps* pm, float* mean, float* var, void* ws, size_t ws_bytes, const char* name,
+           cudaStream_t s) {
   const bool stats = mean && var;
   if (stats && (!ws || ws_bytes < kWorkspaceBytes)) {
     set_error("workspace too small: need %zu bytes", kWorkspaceBytes);
     return EG_ERR_WORKSPACE;
   }
   static std::atomic<unsigned long long> attr_mask{0};  // per template instance, one bit per device
-  if (first_use_on_current_device(attr_mask))
-    EG_CUDA(cudaFuncSetAttribute(gcn_tc_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  if (first_use_on_current_device(attr_mask)) {
+    if (MODE == kPatch)
+      EG_CUDA(cudaFuncSetAttribute(gcn_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<MODE>::kSmemBytes));
+    else
+      EG_CUDA(cudaFuncSetAttribute(gcn_tc_kernel<MODE == kPatch ? kGather : MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)Lay<MODE>::kSmemBytes));
+  }
   const int sms = num_sms();
   const int grid = (int)(p.num_tiles < sms ? p.num_tiles : sms);
   TcParams q = p;
   q.stat_parts = stats ? reinterpret_cast<double*>(ws) : nullptr;
   {
     ProfileScope prof(name, s);
-    gcn_tc_kernel<GATHER><<<grid, kThreads, kSmemBytes, s>>>(q);
+    if (MODE == kPatch)
+      gcn_patch_kernel<<<grid, kThreads, Lay<MODE>::kSmemBytes, s>>>(q, *pm);
+    else
+      gcn_tc_kernel<MODE == kPatch ? kGather : MODE><<<grid, kThreads, Lay<MODE>::kSmemBytes, s>>>(q);
     EG_LAUNCH_CHECK();
   }
   if (stats) return launch_stats_finalize(grid, 128, 128, p.rows, q.stat_parts, mean, var, s);
   return EG_OK;
+}
+
+// ---- tensor maps of the node tensor (patch mode) ------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// Level l of the node tensor X [batch * N, 128] as a 4-D tensor (feature, x, y, frame); boxes of 32 features.
+int encode_patch_maps(const eg_graph_info& info, int batch, const float* X, PatchMaps& out) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return EG_ERR_CUDA;
+  }
+  static const cuuint32_t kBox[3][2] = {{18, 10}, {8, 4}, {32, 4}};  // P, Q, C: (x, y) extent
+  for (int l = 0; l < info.num_levels; ++l) {
+    const cuuint64_t side = (cuuint64_t)info.level_size[l];
+    const cuuint64_t dims[4] = {128, side, side, (cuuint64_t)batch};
+    const cuuint64_t strides[3] = {512, side * 512, (cuuint64_t)info.num_nodes * 512};
+    void* base = const_cast<float*>(X) + (size_t)info.level_offset[l] * 128;
+    for (int k = 0; k < 3; ++k) {
+      const cuuint32_t box[4] = {32, kBox[k][0], kBox[k][1], 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      const CUresult r = enc(&out.m[3 * l + k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for level %d (side %d), box %d", (int)r, l, (int)side, k);
+        return EG_ERR_CUDA;
+      }
+    }
+  }
+  return EG_OK;
+}
+
+// EG_GCN_PLAN=gather forces the gather plan (development / A-B timing); default: the patch plan wherever it applies
+bool patch_plan_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("EG_GCN_PLAN");
+    return !(e && strcmp(e, "gather") == 0);
+  }();
+  return on;
 }
 
 }  // namespace
@@ -901,7 +1286,14 @@ int launch_gcn_tc(const eg_graph* g, int batch, const float* X, const float* W, 
   p.addend = addend;
   p.Out = Out;
   p.AggOut = AggOut;
-  return launch<true>(p, mean, var, ws, ws_bytes, AggOut ? "gcn_tc_bwd" : "gcn_tc_fwd", s);
+  const PatchPlan& pp = graph_patch_plan(g);
+  if (pp.ok && patch_plan_enabled()) {
+    p.patch = pp;
+    PatchMaps maps;
+    if (int rc = encode_patch_maps(info, batch, X, maps)) return rc;
+    return launch<kPatch>(p, &maps, mean, var, ws, ws_bytes, AggOut ? "gcn_tc_bwd" : "gcn_tc_fwd", s);
+  }
+  return launch<kGather>(p, nullptr, mean, var, ws, ws_bytes, AggOut ? "gcn_tc_bwd" : "gcn_tc_fwd", s);
 }
 
 // C = A op(W) + bias + addend (C may alias A: a tile is read completely before its epilogue writes it).
@@ -921,7 +1313,7 @@ int launch_linear_tc(long long rows, const float* A, const float* W, int trans_w
   p.bias = bias;
   p.addend = addend;
   p.Out = C;
-  return launch<false>(p, mean, var, ws, ws_bytes, "linear_tc", s);
+  return launch<kLinear>(p, nullptr, mean, var, ws, ws_bytes, "linear_tc", s);
 }
 
 }  // namespace eg

@@ -44,6 +44,7 @@ struct eg_graph {
   // reads most (its own rows, the lattice halo, the parents) are staged in shared memory; every edge of a
   // tile row is either a slot of that stage or a direct global read (e.g. the 4 children of an aux node).
   eg::TilePlan plan;
+  eg::PatchPlan patch;  // TMA path of the fused kernel (regular lattices only)
 };
 
 using namespace eg;
@@ -275,6 +276,115 @@ HostPlan build_plan(const Topo& t, const std::vector<int32_t>& tiles) {
   return hp;
 }
 
+struct HostPatchPlan {
+  int ok = 0;
+  std::vector<PatchTile> tiles;
+  std::vector<PatchBlockW> blocks;
+};
+
+// Patch plan (see PatchTile / PatchBlockW in common.cuh).  Weights are dis[v] * dis[u] with dis exactly as
+// degree_kernel computes it, so the patch path and the CSR agree bit for bit on every coefficient.
+HostPatchPlan build_patch_plan(const Topo& t, const std::vector<int32_t>& tiles) {
+  HostPatchPlan pp;
+  const int T = (int)(tiles.size() / 128);
+  pp.ok = !t.mdiag && !t.adiag && !t.conn;
+  if (!pp.ok) return pp;
+  PatchTile zt;
+  memset(&zt, 0, sizeof(zt));
+  zt.cls = 2;
+  zt.qlevel = zt.clevel = -1;
+  pp.tiles.assign(T, zt);
+  PatchBlockW zb;
+  memset(&zb, 0, sizeof(zb));
+  pp.blocks.assign((size_t)T * 32, zb);
+  auto dis = [&](int u) { return (float)(1.0 / sqrt((double)(degree_of(t, u) + 1))); };
+  const int main_l = t.nlev - 1;
+  int npatch = 0;
+  for (int l = 0; l < t.nlev; ++l)
+    if (t.lsize[l] % 16 == 0) npatch += (t.lsize[l] / 8) * (t.lsize[l] / 16);
+  int ti = T - npatch;  // build_tiles: the misc tiles come first (they stay CSR tiles), then the patches level by level
+  if (ti < 0) {
+    pp.ok = 0;
+    return pp;
+  }
+  for (int l = 0; l < t.nlev; ++l) {
+    const int p = t.lsize[l], off = t.loff[l];
+    if (p % 16 != 0) continue;
+    const bool is_main = l == main_l;
+    for (int y0 = 0; y0 < p; y0 += 8)
+      for (int x0 = 0; x0 < p; x0 += 16, ++ti) {
+        if (ti >= T || tiles[(size_t)ti * 128] != off + y0 * p + x0) {  // tile table and patch order disagree
+          pp.ok = 0;
+          return pp;
+        }
+        PatchTile& pt = pp.tiles[ti];
+        pt.level = l;
+        pt.y0 = y0;
+        pt.x0 = x0;
+        pt.node0 = off;
+        pt.side = p;
+        // parents (for_each_neighbor: main -> crop window of the last aux level; aux l >= 1 -> level l - 1)
+        if (is_main) {
+          if (!t.main_only) {
+            pt.qlevel = t.naux - 1;
+            pt.qy = t.crop + y0 / 2;
+            pt.qx = t.crop + x0 / 2;
+          }
+        } else if (l >= 1) {
+          pt.qlevel = l - 1;
+          pt.qy = y0 / 2;
+          pt.qx = x0 / 2;
+        }
+        // children
+        if (!is_main) {
+          if (l < t.naux - 1) {
+            pt.clevel = l + 1;
+            pt.cy = 2 * y0;
+            pt.cx = 2 * x0;
+          } else {
+            pt.clevel = main_l;
+            pt.cy = 2 * (y0 - t.crop);
+            pt.cx = 2 * (x0 - t.crop);
+          }
+        }
+        bool any_child = false;
+        for (int q = 0; q < 32; ++q) {
+          PatchBlockW& bw = pp.blocks[(size_t)ti * 32 + q];
+          const int by = q >> 3, bx = q & 7;
+          for (int n = 0; n < 4; ++n) {
+            const int a = y0 + 2 * by + (n >> 1), b = x0 + 2 * bx + (n & 1);
+            const int v = off + a * p + b;
+            const float dv = dis(v);
+            if (a > 0) bw.wl[n][0] = dv * dis(v - p);
+            if (b > 0) bw.wl[n][1] = dv * dis(v - 1);
+            if (b < p - 1) bw.wl[n][2] = dv * dis(v + 1);
+            if (a < p - 1) bw.wl[n][3] = dv * dis(v + p);
+            if (pt.qlevel >= 0) {
+              const int P = t.lsize[pt.qlevel];
+              const int pa = is_main ? t.crop + a / 2 : a / 2, pb = is_main ? t.crop + b / 2 : b / 2;
+              if (!is_main || (a < 2 * t.half && b < 2 * t.half)) bw.wl[n][4] = dv * dis(t.loff[pt.qlevel] + pa * P + pb);
+            }
+            bw.wl[n][5] = dv * dv;
+            if (pt.clevel >= 0) {
+              const int P2 = t.lsize[pt.clevel], off2 = t.loff[pt.clevel];
+              const bool window = l < t.naux - 1 || (a >= t.crop && a < t.crop + t.half && b >= t.crop && b < t.crop + t.half);
+              if (window) {
+                const int ca = l < t.naux - 1 ? 2 * a : 2 * (a - t.crop), cb = l < t.naux - 1 ? 2 * b : 2 * (b - t.crop);
+                for (int i = 0; i < 2; ++i)
+                  for (int j = 0; j < 2; ++j) bw.wc[n][i * 2 + j] = dv * dis(off2 + (ca + i) * P2 + cb + j);
+                any_child = true;
+              }
+            }
+          }
+        }
+        pt.cls = any_child ? 1 : 0;
+        if (!any_child) pt.clevel = -1;
+      }
+  }
+  if (ti != T) pp.ok = 0;
+  return pp;
+}
+
 int init_topo(const eg_graph_spec* spec, Topo& t) {
   if (!spec) {
     set_error("spec is NULL");
@@ -411,6 +521,12 @@ int eg_graph_create(const eg_graph_spec* spec, int device, eg_graph** out) {
     EG_TRY(up(hp.hdr.data(), hp.hdr.size() * sizeof(int4), (void**)&g->plan.hdr));
     EG_TRY(up(hp.src.data(), hp.src.size() * sizeof(int32_t), (void**)&g->plan.src));
     EG_TRY(up(hp.rows.data(), hp.rows.size() * sizeof(PlanRow), (void**)&g->plan.rows));
+    HostPatchPlan pp = build_patch_plan(t, tiles);
+    g->patch.ok = pp.ok;
+    if (pp.ok) {
+      EG_TRY(up(pp.tiles.data(), pp.tiles.size() * sizeof(PatchTile), (void**)&g->patch.tiles));
+      EG_TRY(up(pp.blocks.data(), pp.blocks.size() * sizeof(PatchBlockW), (void**)&g->patch.blocks));
+    }
   }
   std::vector<int32_t> hdeg(t.N);
   EG_TRY(cudaMemcpy(hdeg.data(), deg, sizeof(int32_t) * t.N, cudaMemcpyDeviceToHost));
@@ -437,6 +553,8 @@ void eg_graph_destroy(eg_graph* g) {
   cudaFree((void*)g->plan.hdr);
   cudaFree((void*)g->plan.src);
   cudaFree((void*)g->plan.rows);
+  cudaFree((void*)g->patch.tiles);
+  cudaFree((void*)g->patch.blocks);
   delete g;
 }
 
@@ -555,6 +673,74 @@ int eg_graph_plan_check(const eg_graph_spec* spec, int64_t* stats) {
   return (int)std::min<long long>(bad, 1 << 30);
 }
 
+// Host-only self check of the patch plan (TMA path of the fused kernel): replays, for every patch tile and node, the
+// sources the kernel reads -- box position -> node id, exactly as the tensor-map coordinates address them -- and
+// compares the (source, weight) set with the CSR row.  stats (optional, int64[4]): plan usable (0/1), plain patch
+// tiles, patch tiles with children, CSR tiles.  Returns the number of violations or a negative error code.
+int eg_graph_patch_check(const eg_graph_spec* spec, int64_t* stats) {
+  Topo t;
+  int rc = init_topo(spec, t);
+  if (rc) return rc;
+  const std::vector<int32_t> tiles = build_tiles(t);
+  const HostPatchPlan pp = build_patch_plan(t, tiles);
+  const int T = (int)(tiles.size() / 128);
+  long long bad = 0, cls[3] = {0, 0, 0};
+  if (stats) stats[0] = pp.ok, stats[1] = stats[2] = stats[3] = 0;
+  if (!pp.ok) return 0;
+  std::vector<float> dis(t.N);
+  for (int u = 0; u < t.N; ++u) dis[u] = (float)(1.0 / sqrt((double)(degree_of(t, u) + 1)));
+  auto at = [&](int level, int y, int x) {  // node at a box position, -1 = outside the lattice (TMA fills zeros)
+    const int p = t.lsize[level];
+    return (y < 0 || x < 0 || y >= p || x >= p) ? -1 : t.loff[level] + y * p + x;
+  };
+  std::vector<std::pair<int, float>> want, got;
+  for (int ti = 0; ti < T; ++ti) {
+    const PatchTile& pt = pp.tiles[ti];
+    if (pt.cls < 0 || pt.cls > 2) {
+      ++bad;
+      continue;
+    }
+    ++cls[pt.cls];
+    if (pt.cls == 2) continue;
+    bad += pt.node0 != t.loff[pt.level] || pt.side != t.lsize[pt.level] || (pt.cls == 1) != (pt.clevel >= 0);
+    for (int q = 0; q < 32; ++q) {
+      const PatchBlockW& bw = pp.blocks[(size_t)ti * 32 + q];
+      const int by = q >> 3, bx = q & 7;
+      for (int n = 0; n < 4; ++n) {
+        const int ny = n >> 1, nx = n & 1;
+        const int y = pt.y0 + 2 * by + ny, x = pt.x0 + 2 * bx + nx;
+        const int v = at(pt.level, y, x);
+        bad += v < 0 || v != tiles[(size_t)ti * 128 + (2 * by + ny) * 16 + 2 * bx + nx];
+        got.clear();
+        auto add = [&](float w, int u) {
+          if (w == 0.f) return;
+          if (u < 0) ++bad;  // a weight on a position the copy fills with zeros
+          else got.emplace_back(u, w);
+        };
+        add(bw.wl[n][0], at(pt.level, y - 1, x));
+        add(bw.wl[n][1], at(pt.level, y, x - 1));
+        add(bw.wl[n][2], at(pt.level, y, x + 1));
+        add(bw.wl[n][3], at(pt.level, y + 1, x));
+        add(bw.wl[n][4], pt.qlevel >= 0 ? at(pt.qlevel, pt.qy + by, pt.qx + bx) : -1);
+        add(bw.wl[n][5], v);
+        for (int i = 0; i < 2; ++i)
+          for (int j = 0; j < 2; ++j)
+            add(bw.wc[n][i * 2 + j],
+                pt.clevel >= 0 ? at(pt.clevel, pt.cy + 4 * by + 2 * ny + i, pt.cx + 4 * bx + 2 * nx + j) : -1);
+        if (v < 0) continue;
+        want.clear();
+        for_each_neighbor(t, v, true, [&](int u) { want.emplace_back(u, dis[u] * dis[v]); });
+        want.emplace_back(v, dis[v] * dis[v]);
+        std::sort(want.begin(), want.end());
+        std::sort(got.begin(), got.end());
+        bad += want != got;
+      }
+    }
+  }
+  if (stats) stats[1] = cls[0], stats[2] = cls[1], stats[3] = cls[2];
+  return (int)std::min<long long>(bad, 1 << 30);
+}
+
 int eg_graph_export_edge_index(const eg_graph* g, int batch, int64_t* out, void* stream) {
   EG_CHECK_ARG(g && out && batch >= 1, "bad arguments");
   long long total = (long long)batch * g->topo.N;
@@ -598,4 +784,5 @@ const int32_t* graph_tile_nodes(const eg_graph* g) { return g->tile_nodes; }
 int graph_tiles_per_frame(const eg_graph* g) { return g->tiles_per_frame; }
 const int32_t* graph_tile_groups(const eg_graph* g) { return g->tile_groups; }
 const TilePlan& graph_plan(const eg_graph* g) { return g->plan; }
+const PatchPlan& graph_patch_plan(const eg_graph* g) { return g->patch; }
 }  // namespace eg

@@ -86,6 +86,12 @@ int eg_graph_tiles(const eg_graph* g, const int32_t** tile_nodes, int32_t* tiles
  * class of the fused kernel (lattice, general).  Returns the number of
  * violations (0 = consistent) or a negative EG_ERR_* code. */
 int eg_graph_plan_check(const eg_graph_spec* spec, int64_t* stats);
+/* Host-only consistency check of the PATCH plan (the TMA path of the fused kernel on regular 4-neighbour lattices:
+ * haloed 8x16 patch + parents + children staged by tensor-map box copies, one 2x2 node block per half-warp): the
+ * sources every patch node reads through its box positions and their weights against the closed-form neighbour
+ * lists and gcn_norm weights (no GPU needed).  stats (optional): int64[4] = plan usable for this spec (0/1), plain
+ * patch tiles, patch tiles with children, CSR tiles.  Returns the number of violations or a negative EG_ERR_* code. */
+int eg_graph_patch_check(const eg_graph_spec* spec, int64_t* stats);
 /* edge_index exactly as the reference's loader produces it for a batch of `batch` frames:
  * int64[2, batch*num_edges], grouped by source in the networkx insertion order, frame b offset by
  * b*num_nodes.  `out` is a DEVICE pointer. */
