@@ -95,14 +95,25 @@ class HierarchicalPatchModel(nn.Module):
         assert gnn_jk_mode in ['last', 'max', 'cat'], "Only last, max or cat jumping knowledge mode is supported."
         if output_activation not in ('sigmoid', 'logit'):
             raise TypeError(f"invalid output_activation:{output_activation}")  # reference raises a TypeError too
-        if node_embedding_dim != F or node_hidden_dim != F:
-            raise NotImplementedError(
-                f"echoglad_b200 tensor-core paths are built for node_embedding_dim == node_hidden_dim == {F} "
-                f"(configs/default.yml:14-15); got {node_embedding_dim}/{node_hidden_dim}")
-        if num_output_channels != 4 or classifier_hidden_dim != 32:
-            raise NotImplementedError(
-                "echoglad_b200 classifier kernels are built for num_output_channels == 4 (src/engine.py:92) and "
-                f"classifier_hidden_dim == 32 (configs/default.yml:16); got {num_output_channels}/{classifier_hidden_dim}")
+        # Widths.  node_embedding_dim == node_hidden_dim == 128, classifier_hidden_dim == 32, 4 channels (default.yml)
+        # run the tensor-core kernels; other widths (e.g. the reference constructor defaults 64 / 16,
+        # src/core/models.py:290-296) run the same graph / BatchNorm / loss kernels with the generic fp32 transforms
+        # (eg_linear_fwd / eg_linear_wgrad) and the CSR aggregation (eg_gcn_aggregate).
+        self._wide = (node_embedding_dim == F and node_hidden_dim == F and classifier_hidden_dim == 32 and
+                      num_output_channels == 4)
+        if not self._wide:
+            if node_embedding_dim != F:
+                raise NotImplementedError(f"node_embedding_dim must be {F}: the pyramid / packing kernels move "
+                                          f"{F}-wide node rows (got {node_embedding_dim})")
+            if node_hidden_dim not in (64, 128):
+                raise NotImplementedError(f"node_hidden_dim must be 64 or 128 (eg_gcn_aggregate / eg_bn_act widths); "
+                                          f"got {node_hidden_dim}")
+            if classifier_hidden_dim not in (8, 16, 32, 64, 128):
+                raise NotImplementedError("classifier_hidden_dim must be one of 8, 16, 32, 64, 128 (eg_bn_act widths); "
+                                          f"got {classifier_hidden_dim}")
+            if use_coordinate_graph:
+                raise NotImplementedError("use_coordinate_graph is built for node_hidden_dim == 128 and "
+                                          "classifier_hidden_dim == 32 (eg_coord_update kernels)")
         if gnn_jk_mode == 'cat':
             raise NotImplementedError("gnn_jk_mode='cat' feeds (L+1)*128 features into Linear(128, .) and fails in "
                                       "the reference as well (src/core/models.py:364,479-482)")
@@ -221,7 +232,7 @@ class HierarchicalPatchModel(nn.Module):
             h = self.gnn_stack(feats, graph, batch)
         if graph.meta.num_pixel_nodes != graph.meta.num_nodes:  # drop connection / coordinate rows
             a = graph.meta.first_pixel_node
-            h = h.view(batch, graph.meta.num_nodes, F)[:, a:a + graph.meta.num_pixel_nodes].reshape(-1, F)
+            h = h.view(batch, graph.meta.num_nodes, h.shape[1])[:, a:a + graph.meta.num_pixel_nodes].reshape(-1, h.shape[1])
         out = self.classify(h)
         if self.training:
             self._step += 1
@@ -263,10 +274,20 @@ class HierarchicalPatchModel(nn.Module):
         for i, blk in enumerate(self.gnn_layers):
             bn = blk.module_1
             use_batch_stats = self.training or not bn.track_running_stats
-            y, mean, var = ops.GCNLayer.apply(
-                graph, batch, hidden[i], blk.module_0.lin.weight, blk.module_0.bias, bn.weight, bn.bias,
-                bn.running_mean, bn.running_var, use_batch_stats, bn.eps,
-                blk.dropout_p if self.training else 0.0, self._seed(i), blk.relu, bool(self.residual))
+            if self._wide:
+                y, mean, var = ops.GCNLayer.apply(
+                    graph, batch, hidden[i], blk.module_0.lin.weight, blk.module_0.bias, bn.weight, bn.bias,
+                    bn.running_mean, bn.running_var, use_batch_stats, bn.eps,
+                    blk.dropout_p if self.training else 0.0, self._seed(i), blk.relu, bool(self.residual))
+            else:
+                # generic widths: (A_hat X) W^T + b with the CSR aggregation and the fp32 transform, then the same
+                # BatchNorm / Dropout / ReLU kernels; the residual only where the widths agree (src/core/models.py:434)
+                w = blk.module_0.lin.weight
+                z = ops.LinearGeneric.apply(ops.Aggregate.apply(graph, batch, hidden[i]), w, blk.module_0.bias)
+                res = hidden[i] if (self.residual and w.shape[0] == w.shape[1]) else None
+                y, mean, var = ops.BNAct.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, use_batch_stats,
+                                               bn.eps, blk.dropout_p if self.training else 0.0, self._seed(i), blk.relu,
+                                               res)
             if self.training and bn.track_running_stats:
                 _update_running(bn, mean, var, rows)
             if coords is not None:
@@ -280,7 +301,28 @@ class HierarchicalPatchModel(nn.Module):
             out = hidden[-1]
         return out if coords is None else (out, coords)
 
+    def _classify_generic(self, h: torch.Tensor) -> torch.Tensor:
+        """Node classifiers of any width: per head Linear -> BN -> ReLU -> Dropout -> Linear -> BN -> ReLU -> Dropout
+        -> Linear (src/core/models.py:363-377) on the generic transforms + the BatchNorm / activation kernels."""
+        rows = h.shape[0]
+        p = self.classifier_dropout_p if self.training else 0.0
+        outs = []
+        for k, c in enumerate(self.node_classifiers):
+            a = h
+            for j, (lin, bn) in enumerate(((c[0], c[1]), (c[4], c[5]))):
+                z = ops.LinearGeneric.apply(a, lin.weight, lin.bias)
+                use_batch_stats = self.training or not bn.track_running_stats
+                a, mean, var = ops.BNAct.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, use_batch_stats,
+                                               bn.eps, p, self._seed(101 + 10 * k + j), True, None)
+                if self.training and bn.track_running_stats:
+                    _update_running(bn, mean, var, rows)
+            outs.append(ops.LinearGeneric.apply(a, c[8].weight, c[8].bias))
+        out = torch.cat(outs, dim=1)
+        return torch.sigmoid(out) if self.output_activation == 'sigmoid' else out
+
     def classify(self, h: torch.Tensor) -> torch.Tensor:
+        if not self._wide:
+            return self._classify_generic(h)
         clf = self.node_classifiers
         cat = torch.cat
         w1 = cat([c[0].weight for c in clf]); b1 = cat([c[0].bias for c in clf])

@@ -322,6 +322,70 @@ class EmbedPackNodes(torch.autograd.Function):
         return (None, None, *grads)
 
 
+class LinearGeneric(torch.autograd.Function):
+    """y = x W^T + b for row-major tensors of ANY width (eg_linear_fwd / eg_linear_wgrad, fp32 FMA): the dense
+    transforms of a module whose widths are not the tensor-core kernels' 128 / 32 / 4 (the reference constructor
+    defaults are node_hidden_dim=64, classifier_hidden_dim=16, src/core/models.py:290-296)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        x, w = _f32(x, "x"), _f32(w, "W")
+        rows, k = x.shape
+        n = w.shape[0]
+        if w.shape[1] != k:
+            raise EchogladError(f"LinearGeneric: x {tuple(x.shape)} does not match W {tuple(w.shape)}")
+        y = torch.empty(rows, n, device=x.device)
+        linear_generic(rows, k, n, _view_rows(x), w, True, _view_rows(y), bias=bias, stream=_stream(x))
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _f32(dy, "dy")
+        rows, k = x.shape
+        n = w.shape[0]
+        st = _stream(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            linear_generic(rows, n, k, _view_rows(dy), w, False, _view_rows(dx), stream=st)
+        if ctx.needs_input_grad[1] or ctx.has_bias:
+            dw = torch.empty_like(w)
+            db = torch.empty(n, device=w.device) if ctx.has_bias else None
+            linear_generic_wgrad(rows, k, n, _view_rows(dy), _view_rows(x), dw, db, _ws(w.device), stream=st)
+        return dx, dw, db
+
+
+class BNAct(torch.autograd.Function):
+    """BatchNorm1d (batch or running statistics) -> Dropout -> ReLU|Identity (+ residual) on [rows, cols] with
+    cols in {4, 8, ..., 128} (eg_col_stats / eg_bn_act_fwd / eg_bn_act_bwd).  Returns (y, batch_mean, batch_var)."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, mean_in, var_in, training: bool, eps: float, drop_p: float, seed: int, relu: bool,
+                res):
+        z = _f32(z, "z")
+        if training:
+            mean, var = col_stats(z)
+        else:
+            mean, var = _f32(mean_in, "running_mean"), _f32(var_in, "running_var")
+        p = float(drop_p) if training else 0.0
+        y = bn_act_fwd(z, mean, var, gamma, beta, eps, p, seed, relu, res)
+        ctx.save_for_backward(z, gamma, beta, mean, var)
+        ctx.cfg = (training, eps, p, seed, relu, res is not None)
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, dy, _dm, _dv):
+        z, gamma, beta, mean, var = ctx.saved_tensors
+        training, eps, p, seed, relu, has_res = ctx.cfg
+        dy = _f32(dy, "dy")
+        dz, dgamma, dbeta = bn_act_bwd(dy, z, mean, var, gamma, beta, eps, p, seed, relu, training)
+        return (dz, dgamma, dbeta) + (None,) * 7 + (dy if has_res else None,)
+
+
 class Aggregate(torch.autograd.Function):
     """y = A_hat x (A_hat symmetric => backward is the same kernel)."""
 

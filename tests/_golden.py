@@ -17,6 +17,8 @@ MODEL_CASES = {
                                                                residual=False, num_gnn_layers=2), True),
     "model_avgpool_S12_n3_conn_train": ("avgpool", dict(frame_size=12, num_aux_graphs=3,
                                                         use_connection_nodes=True), True),
+    "model_avgpool_S12_n3_h64_c16_train": ("avgpool", dict(frame_size=12, num_aux_graphs=3, node_hidden_dim=64,
+                                                           classifier_hidden_dim=16), True),
     "model_unet_S16_n3_eval": ("unet", dict(frame_size=16, num_aux_graphs=3), False),
     "model_unet_S16_n3_train": ("unet", dict(frame_size=16, num_aux_graphs=3), True),
     "model_unet_S224_n7_train": ("unet", dict(frame_size=224, num_aux_graphs=7), True),

@@ -214,6 +214,16 @@ def run_reference_model(variant, cfg_kw, batch, seed, *, training, coords_seed=7
     return out
 
 
+def make_default_width_model():
+    """The reference CONSTRUCTOR defaults node_hidden_dim=64 / classifier_hidden_dim=16 (src/core/models.py:290-296):
+    layer 0 maps 128 -> 64 without a residual (widths differ, :434), the classifiers are 64 -> 16 -> 8 -> 1."""
+    o = run_reference_model("avgpool", dict(frame_size=12, num_aux_graphs=3, gnn_dropout_p=0.0, classifier_dropout_p=0.0,
+                                            node_hidden_dim=64, classifier_hidden_dim=16),
+                            batch=3, seed=15, training=True)
+    np.savez_compressed(os.path.join(HERE, "model_avgpool_S12_n3_h64_c16_train.npz"), **o)
+    print("h64/c16", float(o["loss_bce"]), float(o["loss_elmse"]), flush=True)
+
+
 def make_models(skip_big: bool):
     tiny = dict(frame_size=12, num_aux_graphs=3, gnn_dropout_p=0.0, classifier_dropout_p=0.0)
     for training in (False, True):
@@ -236,6 +246,7 @@ def make_models(skip_big: bool):
                             batch=3, seed=14, training=True)
     np.savez_compressed(os.path.join(HERE, "model_avgpool_S12_n3_coord_train.npz"), **o)
     print("coord", float(o["loss_bce"]), float(o["loss_elmse"]), float(o["loss_mae"]), flush=True)
+    make_default_width_model()
     unet = dict(frame_size=16, num_aux_graphs=3, gnn_dropout_p=0.0, classifier_dropout_p=0.0)
     for training in (False, True):
         tag = "train" if training else "eval"

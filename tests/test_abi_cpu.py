@@ -179,8 +179,14 @@ def test_state_dict_layout_is_the_references(eg):
 
 def test_unsupported_configs_fail_loudly_and_cpu_inputs_are_rejected(eg):
     kw = dict(DEFAULT_KW)
+    # the reference constructor defaults (64 / 16, src/core/models.py:290-296) build the generic-width path
+    small = eg.HierarchicalPatchModel(**{**kw, "node_hidden_dim": 64, "classifier_hidden_dim": 16})
+    assert small.state_dict()["gnn_layers.0.module_0.lin.weight"].shape == (64, 128)
+    assert small.state_dict()["node_classifiers.3.4.weight"].shape == (8, 16)
     with pytest.raises(NotImplementedError):
-        eg.HierarchicalPatchModel(**{**kw, "node_hidden_dim": 64})
+        eg.HierarchicalPatchModel(**{**kw, "node_hidden_dim": 96})
+    with pytest.raises(NotImplementedError):
+        eg.HierarchicalPatchModel(**{**kw, "node_hidden_dim": 64, "use_coordinate_graph": True})
     coord = eg.HierarchicalPatchModel(**{**kw, "use_coordinate_graph": True})  # optional branch: 3 coordinate MLPs
     assert [k for k in coord.state_dict() if k.startswith("node_coordinate_mlp.2.8.")] == \
         ["node_coordinate_mlp.2.8.weight", "node_coordinate_mlp.2.8.bias"]

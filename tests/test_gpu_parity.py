@@ -709,8 +709,9 @@ def test_expected_coords_default_size_against_oracle():
 
 def _build_module(cfg, variant):
     kw = dict(frame_size=cfg.frame_size, gnn_dropout_p=cfg.gnn_dropout_p, classifier_dropout_p=cfg.classifier_dropout_p,
-              node_embedding_dim=128, node_hidden_dim=128, num_output_channels=4, num_gnn_layers=cfg.num_gnn_layers,
-              num_aux_graphs=cfg.num_aux_graphs, gnn_jk_mode=cfg.gnn_jk_mode, classifier_hidden_dim=32,
+              node_embedding_dim=128, node_hidden_dim=cfg.node_hidden_dim, num_output_channels=4,
+              num_gnn_layers=cfg.num_gnn_layers, num_aux_graphs=cfg.num_aux_graphs, gnn_jk_mode=cfg.gnn_jk_mode,
+              classifier_hidden_dim=cfg.classifier_hidden_dim,
               residual=cfg.residual, use_coordinate_graph=False, output_activation=cfg.output_activation,
               use_connection_nodes=cfg.use_connection_nodes, use_main_graph_only=cfg.use_main_graph_only)
     if variant == "unet":
