@@ -314,7 +314,28 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
       }
       const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + slab * 32;
       tmem_st32(ta, hi);
+#ifdef EG_TF32X3
       tmem_st32(ta + 128, lo);
+#else
+      // correction operand, bf16, K = 64 per chunk in the order the compute warps emit (see emit / emit2): a group of
+      // G features (G = 4: float4 lanes, G = 2: patch mode) occupies 2 G consecutive K slots, first the slots that meet
+      // the node tile's LOW parts (they carry W_hi), then the slots that meet its HIGH parts (they carry W_lo).
+      // Column c holds K slots 2 c (low half) and 2 c + 1.
+      constexpr int G = MODE == kPatch ? 2 : 4;
+      uint32_t cr[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int kap = 2 * c + e, grp = kap / (2 * G), i = kap % (2 * G);
+          const int feat = grp * G + (i % G);
+          v[e] = i < G ? __uint_as_float(hi[feat]) : __uint_as_float(lo[feat]);
+        }
+        cr[c] = pack_bf16x2(v[0], v[1]);
+      }
+      tmem_st32(ta + 128, cr);
+#endif
     }
     tmem_st_wait();
   }
@@ -420,7 +441,15 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
       split_tf32_op(acc.z, hi.z, lo.z);
       split_tf32_op(acc.w, hi.w, lo.w);
       sts4(a_hi + soff[i], hi);
+#ifdef EG_TF32X3
       sts4(a_hi + kTileBytes + soff[i], lo);
+#else
+      // correction tile (bf16, same 16 bytes): the four low parts, then the four values themselves
+      sts4(a_hi + kTileBytes + soff[i],
+           make_uint4(pack_bf16x2(__uint_as_float(lo.x), __uint_as_float(lo.y)),
+                      pack_bf16x2(__uint_as_float(lo.z), __uint_as_float(lo.w)), pack_bf16x2(acc.x, acc.y),
+                      pack_bf16x2(acc.z, acc.w)));
+#endif
     };
 
     if constexpr (MODE == kLinear) {
@@ -694,7 +723,12 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
         split_tf32_op(f2_lo(v), hi.x, lo.x);
         split_tf32_op(f2_hi(v), hi.y, lo.y);
         sts2(a_hi + off, hi);
+#ifdef EG_TF32X3
         sts2(a_hi + kTileBytes + off, lo);
+#else
+        sts2(a_hi + kTileBytes + off, make_uint2(pack_bf16x2(__uint_as_float(lo.x), __uint_as_float(lo.y)),
+                                                 pack_bf16x2(f2_lo(v), f2_hi(v))));
+#endif
       };
       uint32_t pbuf = 0;
       prefetch_patch(blockIdx.x, 0);
@@ -969,9 +1003,16 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
             const uint32_t w_hi = tmem_base + kc * 32 + ks * 8, w_lo = w_hi + 128;
             const uint32_t o = ks * 32;
 #ifndef EG_DBG_NOMMA
+#ifdef EG_TF32X3
             umma_tf32_ts(d, w_hi, umma_desc_k128(b_lo + o), idesc, (kc | ks) != 0);
             umma_tf32_ts(d, w_lo, umma_desc_k128(b_hi + o), idesc, 1u);
             umma_tf32_ts(d, w_hi, umma_desc_k128(b_hi + o), idesc, 1u);
+#else
+            // W_hi x A_hi in tf32 (exact products), then both correction terms W_hi x A_lo + W_lo x A_hi as ONE bf16
+            // MMA over 16 interleaved K slots: their operands only need 8 bits (each term is 2^-11 of the result)
+            umma_bf16_ts(d, w_lo, umma_desc_k128(b_lo + o), umma_idesc_bf16(128, 128), (kc | ks) != 0);
+            umma_tf32_ts(d, w_hi, umma_desc_k128(b_hi + o), idesc, 1u);
+#endif
 #endif
           }
           umma_commit(&empty[stage]);
