@@ -93,19 +93,23 @@ struct TilePlan {
 // Per K chunk a patch tile stages, with one TMA box copy each,
 //   P: the haloed patch, [10][18] lattice positions x 128 B (out-of-lattice positions arrive as zeros),
 //   Q: the [4][8] parents of the patch (coarser level),
-//   C: (patches with children only) four sub-stages of [4][32] child positions = the children of two patch rows.
+// The 2 x 2 children of a coarse node (patches of the aux levels) are NOT staged: the half-warp that owns a 2 x 2 block
+// reads its 16 child rows straight from global at the top of the chunk (16 LDG.64 per lane in flight across the wait for
+// the slot), so every tile costs one slot use per chunk and the ring stays four chunks ahead.
 // A compute half-warp owns a 2 x 2 block of the patch; its 4 x 6 lattice weights (up, left, right, down, parent, self;
 // 0 = no such edge) and 4 x 4 child weights are gcn_norm's dis[v] * dis[u], precomputed per block.
-constexpr int kPatchPRows = 10 * 18, kPatchQRows = 4 * 8, kPatchCRows = 4 * 32;
-struct alignas(16) PatchTile {  // 48 bytes
+constexpr int kPatchPRows = 10 * 18, kPatchQRows = 4 * 8;
+struct alignas(16) PatchTile {  // 64 bytes
   int32_t cls;              // 0 = patch, 1 = patch with children, 2 = CSR tile (rows summed from the device CSR)
   int32_t level;            // lattice level of the patch
   int32_t y0, x0;           // patch origin inside the level
   int32_t qlevel, qy, qx;   // parents: level (-1 = none) and origin of the 4 x 8 box
   int32_t clevel, cy, cx;   // children: level (-1 = none) and origin of the 16 x 32 box (may lie partly outside)
   int32_t node0, side;      // frame-local node id of lattice position (0, 0) and side of the level
+  int32_t cnode0, cside;    // same for the children level
+  int32_t pad_[2];
 };
-static_assert(sizeof(PatchTile) == 48, "PatchTile layout");
+static_assert(sizeof(PatchTile) == 64, "PatchTile layout");
 struct alignas(16) PatchBlockW {  // 160 bytes
   float wl[4][6];  // node (a, b, c, d) = ((0,0), (0,1), (1,0), (1,1)) of the block x (up, left, right, down, parent, self)
   float wc[4][4];  // node x child (2 ny + i, 2 nx + j) -> [i * 2 + j]

@@ -93,8 +93,19 @@ constexpr int kThreads = (kProdWarp0 + kProdWarps) * 32;  // 768 threads launche
 static_assert(kProdWarp0 == 8, "warpgroup layout of setmaxnreg");
 // Register budget by warpgroup (setmaxnreg): epilogue 72, MMA + loaders 56, the 16 compute warps 88
 // (each SM sub-partition hosts 1 + 1 + 4 of them: (72 + 56 + 4 x 88) x 32 lanes = 15360 <= 16384 registers).
-constexpr int kRegsCompute = 88, kRegsEpi = 72, kRegsLoad = 56;
-static_assert(4 * 32 * (kRegsEpi + kRegsLoad) + kProdWarps * 32 * kRegsCompute <= kThreads * 80, "register pool of the CTA");
+#ifndef EG_REGS_PATCH
+#define EG_REGS_PATCH 88, 80, 48
+#endif
+struct RegBudget {
+  int compute, epi, load;
+};
+constexpr RegBudget kRegsDefault{88, 72, 56};
+// patch mode: the loader warpgroup only hosts the MMA issuer and the one TMA thread (48 registers are plenty), which
+// lets the epilogue keep the launch's 80 (at 72 it spilled inside its slab loop as
+// soon as the compute code grew: r02x)
+constexpr RegBudget kRegsPatch{EG_REGS_PATCH};
+constexpr bool regs_fit(RegBudget r) { return 4 * 32 * (r.epi + r.load) + kProdWarps * 32 * r.compute <= 65536 && r.epi <= 80 && r.load <= 80; }
+static_assert(regs_fit(kRegsDefault) && regs_fit(kRegsPatch), "register pool of the SM (64 K registers, launched at 80 per thread)");
 constexpr int kTileBytes = 128 * 128;      // one [128 rows x 32 tf32] operand tile
 constexpr uint32_t kABytes = kStages * 2 * kTileBytes;
 // Kernel modes: plain per-node transform / gather plan (any graph: cp.async row copies, per-row slot plan) / patch plan
@@ -120,12 +131,11 @@ struct Lay {
                             kOffRawEmpty = kOffRawFull + 8 * kRawStages;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory of one CTA");
 };
-static_assert(kPatchCRows * 128 <= Lay<kPatch>::kRawBytes && kPatchPRows * 128 % 128 == 0, "patch slot layout");
 constexpr int kTmemCols = 512;             // [0,128) W hi, [128,256) W lo, [256,384) / [384,512) accumulators
 constexpr uint32_t kTmemAcc = 256;
 static_assert(kPlanSrc % (kLoadWarps * 4) == 0 && kPlanSrc >= 128, "loader mapping");
 
-struct PatchMaps {  // tensor maps of the node tensor, per lattice level: [3 l + 0 / 1 / 2] = P / Q / C box (see PatchTile)
+struct PatchMaps {  // tensor maps of the node tensor, per lattice level: [3 l + 0 / 1] = P / Q box (see PatchTile)
   CUtensorMap m[3 * EG_MAX_LEVELS];
 };
 
@@ -236,6 +246,147 @@ __device__ __forceinline__ void fma4_x2(float4& acc, float w, const float4& x) {
 // 128-bit load of a far (not staged) source row slice: read once per SM, so it bypasses the ~28 KB of L1 left beside
 // the 203 KB of shared memory (ld.global.cg; measured -1 % against ld.global.nc, L1::no_allocate +4 %).
 __device__ __forceinline__ float4 ld_far(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ int lane_id() {
+  int l;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+  return l;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// child rows: read once per SM, straight from L2 (no L1 allocation)
+__device__ __forceinline__ F2 ldcg_f2(const float* p) {
+  const float2 v = __ldcg(reinterpret_cast<const float2*>(p));
+  return f2_pack(v.x, v.y);
+}
+// 3xTF32 operand split of a packed pair -> operand tiles (see emit in tc_body for the layout of the correction tile)
+__device__ __forceinline__ void emit_pair(uint32_t a_hi, uint32_t off, F2 v) {
+#ifdef EG_DBG_NOEMIT
+  if (f2_lo(v) == 123.456f) sts2(a_hi + off, make_uint2(0, 0));
+  return;
+#endif
+  uint2 hi, lo;
+  split_tf32_op(f2_lo(v), hi.x, lo.x);
+  split_tf32_op(f2_hi(v), hi.y, lo.y);
+  sts2(a_hi + off, hi);
+#ifdef EG_TF32X3
+  sts2(a_hi + kTileBytes + off, lo);
+#else
+  sts2(a_hi + kTileBytes + off, make_uint2(pack_bf16x2(__uint_as_float(lo.x), __uint_as_float(lo.y)),
+                                           pack_bf16x2(f2_lo(v), f2_hi(v))));
+#endif
+}
+
+// ---- patch mode, one tile WITH CHILDREN, as a function of its own --------------------------------------------------
+// The 2 x 2 children of the block's four nodes (a 4 x 4 window of the finer level) are not staged: 16 LDG.64 per lane,
+// issued one chunk AHEAD -- right after the previous chunk's sums, when the 13 staged rows are dead -- so the operand
+// stores / fence / barrier round trip cover most of their L2 latency; they are summed first, before the staged rows are
+// loaded.  Children exist per NODE (all four or none): a zero weight marks a node without (crop border).
+// __noinline__ on purpose: inlined into the tile loop, its 32 registers of loads in flight made the compiler spill
+// kernel-wide values (the lane id, ring addresses) that the plain tiles and the MMA issuer then re-loaded from local
+// memory on their critical paths (plain tiles +25 %, r02r-w).
+struct AuxTileArgs {
+  const float* cwin;   // first child row of the block's window, this lane's 2 features, chunk 0
+  float* agg_a;        // A_hat dH side output (backward) of node a, or nullptr
+  uint32_t wlu;        // shared address of the block's weights: wl[4][6], wc[4][4]
+  uint32_t pb, qb;     // shared offsets of P[0][0] / the parent row of the block inside a slot (slot base not added)
+  uint32_t so_a, so_b; // operand-tile offsets of tile rows a and b (c, d: + 2048)
+  int cside, side;     // sides of the children level / the patch level
+  uint32_t use, chunk; // ring counters (in / out)
+};
+template <uint32_t kRawStagesT, uint32_t kRawBytesT, uint32_t kOffRawFullT, uint32_t kOffRawEmptyT, uint32_t kOffFullT,
+          uint32_t kOffEmptyT>
+#ifndef EG_AUX_INLINE
+#define EG_AUX_INLINE __forceinline__
+#endif
+__device__ EG_AUX_INLINE void patch_aux_tile(AuxTileArgs& a) {
+  constexpr uint32_t sm = 0x400;
+  const int lane = lane_id();
+  uint32_t use = a.use, chunk = a.chunk;
+  const uint32_t wlu = a.wlu;
+  const float* cwin = a.cwin;
+  const int cside = a.cside;
+  uint32_t has = 0;
+#pragma unroll
+  for (int n = 0; n < 4; ++n) has |= (__uint_as_float(lds_u32(wlu + 96 + n * 16)) != 0.f ? 1u : 0u) << n;
+  F2 ch[16];
+  auto load_children = [&](int kc) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = 2 * (n >> 1) + (k >> 1), c = 2 * (n & 1) + (k & 1);
+#ifdef EG_PD_NOCHILD
+        ch[n * 4 + k] = f2_pack(0.f, 0.f);
+#else
+        ch[n * 4 + k] = (has >> n & 1u) ? ldcg_f2(cwin + ((long long)r * cside + c) * 128 + kc * 32) : f2_pack(0.f, 0.f);
+#endif
+      }
+    }
+  };
+  load_children(0);
+#pragma unroll 1
+  for (int kc = 0; kc < 4; ++kc) {
+    const uint32_t rs = use % kRawStagesT;
+    mbar_wait_a(sm + kOffRawFullT + rs * 8, (use / kRawStagesT) & 1u);
+    const uint32_t ro = rs * kRawBytesT;
+    F2 aa = f2_pack(0.f, 0.f), ab = aa, ac = aa, ad = aa;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const float4 wc = lds4(wlu + 96 + n * 16);
+      F2& acc = n == 0 ? aa : n == 1 ? ab : n == 2 ? ac : ad;
+      fma2(acc, wc.x, ch[n * 4]), fma2(acc, wc.y, ch[n * 4 + 1]), fma2(acc, wc.z, ch[n * 4 + 2]), fma2(acc, wc.w, ch[n * 4 + 3]);
+    }
+    {
+      const uint32_t pa = a.pb + ro;
+      const F2 p01 = lds_f2(pa + (0 * 18 + 1) * 128), p02 = lds_f2(pa + (0 * 18 + 2) * 128);
+      const F2 p10 = lds_f2(pa + (1 * 18 + 0) * 128), p11 = lds_f2(pa + (1 * 18 + 1) * 128);
+      const F2 p12 = lds_f2(pa + (1 * 18 + 2) * 128), p13 = lds_f2(pa + (1 * 18 + 3) * 128);
+      const F2 p20 = lds_f2(pa + (2 * 18 + 0) * 128), p21 = lds_f2(pa + (2 * 18 + 1) * 128);
+      const F2 p22 = lds_f2(pa + (2 * 18 + 2) * 128), p23 = lds_f2(pa + (2 * 18 + 3) * 128);
+      const F2 p31 = lds_f2(pa + (3 * 18 + 1) * 128), p32 = lds_f2(pa + (3 * 18 + 2) * 128);
+      const F2 pq = lds_f2(a.qb + ro);
+      {
+        const float4 w0 = lds4(wlu), w1 = lds4(wlu + 16), w2 = lds4(wlu + 32);  // wl[0][0..5], wl[1][0..5]
+        fma2(aa, w0.x, p01), fma2(aa, w0.y, p10), fma2(aa, w0.z, p12), fma2(aa, w0.w, p21), fma2(aa, w1.x, pq), fma2(aa, w1.y, p11);
+        fma2(ab, w1.z, p02), fma2(ab, w1.w, p11), fma2(ab, w2.x, p13), fma2(ab, w2.y, p22), fma2(ab, w2.z, pq), fma2(ab, w2.w, p12);
+      }
+      {
+        const float4 w3 = lds4(wlu + 48), w4 = lds4(wlu + 64), w5 = lds4(wlu + 80);  // wl[2][0..5], wl[3][0..5]
+        fma2(ac, w3.x, p11), fma2(ac, w3.y, p20), fma2(ac, w3.z, p22), fma2(ac, w3.w, p31), fma2(ac, w4.x, pq), fma2(ac, w4.y, p21);
+        fma2(ad, w4.z, p12), fma2(ad, w4.w, p21), fma2(ad, w5.x, p23), fma2(ad, w5.y, p32), fma2(ad, w5.z, pq), fma2(ad, w5.w, p22);
+      }
+    }
+    asm volatile("" : "+l"(aa.u), "+l"(ab.u), "+l"(ac.u), "+l"(ad.u) : : "memory");  // the slot's loads have landed
+    __syncwarp();
+    if (lane == 0) mbar_arrive_a(sm + kOffRawEmptyT + rs * 8);
+    ++use;
+    if (kc < 3) load_children(kc + 1);
+    const uint32_t stage = chunk % kStages;
+    mbar_wait_a(sm + kOffEmptyT + stage * 8, ((chunk / kStages) & 1u) ^ 1u);
+    const uint32_t a_hi = sm + stage * 2 * kTileBytes;
+    emit_pair(a_hi, a.so_a, aa);
+    emit_pair(a_hi, a.so_b, ab);
+    emit_pair(a_hi, a.so_a + 2048, ac);
+    emit_pair(a_hi, a.so_b + 2048, ad);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_a(sm + kOffFullT + stage * 8);
+    ++chunk;
+    if (a.agg_a) {
+      float* o = a.agg_a + kc * 32;
+      st_f2(o, aa);
+      st_f2(o + 128, ab);
+      st_f2(o + (long long)a.side * 128, ac);
+      st_f2(o + (long long)a.side * 128 + 128, ad);
+    }
+  }
+  a.use = use;
+  a.chunk = chunk;
+}
 
 template <int MODE>
 __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) {
@@ -356,11 +507,12 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
 
   // one setmaxnreg per warpgroup: warps 0-7 release registers, warps 8-23 take them
   if (warp >= kProdWarp0) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsCompute));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MODE == kPatch ? kRegsPatch.compute : kRegsDefault.compute));
   } else if (warp < kEpiWarps) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
+    if constexpr ((MODE == kPatch ? kRegsPatch.epi : kRegsDefault.epi) < 80)
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MODE == kPatch ? kRegsPatch.epi : kRegsDefault.epi));
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLoad));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MODE == kPatch ? kRegsPatch.load : kRegsDefault.load));
   }
 #ifdef EG_TC_TIMING
   dbg_acc[6] = clock64() - dbg_t0;  // one-time setup (TMEM allocation, weight -> TMEM, barriers)
@@ -662,7 +814,6 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
       asm volatile("" : "+r"(so_a), "+r"(so_b));
       const uint32_t pb = sm + kOffRaw + (2 * by * 18 + 2 * bx) * 128 + l16 * 8;  // P[0][0] of the block's 4 x 4 window
       const uint32_t qb = sm + kOffRaw + kPatchPRows * 128 + (by * 8 + bx) * 128 + l16 * 8;
-      const uint32_t cb = sm + kOffRaw + 4 * bx * 128 + l16 * 8;  // children window inside a C sub-stage ([4][32] rows)
       const bool agg_out = p.AggOut != nullptr;
       auto prefetch_patch = [&](int tile, uint32_t buf) {
         if (tile >= p.num_tiles) return;
@@ -671,7 +822,7 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.patch.blocks + (size_t)t * 32 + pw * 2);
         const uint8_t* tsrc = reinterpret_cast<const uint8_t*>(p.patch.tiles + t);
         if (lane < 20) cp_async16(dst + lane * 16, wsrc + lane * 16);
-        else if (lane < 23) cp_async16(dst + lane * 16, tsrc + (lane - 20) * 16);
+        else if (lane < 24) cp_async16(dst + lane * 16, tsrc + (lane - 20) * 16);
       };
       uint32_t use = 0;  // raw-slot uses so far (the producer counts the same sequence)
       auto wait_raw = [&]() -> uint32_t {
@@ -714,22 +865,7 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
         if (lane == 0) mbar_arrive_a(sm + kOffFull + (chunk % kStages) * 8);
         ++chunk;
       };
-      auto emit2 = [&](uint32_t a_hi, uint32_t off, F2 v) {
-#ifdef EG_DBG_NOEMIT
-        if (f2_lo(v) == 123.456f) sts2(a_hi + off, make_uint2(0, 0));
-        return;
-#endif
-        uint2 hi, lo;
-        split_tf32_op(f2_lo(v), hi.x, lo.x);
-        split_tf32_op(f2_hi(v), hi.y, lo.y);
-        sts2(a_hi + off, hi);
-#ifdef EG_TF32X3
-        sts2(a_hi + kTileBytes + off, lo);
-#else
-        sts2(a_hi + kTileBytes + off, make_uint2(pack_bf16x2(__uint_as_float(lo.x), __uint_as_float(lo.y)),
-                                                 pack_bf16x2(f2_lo(v), f2_hi(v))));
-#endif
-      };
+      auto emit2 = [&](uint32_t a_hi, uint32_t off, F2 v) { emit_pair(a_hi, off, v); };
       uint32_t pbuf = 0;
       prefetch_patch(blockIdx.x, 0);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, pbuf ^= 1u) {
@@ -742,6 +878,25 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
         const float4 d0 = lds4(pl + 320), d2 = lds4(pl + 352);
         const int cls = __float_as_int(d0.x), y0 = __float_as_int(d0.z), x0 = __float_as_int(d0.w);
         const int node0 = __float_as_int(d2.z), side = __float_as_int(d2.w);
+#ifndef EG_PD_PLAINAUX
+        if (cls == 1) {  // patch with children: a function of its own (see patch_aux_tile)
+          const float4 d3 = lds4(pl + 368);
+          const int cy = __float_as_int(d2.x), cx = __float_as_int(d2.y);
+          const int cnode0 = __float_as_int(d3.x), cside = __float_as_int(d3.y);
+          AuxTileArgs a;
+          a.cwin = p.X + (frow0 + cnode0 + (long long)(cy + 4 * by) * cside + cx + 4 * bx) * 128 + l16 * 2;
+          a.agg_a = agg_out ? p.AggOut + (frow0 + node0 + (long long)(y0 + 2 * by) * side + x0 + 2 * bx) * 128 + l16 * 2
+                            : nullptr;
+          a.wlu = pl + h * 160;
+          a.pb = pb, a.qb = qb, a.so_a = so_a, a.so_b = so_b;
+          a.cside = cside, a.side = side;
+          a.use = use, a.chunk = chunk;
+          prefetch_patch(tile + gridDim.x, pbuf ^ 1u);
+          patch_aux_tile<kRawStages, kRawBytes, kOffRawFull, kOffRawEmpty, kOffFull, kOffEmpty>(a);
+          use = a.use, chunk = a.chunk;
+          continue;
+        }
+#endif
         if (cls == 2) {
           // ---- CSR tile (ragged small lattices, coordinate nodes): rows summed straight from the device CSR
           prefetch_patch(tile + gridDim.x, pbuf ^ 1u);
@@ -777,7 +932,7 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
                                : nullptr;
 #pragma unroll 1
         for (int kc = 0; kc < 4; ++kc) {
-          uint32_t ro = wait_raw();
+          const uint32_t ro = wait_raw();
           const uint32_t pa = pb + ro;
 #ifdef EG_PD_NOGATHER
 #define lds_f2x(a) f2_pack(1.f, 2.f)
@@ -799,35 +954,6 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
           fma2(ad, wl[18], p12), fma2(ad, wl[19], p21), fma2(ad, wl[20], p23), fma2(ad, wl[21], p32), fma2(ad, wl[22], pq), fma2(ad, wl[23], p22);
           asm volatile("" : "+l"(aa.u), "+l"(ab.u), "+l"(ac.u), "+l"(ad.u) : : "memory");  // the slot's loads have landed
           release_raw();
-#ifdef EG_PD_PLAINAUX
-          if (false) {
-#else
-          if (cls == 1) {
-#endif
-#pragma unroll 1
-            for (int sub = 0; sub < 4; ++sub) {  // sub-stage `sub` = children of patch rows 2 sub, 2 sub + 1
-              ro = wait_raw();
-#ifdef EG_PD_NOCHILD
-              if (false) {
-#else
-              if (sub == by) {
-#endif
-                const uint32_t ca = cb + ro;
-                const uint32_t wcu = pl + h * 160 + 96;
-#pragma unroll
-                for (int n = 0; n < 4; ++n) {  // node n = (ny, nx): children rows 2 ny + i, columns 2 nx + j of the window
-                  const int ny = n >> 1, nx = n & 1;
-                  const float4 wc = lds4(wcu + n * 16);
-                  const F2 c0 = lds_f2(ca + ((2 * ny) * 32 + 2 * nx) * 128), c1 = lds_f2(ca + ((2 * ny) * 32 + 2 * nx + 1) * 128);
-                  const F2 c2 = lds_f2(ca + ((2 * ny + 1) * 32 + 2 * nx) * 128), c3 = lds_f2(ca + ((2 * ny + 1) * 32 + 2 * nx + 1) * 128);
-                  F2& acc = n == 0 ? aa : n == 1 ? ab : n == 2 ? ac : ad;
-                  fma2(acc, wc.x, c0), fma2(acc, wc.y, c1), fma2(acc, wc.z, c2), fma2(acc, wc.w, c3);
-                }
-                asm volatile("" : "+l"(aa.u), "+l"(ab.u), "+l"(ac.u), "+l"(ad.u) : : "memory");
-              }
-              release_raw();
-            }
-          }
           const uint32_t a_hi = wait_op();
           emit2(a_hi, so_a, aa);
           emit2(a_hi, so_b, ab);
@@ -876,13 +1002,12 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
         int4 na = make_int4(2, 0, 0, 0), nb = na, nc = na;
         load_desc(blockIdx.x, na, nb, nc);
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-          const int4 ta = na, tb = nb, tcd = nc;  // {cls, level, y0, x0} {qlevel, qy, qx, clevel} {cy, cx, node0, side}
+          const int4 ta = na, tb = nb;  // {cls, level, y0, x0} {qlevel, qy, qx, clevel}
           load_desc(tile + gridDim.x, na, nb, nc);
           if (ta.x == 2) continue;
           const int b = tile / p.tiles_per_frame;
           const CUtensorMap* mp = &pm->m[3 * ta.y];
           const CUtensorMap* mq = tb.x >= 0 ? &pm->m[3 * tb.x + 1] : nullptr;
-          const CUtensorMap* mc = tb.w >= 0 ? &pm->m[3 * tb.w + 2] : nullptr;
 #pragma unroll 1
           for (int kc = 0; kc < 4; ++kc) {
             uint32_t dst, bar;
@@ -891,19 +1016,6 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
             tma_load_4d(dst, mp, kc * 32, ta.w - 1, ta.z - 1, b, bar);
             if (mq) tma_load_4d(dst + kPatchPRows * 128, mq, kc * 32, tb.z, tb.y, b, bar);
 #endif
-#ifdef EG_PD_PLAINAUX
-            if (false) {
-#else
-            if (ta.x == 1) {
-#endif
-#pragma unroll 1
-              for (int sub = 0; sub < 4; ++sub) {
-                slot_acquire(kPatchCRows * 128, dst, bar);
-#ifndef EG_PD_NOTMA
-                tma_load_4d(dst, mc, kc * 32, tcd.y, tcd.x + 4 * sub, b, bar);
-#endif
-              }
-            }
           }
         }
       }
@@ -984,6 +1096,7 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
       }
     }
   } else if (warp == kMmaWarp) {
+    const int lane = lane_id();  // fresh read: keeps the issuer's only use of the lane out of the kernel-wide live set
     // ===== MMA issuer ======================================================================================
     constexpr uint32_t idesc = umma_idesc_tf32(128, 128, 0, 0);
     uint32_t chunk = 0, it = 0;
@@ -1260,13 +1373,13 @@ int encode_patch_maps(const eg_graph_info& info, int batch, const float* X, Patc
     set_error("cuTensorMapEncodeTiled is not available from this driver");
     return EG_ERR_CUDA;
   }
-  static const cuuint32_t kBox[3][2] = {{18, 10}, {8, 4}, {32, 4}};  // P, Q, C: (x, y) extent
+  static const cuuint32_t kBox[2][2] = {{18, 10}, {8, 4}};  // P, Q: (x, y) extent
   for (int l = 0; l < info.num_levels; ++l) {
     const cuuint64_t side = (cuuint64_t)info.level_size[l];
     const cuuint64_t dims[4] = {128, side, side, (cuuint64_t)batch};
     const cuuint64_t strides[3] = {512, side * 512, (cuuint64_t)info.num_nodes * 512};
     void* base = const_cast<float*>(X) + (size_t)info.level_offset[l] * 128;
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 2; ++k) {
       const cuuint32_t box[4] = {32, kBox[k][0], kBox[k][1], 1};
       const cuuint32_t estr[4] = {1, 1, 1, 1};
       const CUresult r = enc(&out.m[3 * l + k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr,

@@ -154,13 +154,35 @@ std::vector<int32_t> build_tiles(const Topo& t) {
   for (int v = t.N - t.ncoord; v < t.N; ++v) push_misc(v);
   close_group();
   while (tiles.size() % 128) tiles.push_back(-1);
+  // patches: (level, a0, b0), level by level ...
+  struct Patch { int l, a0, b0; };
+  std::vector<Patch> coarse, fine;  // patches of the aux levels / of the main level
   for (int l = 0; l < t.nlev; ++l) {
-    const int p = t.lsize[l], off = t.loff[l];
+    const int p = t.lsize[l];
     if (p % 16 != 0) continue;
     for (int a0 = 0; a0 < p; a0 += 8)
-      for (int b0 = 0; b0 < p; b0 += 16)
-        for (int a = a0; a < a0 + 8; ++a)
-          for (int b = b0; b < b0 + 16; ++b) tiles.push_back(off + a * p + b);
+      for (int b0 = 0; b0 < p; b0 += 16) (l == t.nlev - 1 ? fine : coarse).push_back({l, a0, b0});
+  }
+  // ... in table order (aux levels, then the main level), or -- EG_TILE_ORDER=spread -- the aux patches spread evenly
+  // among the main patches: an aux patch pulls 3x the bytes of a main patch through the SM's L2 port (its 512 child
+  // rows), and with all SMs on aux patches at the same time the L2 is the limit
+  std::vector<Patch> order;
+  const char* ord = getenv("EG_TILE_ORDER");
+  if (ord && strcmp(ord, "spread") == 0 && !coarse.empty() && !fine.empty()) {
+    const size_t T2 = coarse.size() + fine.size();
+    size_t ci = 0, fi = 0;
+    for (size_t i = 0; i < T2; ++i) {
+      const bool take_coarse = ci < coarse.size() && (fi >= fine.size() || ci * T2 <= i * coarse.size());
+      order.push_back(take_coarse ? coarse[ci++] : fine[fi++]);
+    }
+  } else {
+    order = coarse;
+    order.insert(order.end(), fine.begin(), fine.end());
+  }
+  for (const Patch& q : order) {
+    const int p = t.lsize[q.l], off = t.loff[q.l];
+    for (int a = q.a0; a < q.a0 + 8; ++a)
+      for (int b = q.b0; b < q.b0 + 16; ++b) tiles.push_back(off + a * p + b);
   }
   return tiles;
 }
@@ -307,16 +329,20 @@ HostPatchPlan build_patch_plan(const Topo& t, const std::vector<int32_t>& tiles)
     pp.ok = 0;
     return pp;
   }
-  for (int l = 0; l < t.nlev; ++l) {
-    const int p = t.lsize[l], off = t.loff[l];
-    if (p % 16 != 0) continue;
-    const bool is_main = l == main_l;
-    for (int y0 = 0; y0 < p; y0 += 8)
-      for (int x0 = 0; x0 < p; x0 += 16, ++ti) {
-        if (ti >= T || tiles[(size_t)ti * 128] != off + y0 * p + x0) {  // tile table and patch order disagree
-          pp.ok = 0;
-          return pp;
-        }
+  for (; ti < T; ++ti) {
+    {
+      // the patch of this tile, from its first node (the order of the patches in the table is free)
+      const int v0 = tiles[(size_t)ti * 128];
+      int l = t.nlev - 1;
+      while (l > 0 && v0 < t.loff[l]) --l;
+      const int p = t.lsize[l], off = t.loff[l];
+      const int y0 = v0 < off ? -1 : (v0 - off) / p, x0 = v0 < off ? -1 : (v0 - off) % p;
+      if (v0 < off || p % 16 != 0 || y0 % 8 != 0 || x0 % 16 != 0 || y0 + 8 > p) {
+        pp.ok = 0;
+        return pp;
+      }
+      const bool is_main = l == main_l;
+      {
         PatchTile& pt = pp.tiles[ti];
         pt.level = l;
         pt.y0 = y0;
@@ -346,6 +372,8 @@ HostPatchPlan build_patch_plan(const Topo& t, const std::vector<int32_t>& tiles)
             pt.cy = 2 * (y0 - t.crop);
             pt.cx = 2 * (x0 - t.crop);
           }
+          pt.cnode0 = t.loff[pt.clevel];
+          pt.cside = t.lsize[pt.clevel];
         }
         bool any_child = false;
         for (int q = 0; q < 32; ++q) {
@@ -380,6 +408,7 @@ HostPatchPlan build_patch_plan(const Topo& t, const std::vector<int32_t>& tiles)
         pt.cls = any_child ? 1 : 0;
         if (!any_child) pt.clevel = -1;
       }
+    }
   }
   if (ti != T) pp.ok = 0;
   return pp;
