@@ -72,6 +72,7 @@ SIGNATURES = {
     "eg_graph_tiles": (_I, [_P, C.POINTER(_P), C.POINTER(C.c_int32)]),
     "eg_graph_plan_check": (_I, [C.POINTER(GraphSpec), C.POINTER(C.c_int64)]),
     "eg_graph_patch_check": (_I, [C.POINTER(GraphSpec), C.POINTER(C.c_int64)]),
+    "eg_gcn_plan_select": (_I, [_I]),
     "eg_graph_export_edge_index": (_I, [_P, _I, _P, _P]),
     "eg_graph_host_edge_index": (_I, [C.POINTER(GraphSpec), _I, _P]),
     "eg_graph_host_node_type": (_I, [C.POINTER(GraphSpec), _I, _P]),

@@ -1394,16 +1394,26 @@ int encode_patch_maps(const eg_graph_info& info, int batch, const float* X, Patc
   return EG_OK;
 }
 
-// EG_GCN_PLAN=gather forces the gather plan (development / A-B timing); default: the patch plan wherever it applies
+// Plan selection: 0 = automatic (the patch plan wherever the graph allows it), 1 = always the gather plan.  Initialised
+// from EG_GCN_PLAN=gather (development / A-B timing); eg_gcn_plan_select() switches it at run time (parity tests run
+// both plans on the same inputs).
+std::atomic<int> g_plan_mode{-1};
 bool patch_plan_enabled() {
-  static const bool on = [] {
+  int m = g_plan_mode.load(std::memory_order_relaxed);
+  if (m < 0) {
     const char* e = getenv("EG_GCN_PLAN");
-    return !(e && strcmp(e, "gather") == 0);
-  }();
-  return on;
+    m = (e && strcmp(e, "gather") == 0) ? 1 : 0;
+    g_plan_mode.store(m, std::memory_order_relaxed);
+  }
+  return m == 0;
 }
 
 }  // namespace
+
+extern "C" int eg_gcn_plan_select(int mode) {
+  patch_plan_enabled();  // resolve the environment default first
+  return g_plan_mode.exchange(mode ? 1 : 0, std::memory_order_relaxed);
+}
 
 #ifdef EG_TC_TIMING
 extern "C" int eg_tc_debug_read(long long* out) {  // HOST buffer of kNumSMs * 16 counters

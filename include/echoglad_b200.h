@@ -86,6 +86,12 @@ int eg_graph_tiles(const eg_graph* g, const int32_t** tile_nodes, int32_t* tiles
  * class of the fused kernel (lattice, general).  Returns the number of
  * violations (0 = consistent) or a negative EG_ERR_* code. */
 int eg_graph_plan_check(const eg_graph_spec* spec, int64_t* stats);
+/* The fused GCN kernel has two staging plans: the PATCH plan (regular 4-neighbour lattices: TMA box copies of the haloed
+ * 8x16 patch + parents, 2x2 node blocks) and the GATHER plan (any graph: per-row slot plan, cp.async row copies).
+ * mode 0 = automatic (patch wherever the graph allows it; the default, or EG_GCN_PLAN=gather in the environment),
+ * 1 = always gather.  Returns the previous mode.  Same results either way (within the summation-order tolerance):
+ * a test / A-B hook, not a tuning knob. */
+int eg_gcn_plan_select(int mode);
 /* Host-only consistency check of the PATCH plan (the TMA path of the fused kernel on regular 4-neighbour lattices:
  * haloed 8x16 patch + parents + children staged by tensor-map box copies, one 2x2 node block per half-warp): the
  * sources every patch node reads through its box positions and their weights against the closed-form neighbour

@@ -191,12 +191,23 @@ def test_aggregate_full_graph_linearity_and_symmetry():
     (dict(use_connection_nodes=True), 2),                              # hub rows (CSR rows of the gather plan)
     (dict(main_graph_type="grid-diagonal", aux_graph_type="grid-diagonal"), 2),
 ])
-def test_fused_gcn_kernel_equals_csr_composition_at_full_size(kw, batch):
+@pytest.mark.parametrize("plan", ["auto", "gather"])
+def test_fused_gcn_kernel_equals_csr_composition_at_full_size(kw, batch, plan):
     """At the full graph sizes of BASELINE.json's configs the fused tcgen05 kernel (tile plan, shared-memory
     gather, tensor-core transform) must agree with the composition of the two independent kernels of the library
     (CSR segmented aggregation `eg_gcn_aggregate`, then `eg_linear128`), which the small-graph tests pin to the
     oracle element by element: forward H and BatchNorm statistics, backward dX, the A_hat dH side output and dW.
+    Both staging plans of the fused kernel run: `auto` = the patch plan (TMA box copies, 2x2 blocks) on the regular
+    lattices and the gather plan on hubs / diagonal lattices; `gather` = the gather plan everywhere.
     Tolerance: |a-b| <= 1e-4 |b| + 1e-5 max|b| (both sides are fp32-class; summation orders differ)."""
+    prev = ops.lib.eg_gcn_plan_select(1 if plan == "gather" else 0)
+    try:
+        _fused_vs_csr(kw, batch)
+    finally:
+        ops.lib.eg_gcn_plan_select(prev)
+
+
+def _fused_vs_csr(kw, batch):
     spec = eg.HierGraphSpec(**kw)
     g = eg.DeviceGraph.get(spec, DEV)
     n = g.meta.num_nodes
