@@ -7,7 +7,6 @@
 #include <string.h>
 
 #include <algorithm>
-#include <functional>
 #include <cmath>
 #include <utility>
 #include <vector>
@@ -164,61 +163,12 @@ std::vector<int32_t> build_tiles(const Topo& t) {
     for (int a0 = 0; a0 < p; a0 += 8)
       for (int b0 = 0; b0 < p; b0 += 16) (l == t.nlev - 1 ? fine : coarse).push_back({l, a0, b0});
   }
-  // ... level by level (default).  EG_TILE_ORDER=tree / spread: two interleavings of the aux patches with the main
-  // patches, both measured slower (kept for A/B runs)
-  std::vector<Patch> order;
-  const char* ord = getenv("EG_TILE_ORDER");
-  if (ord && strcmp(ord, "tree") == 0 && !coarse.empty() && !fine.empty()) {
-    // EG_TILE_ORDER=tree: depth-first over the patch pyramid -- a patch, then the (up to) 2 x 2 patches of the finer
-    // level that hold its children, recursively, so that a coarse patch and the patches of its children run at the
-    // same time on neighbouring SMs of the persistent grid.  Meant to make the second read of the main-level rows
-    // (once as children, once as own rows: 5.9 GB of DRAM traffic per launch against 4.7 GB algorithmic) an L2 hit;
-    // measured: DRAM reads unchanged (3.66 against 3.54 GB), forward 1.31 against 1.28 ms (r02z) -- not the default.
-    std::vector<int> pl;  // patch levels, coarse to fine
-    for (int l = 0; l < t.nlev; ++l)
-      if (t.lsize[l] % 16 == 0) pl.push_back(l);
-    std::function<void(int, int, int)> dfs = [&](int li, int ty, int tx) {
-      const int l = pl[li];
-      order.push_back({l, ty * 8, tx * 16});
-      if (li + 1 >= (int)pl.size()) return;
-      const int lc = pl[li + 1], pc = t.lsize[lc];
-      const bool to_main = lc == t.nlev - 1;
-      // child tiles: rows 2 ty .. 2 ty + 1, columns 2 tx .. 2 tx + 1, shifted by the crop window towards the main level
-      const int cy0 = to_main ? 2 * (ty * 8 - t.crop) : 2 * ty * 8, cx0 = to_main ? 2 * (tx * 16 - t.crop) : 2 * tx * 16;
-      for (int y = cy0; y < cy0 + 16; y += 8)
-        for (int x = cx0; x < cx0 + 32; x += 16) {
-          // the finer patch at (y, x) belongs to this patch iff its FIRST node's parent lies in it (every finer
-          // patch has exactly one such parent patch, also when the crop shift is not a multiple of the patch size)
-          const int yy = ((y % 8) + 8) % 8 ? y - (((y % 8) + 8) % 8) : y, xx = ((x % 16) + 16) % 16 ? x - (((x % 16) + 16) % 16) : x;
-          if (yy < 0 || xx < 0 || yy >= pc || xx >= pc) continue;
-          const int py = to_main ? t.crop + yy / 2 : yy / 2, px = to_main ? t.crop + xx / 2 : xx / 2;
-          if (py / 8 != ty || px / 16 != tx) continue;
-          bool seen = false;
-          for (const Patch& q : order) seen = seen || (q.l == lc && q.a0 == yy && q.b0 == xx);
-          if (!seen) dfs(li + 1, yy / 8, xx / 16);
-        }
-    };
-    const int p0 = t.lsize[pl[0]];
-    for (int ty = 0; ty < p0 / 8; ++ty)
-      for (int tx = 0; tx < p0 / 16; ++tx) dfs(0, ty, tx);
-    // finer patches no coarse patch claimed (cannot happen for the reference's pyramids; keeps the table complete)
-    for (const std::vector<Patch>* src : {&coarse, &fine})
-      for (const Patch& q : *src) {
-        bool seen = false;
-        for (const Patch& o : order) seen = seen || (o.l == q.l && o.a0 == q.a0 && o.b0 == q.b0);
-        if (!seen) order.push_back(q);
-      }
-  } else if (ord && strcmp(ord, "spread") == 0 && !coarse.empty() && !fine.empty()) {
-    const size_t T2 = coarse.size() + fine.size();
-    size_t ci = 0, fi = 0;
-    for (size_t i = 0; i < T2; ++i) {
-      const bool take_coarse = ci < coarse.size() && (fi >= fine.size() || ci * T2 <= i * coarse.size());
-      order.push_back(take_coarse ? coarse[ci++] : fine[fi++]);
-    }
-  } else {
-    order = coarse;
-    order.insert(order.end(), fine.begin(), fine.end());
-  }
+  // ... level by level, coarse to fine.  Three other orders were measured on B200 (r02z, forward at batch 64) and
+  // dropped: the aux patches spread evenly among the main patches (1.36 ms against 1.30), depth-first over the patch
+  // pyramid (a patch followed by the patches of its children: 1.31 ms, DRAM reads 3.66 against 3.54 GB) and fine to
+  // coarse with the coarse patch one round behind its children (1.36 ms, DRAM reads 4.16 GB).
+  std::vector<Patch> order = coarse;
+  order.insert(order.end(), fine.begin(), fine.end());
   for (const Patch& q : order) {
     const int p = t.lsize[q.l], off = t.loff[q.l];
     for (int a = q.a0; a < q.a0 + 8; ++a)
