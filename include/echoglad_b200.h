@@ -179,7 +179,7 @@ int eg_dropout_mask(int64_t rows, int cols, float drop_p, uint64_t seed, float* 
 int eg_col_stats(int64_t rows, int cols, const float* Z, float* mean, float* var, void* ws, size_t ws_bytes,
                  void* stream);
 
-/* ---- dense per-node transforms (tensor cores, 3xTF32 error-compensated => fp32-class accuracy) -----
+/* ---- dense per-node transforms (tensor cores, split precision: tf32 main term + bf16 correction terms, fp32 accumulate => fp32-class accuracy, within 2e-6 of fp64) -----
  * replaces nn.Linear inside GCNConv.lin and node_classifiers[k][0] stacked over k
  * (src/core/models.py:330,364).  C[rows,128] = A[rows,128] * op(W) + bias, op(W) = W^T when
  * trans_w != 0 (nn.Linear forward), W otherwise (its input gradient).  mean/var optional as above. */
