@@ -93,32 +93,49 @@ struct TilePlan {
 // Per K chunk a patch tile stages, with one TMA box copy each,
 //   P: the haloed patch, [10][18] lattice positions x 128 B (out-of-lattice positions arrive as zeros),
 //   Q: the [4][8] parents of the patch (coarser level),
-// The 2 x 2 children of a coarse node (patches of the aux levels) are NOT staged: the half-warp that owns a 2 x 2 block
-// reads its 16 child rows straight from global at the top of the chunk (16 LDG.64 per lane in flight across the wait for
-// the slot), so every tile costs one slot use per chunk and the ring stays four chunks ahead.
+// The 2 x 2 children of a coarse node are NOT staged.  Two routes:
+//   * families (the last aux level -> the main level, where 90 % of the child bytes are): an aux patch and the (up to)
+//     2 x 2 main patches that hold its children form a UNIT that one SM processes back to back.  The main patches have
+//     the four children of a coarse node in one half-warp's registers anyway: they write the pooled sum
+//     S[parent] = sum_c dis[c] x[c] (one row per 2 x 2 block) to a per-SM scratch buffer in global memory (128 rows,
+//     L2-resident, double-buffered by unit), and the aux patch adds dis[v] * S[v] -- 16 KB per chunk instead of 64 KB of
+//     child rows, and the main-level rows cross HBM once.  Same SM, so a CTA barrier orders the writes and the reads;
+//   * every other patch with children: the half-warp that owns a 2 x 2 block reads its 16 child rows straight from
+//     global, issued one chunk ahead (16 LDG.64 per lane in flight across the operand stores / barrier round trip).
+// Either way a tile costs one slot use per chunk and the ring stays four chunks ahead.
 // A compute half-warp owns a 2 x 2 block of the patch; its 4 x 6 lattice weights (up, left, right, down, parent, self;
 // 0 = no such edge) and 4 x 4 child weights are gcn_norm's dis[v] * dis[u], precomputed per block.
 constexpr int kPatchPRows = 10 * 18, kPatchQRows = 4 * 8;
+constexpr int kPoolRows = 128;  // pooled rows of one aux patch
 struct alignas(16) PatchTile {  // 64 bytes
-  int32_t cls;              // 0 = patch, 1 = patch with children, 2 = CSR tile (rows summed from the device CSR)
+  int32_t cls;              // 0 = patch, 1 = patch with children (direct loads), 2 = CSR tile (rows summed from the device
+                            // CSR), 3 = patch with children through the pool of its unit
   int32_t level;            // lattice level of the patch
   int32_t y0, x0;           // patch origin inside the level
   int32_t qlevel, qy, qx;   // parents: level (-1 = none) and origin of the 4 x 8 box
   int32_t clevel, cy, cx;   // children: level (-1 = none) and origin of the 16 x 32 box (may lie partly outside)
   int32_t node0, side;      // frame-local node id of lattice position (0, 0) and side of the level
   int32_t cnode0, cside;    // same for the children level
-  int32_t pad_[2];
+  int32_t pool_rel;         // >= 0: member of a unit -- block (by, bx) writes its pooled sum to pool row pool_rel + 16 by + bx; -1: no
+  int32_t pad_;
 };
 static_assert(sizeof(PatchTile) == 64, "PatchTile layout");
-struct alignas(16) PatchBlockW {  // 160 bytes
+struct alignas(16) PatchBlockW {  // 192 bytes
   float wl[4][6];  // node (a, b, c, d) = ((0,0), (0,1), (1,0), (1,1)) of the block x (up, left, right, down, parent, self)
   float wc[4][4];  // node x child (2 ny + i, 2 nx + j) -> [i * 2 + j]
+  float dv[4];     // dis[node]: its coefficient in the pooled sum of its parent
+  float wp[4];     // dis[node] if the node has children (coefficient of its pooled child sum), else 0
 };
-static_assert(sizeof(PatchBlockW) == 160, "PatchBlockW layout");
+static_assert(sizeof(PatchBlockW) == 192, "PatchBlockW layout");
 struct PatchPlan {
   int ok;                      // 0: the graph has tiles this path cannot run (diagonal lattices, hubs): use the gather plan
   const PatchTile* tiles;      // [tiles_per_frame]
   const PatchBlockW* blocks;   // [tiles_per_frame][32]
+  // processing sequence of a frame: units (runs of tiles one SM processes back to back: a family, or a single tile);
+  // the persistent grid deals UNITS round-robin
+  const int32_t* seq;          // [tiles_per_frame] tile ids, unit by unit
+  const int32_t* unit_off;     // [units_per_frame + 1] first position of each unit in seq
+  int units_per_frame;
 };
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -58,6 +58,7 @@ const int32_t* graph_tile_groups(const eg_graph* g);
 int graph_tiles_per_frame(const eg_graph* g);
 const TilePlan& graph_plan(const eg_graph* g);
 const PatchPlan& graph_patch_plan(const eg_graph* g);
+int graph_pool_scratch(const eg_graph* g, cudaStream_t s, float** pool);
 int launch_stats_finalize(int nparts, int cols, int stride, long long rows, const double* parts, float* mean,
                           float* var, cudaStream_t s);
 }  // namespace eg
@@ -143,7 +144,9 @@ struct TcParams {
   const int32_t* tile_nodes;   // GATHER: [tiles_per_frame][128]
   const int32_t* tile_groups;  // GATHER: [tiles_per_frame][16] first node / rows of each 16-row group
   TilePlan plan;               // gather mode: per-tile staged sources and per-row edges
-  PatchPlan patch;             // patch mode: tile descriptors and per-block weights
+  PatchPlan patch;             // patch mode: tile descriptors, per-block weights, processing sequence
+  float* pool;                 // patch mode: pooled child sums, [SMs][2][kPoolRows][128]
+  int batch;                   // patch mode: frames
   int tiles_per_frame;
   int nodes_per_frame;
   int num_tiles;              // < 2^31 / 128 (rows < 2^31, checked by the launchers)
@@ -289,16 +292,18 @@ __device__ __forceinline__ void emit_pair(uint32_t a_hi, uint32_t off, F2 v) {
 // kernel-wide values (the lane id, ring addresses) that the plain tiles and the MMA issuer then re-loaded from local
 // memory on their critical paths (plain tiles +25 %, r02r-w).
 struct AuxTileArgs {
-  const float* cwin;   // first child row of the block's window, this lane's 2 features, chunk 0
+  const float* cwin;   // direct: first child row of the block's window; pooled: pool row of node a; this lane's 2 features, chunk 0
   float* agg_a;        // A_hat dH side output (backward) of node a, or nullptr
-  uint32_t wlu;        // shared address of the block's weights: wl[4][6], wc[4][4]
+  uint32_t wlu;        // shared address of the block's weights: wl[4][6], wc[4][4], dv[4], wp[4]
   uint32_t pb, qb;     // shared offsets of P[0][0] / the parent row of the block inside a slot (slot base not added)
   uint32_t so_a, so_b; // operand-tile offsets of tile rows a and b (c, d: + 2048)
   int cside, side;     // sides of the children level / the patch level
   uint32_t use, chunk; // ring counters (in / out)
 };
-template <uint32_t kRawStagesT, uint32_t kRawBytesT, uint32_t kOffRawFullT, uint32_t kOffRawEmptyT, uint32_t kOffFullT,
-          uint32_t kOffEmptyT>
+// POOLED: the children arrive as ONE pooled row per node (written by the main patches of the tile's unit, see
+// PatchPlan): 4 loads per lane and chunk instead of 16, weights wp[4].
+template <bool POOLED, uint32_t kRawStagesT, uint32_t kRawBytesT, uint32_t kOffRawFullT, uint32_t kOffRawEmptyT,
+          uint32_t kOffFullT, uint32_t kOffEmptyT>
 #ifndef EG_AUX_INLINE
 #define EG_AUX_INLINE __forceinline__
 #endif
@@ -311,19 +316,25 @@ __device__ EG_AUX_INLINE void patch_aux_tile(AuxTileArgs& a) {
   const int cside = a.cside;
   uint32_t has = 0;
 #pragma unroll
-  for (int n = 0; n < 4; ++n) has |= (__uint_as_float(lds_u32(wlu + 96 + n * 16)) != 0.f ? 1u : 0u) << n;
-  F2 ch[16];
+  for (int n = 0; n < 4; ++n)
+    has |= (__uint_as_float(lds_u32(POOLED ? wlu + 176 + n * 4 : wlu + 96 + n * 16)) != 0.f ? 1u : 0u) << n;
+  constexpr int NCH = POOLED ? 4 : 16;
+  F2 ch[NCH];
   auto load_children = [&](int kc) {
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
+      if constexpr (POOLED) {  // pool row of node n = (ny, nx): row of node a + 16 ny + nx
+        ch[n] = (has >> n & 1u) ? ldcg_f2(cwin + ((n >> 1) * 16 + (n & 1)) * 128 + kc * 32) : f2_pack(0.f, 0.f);
+      } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int r = 2 * (n >> 1) + (k >> 1), c = 2 * (n & 1) + (k & 1);
+        for (int k = 0; k < 4; ++k) {
+          const int r = 2 * (n >> 1) + (k >> 1), c = 2 * (n & 1) + (k & 1);
 #ifdef EG_PD_NOCHILD
-        ch[n * 4 + k] = f2_pack(0.f, 0.f);
+          ch[n * 4 + k] = f2_pack(0.f, 0.f);
 #else
-        ch[n * 4 + k] = (has >> n & 1u) ? ldcg_f2(cwin + ((long long)r * cside + c) * 128 + kc * 32) : f2_pack(0.f, 0.f);
+          ch[n * 4 + k] = (has >> n & 1u) ? ldcg_f2(cwin + ((long long)r * cside + c) * 128 + kc * 32) : f2_pack(0.f, 0.f);
 #endif
+        }
       }
     }
   };
@@ -334,11 +345,16 @@ __device__ EG_AUX_INLINE void patch_aux_tile(AuxTileArgs& a) {
     mbar_wait_a(sm + kOffRawFullT + rs * 8, (use / kRawStagesT) & 1u);
     const uint32_t ro = rs * kRawBytesT;
     F2 aa = f2_pack(0.f, 0.f), ab = aa, ac = aa, ad = aa;
+    if constexpr (POOLED) {
+      const float4 wp = lds4(wlu + 176);
+      fma2(aa, wp.x, ch[0]), fma2(ab, wp.y, ch[1]), fma2(ac, wp.z, ch[2]), fma2(ad, wp.w, ch[3]);
+    } else {
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      const float4 wc = lds4(wlu + 96 + n * 16);
-      F2& acc = n == 0 ? aa : n == 1 ? ab : n == 2 ? ac : ad;
-      fma2(acc, wc.x, ch[n * 4]), fma2(acc, wc.y, ch[n * 4 + 1]), fma2(acc, wc.z, ch[n * 4 + 2]), fma2(acc, wc.w, ch[n * 4 + 3]);
+      for (int n = 0; n < 4; ++n) {
+        const float4 wc = lds4(wlu + 96 + n * 16);
+        F2& acc = n == 0 ? aa : n == 1 ? ab : n == 2 ? ac : ad;
+        fma2(acc, wc.x, ch[n * 4]), fma2(acc, wc.y, ch[n * 4 + 1]), fma2(acc, wc.z, ch[n * 4 + 2]), fma2(acc, wc.w, ch[n * 4 + 3]);
+      }
     }
     {
       const uint32_t pa = a.pb + ro;
@@ -397,6 +413,44 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
   constexpr uint32_t kOffRaw = L::kOffRaw, kOffPlan = L::kOffPlan, kOffFull = L::kOffFull, kOffEmpty = L::kOffEmpty,
                      kOffRawFull = L::kOffRawFull, kOffRawEmpty = L::kOffRawEmpty;
   (void)kRawRows, (void)kOffPlan, (void)kPlanWarpBytes, (void)pm;
+  // Patch mode walks UNITS (PatchPlan: runs of tiles one SM processes back to back), dealt round-robin; every role walks
+  // the same sequence.  `t` is read one step ahead of its use wherever a role needs it early.
+  struct PIter {
+    int u, i, i1, b, t;
+  };
+  const int units_total = MODE == kPatch ? p.batch * p.patch.units_per_frame : 0;
+  // (iterators are passed and returned BY VALUE: taken by reference they lived in local memory, and the MMA issuer and
+  // the epilogue re-loaded them between tiles)
+  auto pit_at = [&](int u) -> PIter {
+    PIter it{u, 0, 0, 0, 0};
+    if (u < units_total) {
+      it.b = u / p.patch.units_per_frame;
+      const int uf = u - it.b * p.patch.units_per_frame;
+      it.i = __ldg(p.patch.unit_off + uf);
+      it.i1 = __ldg(p.patch.unit_off + uf + 1);
+      it.t = __ldg(p.patch.seq + it.i);
+    }
+    return it;
+  };
+  auto pit_begin = [&]() -> PIter { return pit_at((int)blockIdx.x); };
+  auto pit_valid = [&](PIter it) { return it.u < units_total; };
+  auto pit_next = [&](PIter it) -> PIter {
+    if (it.i + 1 < it.i1) {
+      ++it.i;
+      it.t = __ldg(p.patch.seq + it.i);
+      return it;
+    }
+    return pit_at(it.u + (int)gridDim.x);
+  };
+  (void)units_total, (void)pit_begin, (void)pit_valid, (void)pit_next;
+  // The MMA issuer and the epilogue walk "virtual tile indices" b * tiles_per_frame + t (-1 = done): the running tile
+  // index in linear / gather mode, the unit sequence in patch mode (state `wit`, owned by the role).
+  auto walk_tile = [&](PIter wit, int v) -> int {
+    if constexpr (MODE == kPatch) return pit_valid(wit) ? 0 : -1;  // (patch mode: only validity; frame / tile come from wit)
+    return v < p.num_tiles ? v : -1;
+  };
+  (void)walk_tile;
+
 #ifdef EG_TC_TIMING
   long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long dbg_n = 0;
@@ -815,14 +869,13 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
       const uint32_t pb = sm + kOffRaw + (2 * by * 18 + 2 * bx) * 128 + l16 * 8;  // P[0][0] of the block's 4 x 4 window
       const uint32_t qb = sm + kOffRaw + kPatchPRows * 128 + (by * 8 + bx) * 128 + l16 * 8;
       const bool agg_out = p.AggOut != nullptr;
-      auto prefetch_patch = [&](int tile, uint32_t buf) {
-        if (tile >= p.num_tiles) return;
-        const int t = tile % p.tiles_per_frame;
+      auto prefetch_patch = [&](int t, uint32_t buf) {
+        if (t < 0) return;
         const uint32_t dst = plan_u + buf * kPlanWarpBytes;
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.patch.blocks + (size_t)t * 32 + pw * 2);
         const uint8_t* tsrc = reinterpret_cast<const uint8_t*>(p.patch.tiles + t);
-        if (lane < 20) cp_async16(dst + lane * 16, wsrc + lane * 16);
-        else if (lane < 24) cp_async16(dst + lane * 16, tsrc + (lane - 20) * 16);
+        if (lane < 24) cp_async16(dst + lane * 16, wsrc + lane * 16);  // 2 x 192 B of weights
+        else if (lane < 28) cp_async16(dst + lane * 16, tsrc + (lane - 24) * 16);
       };
       uint32_t use = 0;  // raw-slot uses so far (the producer counts the same sequence)
       auto wait_raw = [&]() -> uint32_t {
@@ -867,39 +920,59 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
       };
       auto emit2 = [&](uint32_t a_hi, uint32_t off, F2 v) { emit_pair(a_hi, off, v); };
       uint32_t pbuf = 0;
-      prefetch_patch(blockIdx.x, 0);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, pbuf ^= 1u) {
-        const int b = tile / p.tiles_per_frame;
-        const int t = tile - b * p.tiles_per_frame;
+      // this SM's pool buffers: [2][kPoolRows][128] floats, alternating by unit (`par`), so the writers of the next unit
+      // never meet a reader of the current one
+      float* const pool_cta = p.pool + (size_t)blockIdx.x * 2 * kPoolRows * 128 + l16 * 2;
+      uint32_t par = 0;
+      // (b, t): this tile; t_nxt: the next one (-1 = none), whose plan is prefetched during this tile; `ahead` runs
+      // TWO tiles ahead, so that the table reads behind it are never waited for
+      PIter ahead = pit_begin();
+      int b = ahead.b, t = pit_valid(ahead) ? ahead.t : -1;
+      ahead = pit_next(ahead);
+      int b_nxt = ahead.b, t_nxt = pit_valid(ahead) ? ahead.t : -1;
+      ahead = pit_next(ahead);
+      prefetch_patch(t, 0);
+      for (; t >= 0; pbuf ^= 1u, b = b_nxt, t = t_nxt, b_nxt = ahead.b, t_nxt = pit_valid(ahead) ? ahead.t : -1, ahead = pit_next(ahead)) {
         const long long frow0 = (long long)b * p.nodes_per_frame;
         cp_async_wait_all();  // this tile's weights and descriptor (prefetched one tile ahead)
         __syncwarp();
         const uint32_t pl = plan_u + pbuf * kPlanWarpBytes;
-        const float4 d0 = lds4(pl + 320), d2 = lds4(pl + 352);
+        const float4 d0 = lds4(pl + 384), d2 = lds4(pl + 416), d3 = lds4(pl + 432);
         const int cls = __float_as_int(d0.x), y0 = __float_as_int(d0.z), x0 = __float_as_int(d0.w);
         const int node0 = __float_as_int(d2.z), side = __float_as_int(d2.w);
 #ifndef EG_PD_PLAINAUX
-        if (cls == 1) {  // patch with children: a function of its own (see patch_aux_tile)
-          const float4 d3 = lds4(pl + 368);
-          const int cy = __float_as_int(d2.x), cx = __float_as_int(d2.y);
-          const int cnode0 = __float_as_int(d3.x), cside = __float_as_int(d3.y);
+        if (cls == 1 || cls == 3) {  // patch with children: a function of its own (see patch_aux_tile)
           AuxTileArgs a;
-          a.cwin = p.X + (frow0 + cnode0 + (long long)(cy + 4 * by) * cside + cx + 4 * bx) * 128 + l16 * 2;
           a.agg_a = agg_out ? p.AggOut + (frow0 + node0 + (long long)(y0 + 2 * by) * side + x0 + 2 * bx) * 128 + l16 * 2
                             : nullptr;
-          a.wlu = pl + h * 160;
+          a.wlu = pl + h * 192;
           a.pb = pb, a.qb = qb, a.so_a = so_a, a.so_b = so_b;
-          a.cside = cside, a.side = side;
+          a.side = side;
           a.use = use, a.chunk = chunk;
-          prefetch_patch(tile + gridDim.x, pbuf ^ 1u);
-          patch_aux_tile<kRawStages, kRawBytes, kOffRawFull, kOffRawEmpty, kOffFull, kOffEmpty>(a);
+          prefetch_patch(t_nxt, pbuf ^ 1u);
+          if (cls == 3) {
+            // the pooled child sums of this patch were written by the main patches of its unit, by ALL compute warps of
+            // this CTA: one CTA-scope fence + barrier among the 16 compute warps orders them before the reads below
+            __threadfence_block();
+            asm volatile("bar.sync 1, %0;" ::"n"(kProdWarps * 32) : "memory");
+            a.cwin = pool_cta + ((size_t)par * kPoolRows + (2 * by) * 16 + 2 * bx) * 128;
+            a.cside = 0;
+            patch_aux_tile<true, kRawStages, kRawBytes, kOffRawFull, kOffRawEmpty, kOffFull, kOffEmpty>(a);
+            par ^= 1u;
+          } else {
+            const int cy = __float_as_int(d2.x), cx = __float_as_int(d2.y);
+            const int cnode0 = __float_as_int(d3.x), cside = __float_as_int(d3.y);
+            a.cwin = p.X + (frow0 + cnode0 + (long long)(cy + 4 * by) * cside + cx + 4 * bx) * 128 + l16 * 2;
+            a.cside = cside;
+            patch_aux_tile<false, kRawStages, kRawBytes, kOffRawFull, kOffRawEmpty, kOffFull, kOffEmpty>(a);
+          }
           use = a.use, chunk = a.chunk;
           continue;
         }
 #endif
         if (cls == 2) {
           // ---- CSR tile (ragged small lattices, coordinate nodes): rows summed straight from the device CSR
-          prefetch_patch(tile + gridDim.x, pbuf ^ 1u);
+          prefetch_patch(t_nxt, pbuf ^ 1u);
           const float* fbase = p.X + frow0 * 128 + l16 * 2;
 #pragma unroll 1
           for (int kc = 0; kc < 4; ++kc) {
@@ -924,10 +997,14 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
         float wl[24];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          const float4 v = lds4(pl + h * 160 + i * 16);
+          const float4 v = lds4(pl + h * 192 + i * 16);
           wl[4 * i] = v.x, wl[4 * i + 1] = v.y, wl[4 * i + 2] = v.z, wl[4 * i + 3] = v.w;
         }
-        prefetch_patch(tile + gridDim.x, pbuf ^ 1u);
+        prefetch_patch(t_nxt, pbuf ^ 1u);
+        // member of a unit: the pooled sum of this block (= the child term of its parent) goes to the SM's pool buffer
+        const int pool_rel = __float_as_int(d3.z);
+        float* const pool_row = pool_rel >= 0 ? pool_cta + ((size_t)par * kPoolRows + pool_rel + by * 16 + bx) * 128 : nullptr;
+        const uint32_t dvu = pl + h * 192 + 160;
         float* agg_a = agg_out ? p.AggOut + (frow0 + node0 + (long long)(y0 + 2 * by) * side + x0 + 2 * bx) * 128 + l16 * 2
                                : nullptr;
 #pragma unroll 1
@@ -952,6 +1029,14 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
           fma2(ab, wl[6], p02), fma2(ab, wl[7], p11), fma2(ab, wl[8], p13), fma2(ab, wl[9], p22), fma2(ab, wl[10], pq), fma2(ab, wl[11], p12);
           fma2(ac, wl[12], p11), fma2(ac, wl[13], p20), fma2(ac, wl[14], p22), fma2(ac, wl[15], p31), fma2(ac, wl[16], pq), fma2(ac, wl[17], p21);
           fma2(ad, wl[18], p12), fma2(ad, wl[19], p21), fma2(ad, wl[20], p23), fma2(ad, wl[21], p32), fma2(ad, wl[22], pq), fma2(ad, wl[23], p22);
+#ifndef EG_PD_NOPOOLOUT
+          if (pool_row) {  // sum_c dis[c] x[c] over the block's four nodes = the pooled child sum of their parent
+            const float4 dv = lds4(dvu);
+            F2 ps = f2_pack(0.f, 0.f);
+            fma2(ps, dv.x, p11), fma2(ps, dv.y, p12), fma2(ps, dv.z, p21), fma2(ps, dv.w, p22);
+            st_f2(pool_row + kc * 32, ps);
+          }
+#endif
           asm volatile("" : "+l"(aa.u), "+l"(ab.u), "+l"(ac.u), "+l"(ad.u) : : "memory");  // the slot's loads have landed
           release_raw();
           const uint32_t a_hi = wait_op();
@@ -994,18 +1079,20 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
 #endif
           ++use;
         };
-        auto load_desc = [&](int tile, int4& a, int4& b4, int4& c) {
-          if (tile >= p.num_tiles) return;
-          const int4* d = reinterpret_cast<const int4*>(p.patch.tiles + tile % p.tiles_per_frame);
-          a = __ldg(d), b4 = __ldg(d + 1), c = __ldg(d + 2);
+        auto load_desc = [&](const PIter& it, int4& a, int4& b4) {
+          if (!pit_valid(it)) return;
+          const int4* d = reinterpret_cast<const int4*>(p.patch.tiles + it.t);
+          a = __ldg(d), b4 = __ldg(d + 1);
         };
-        int4 na = make_int4(2, 0, 0, 0), nb = na, nc = na;
-        load_desc(blockIdx.x, na, nb, nc);
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int4 na = make_int4(2, 0, 0, 0), nb = na;
+        PIter cur = pit_begin();
+        load_desc(cur, na, nb);
+        while (pit_valid(cur)) {
           const int4 ta = na, tb = nb;  // {cls, level, y0, x0} {qlevel, qy, qx, clevel}
-          load_desc(tile + gridDim.x, na, nb, nc);
+          const int b = cur.b;
+          cur = pit_next(cur);
+          load_desc(cur, na, nb);  // the next tile's descriptor, in flight while this tile's copies are issued
           if (ta.x == 2) continue;
-          const int b = tile / p.tiles_per_frame;
           const CUtensorMap* mp = &pm->m[3 * ta.y];
           const CUtensorMap* mq = tb.x >= 0 ? &pm->m[3 * tb.x + 1] : nullptr;
 #pragma unroll 1
@@ -1100,7 +1187,17 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
     // ===== MMA issuer ======================================================================================
     constexpr uint32_t idesc = umma_idesc_tf32(128, 128, 0, 0);
     uint32_t chunk = 0, it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    // the issuer only needs the NUMBER of tiles this CTA processes (patch mode: summed over its units, once)
+    uint32_t my_tiles = 0;
+    if constexpr (MODE == kPatch) {
+      for (int u = blockIdx.x; u < units_total; u += gridDim.x) {
+        const int uf = u % p.patch.units_per_frame;
+        my_tiles += __ldg(p.patch.unit_off + uf + 1) - __ldg(p.patch.unit_off + uf);
+      }
+    } else {
+      my_tiles = (int)blockIdx.x < p.num_tiles ? (p.num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    }
+    for (; it < my_tiles; ++it) {
       const uint32_t buf = it & 1u, acc_phase = (it >> 1) & 1u;
       TC_TIMED_WAIT(0, &acc_empty[buf], acc_phase ^ 1u);
       tc_fence_after();
@@ -1145,13 +1242,20 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
     // row groups of a tile: lane l < 8 holds the first global row of group l (or -1), lane 8 + l its row count.
     // They are fetched ONE TILE AHEAD (the table read is a dependent global load that would otherwise be exposed
     // at the top of every tile).
+    PIter wit = MODE == kPatch ? pit_begin() : PIter{0, 0, 0, 0, 0};  // patch mode: the tile `tile_rows` is asked about
     auto tile_rows = [&](int tile, long long& base, int& cnt) {
       base = -1;
       cnt = 0;
-      if (tile >= p.num_tiles) return;
+      if (tile < 0 || tile >= p.num_tiles) return;
       if (GATHER) {
-        const int b = tile / p.tiles_per_frame;
-        const int v = lane < 16 ? __ldg(p.tile_groups + (tile - b * p.tiles_per_frame) * 16 + lane) : 0;
+        int b, t;
+        if constexpr (MODE == kPatch) {  // (the walker knows frame and tile: no division)
+          b = wit.b, t = wit.t;
+        } else {
+          b = tile / p.tiles_per_frame;
+          t = tile - b * p.tiles_per_frame;
+        }
+        const int v = lane < 16 ? __ldg(p.tile_groups + t * 16 + lane) : 0;
         cnt = v;
         base = (lane < 8 && v >= 0) ? (long long)b * p.nodes_per_frame + v : -1;
       } else {
@@ -1162,11 +1266,15 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
     };
     long long gbase, nbase;
     int gcnt, ncnt;
-    tile_rows(blockIdx.x, gbase, gcnt);
+    int vt = (int)blockIdx.x;
+    tile_rows(walk_tile(wit, vt), gbase, gcnt);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = walk_tile(wit, vt); tile >= 0; ++it) {
       const uint32_t buf = it & 1u, acc_phase = (it >> 1) & 1u;
-      tile_rows(tile + gridDim.x, nbase, ncnt);  // consumed after the slab loop
+      if constexpr (MODE == kPatch) wit = pit_next(wit);
+      vt += gridDim.x;
+      tile = walk_tile(wit, vt);           // (from here on `tile` is the NEXT tile)
+      tile_rows(tile, nbase, ncnt);        // consumed after the slab loop
       float adA[16], adB[16];
       auto slab_rows = [&](int sl, long long& base, int& cnt) {
         base = __shfl_sync(0xffffffffu, gbase, sl);
@@ -1335,7 +1443,8 @@ int launch(const TcParams& p, const PatchMaps* pm, float* mean, float* var, void
                                    (int)Lay<MODE>::kSmemBytes));
   }
   const int sms = num_sms();
-  const int grid = (int)(p.num_tiles < sms ? p.num_tiles : sms);
+  const long long work = MODE == kPatch ? (long long)p.batch * p.patch.units_per_frame : (long long)p.num_tiles;
+  const int grid = (int)(work < sms ? work : sms);
   TcParams q = p;
   q.stat_parts = stats ? reinterpret_cast<double*>(ws) : nullptr;
   {
@@ -1453,6 +1562,8 @@ int launch_gcn_tc(const eg_graph* g, int batch, const float* X, const float* W, 
   const PatchPlan& pp = graph_patch_plan(g);
   if (pp.ok && patch_plan_enabled()) {
     p.patch = pp;
+    p.batch = batch;
+    if (int rc = graph_pool_scratch(g, s, &p.pool)) return rc;
     PatchMaps maps;
     if (int rc = encode_patch_maps(info, batch, X, maps)) return rc;
     return launch<kPatch>(p, &maps, mean, var, ws, ws_bytes, AggOut ? "gcn_tc_bwd" : "gcn_tc_fwd", s);

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <cmath>
 #include <utility>
 #include <vector>
@@ -45,6 +46,14 @@ struct eg_graph {
   // tile row is either a slot of that stage or a direct global read (e.g. the 4 children of an aux node).
   eg::TilePlan plan;
   eg::PatchPlan patch;  // TMA path of the fused kernel (regular lattices only)
+  // pool scratch of the patch path ([SMs][2][kPoolRows][128] floats, zero at allocation), one per stream that has
+  // launched on this graph (launches on one stream are ordered; two streams must not share it)
+  struct PoolScratch {
+    cudaStream_t stream;
+    float* pool;
+  };
+  std::vector<PoolScratch> pool;
+  std::mutex pool_mu;
 };
 
 using namespace eg;
@@ -292,6 +301,7 @@ struct HostPatchPlan {
   int ok = 0;
   std::vector<PatchTile> tiles;
   std::vector<PatchBlockW> blocks;
+  std::vector<int32_t> seq, unit_off;  // processing sequence of a frame (PatchPlan)
 };
 
 // Patch plan (see PatchTile / PatchBlockW in common.cuh).  Weights are dis[v] * dis[u] with dis exactly as
@@ -305,6 +315,7 @@ HostPatchPlan build_patch_plan(const Topo& t, const std::vector<int32_t>& tiles)
   memset(&zt, 0, sizeof(zt));
   zt.cls = 2;
   zt.qlevel = zt.clevel = -1;
+  zt.pool_rel = -1;
   pp.tiles.assign(T, zt);
   PatchBlockW zb;
   memset(&zb, 0, sizeof(zb));
@@ -383,6 +394,7 @@ HostPatchPlan build_patch_plan(const Topo& t, const std::vector<int32_t>& tiles)
               if (!is_main || (a < 2 * t.half && b < 2 * t.half)) bw.wl[n][4] = dv * dis(t.loff[pt.qlevel] + pa * P + pb);
             }
             bw.wl[n][5] = dv * dv;
+            bw.dv[n] = dv;
             if (pt.clevel >= 0) {
               const int P2 = t.lsize[pt.clevel], off2 = t.loff[pt.clevel];
               const bool window = l < t.naux - 1 || (a >= t.crop && a < t.crop + t.half && b >= t.crop && b < t.crop + t.half);
@@ -390,6 +402,7 @@ HostPatchPlan build_patch_plan(const Topo& t, const std::vector<int32_t>& tiles)
                 const int ca = l < t.naux - 1 ? 2 * a : 2 * (a - t.crop), cb = l < t.naux - 1 ? 2 * b : 2 * (b - t.crop);
                 for (int i = 0; i < 2; ++i)
                   for (int j = 0; j < 2; ++j) bw.wc[n][i * 2 + j] = dv * dis(off2 + (ca + i) * P2 + cb + j);
+                bw.wp[n] = dv;
                 any_child = true;
               }
             }
@@ -401,6 +414,59 @@ HostPatchPlan build_patch_plan(const Topo& t, const std::vector<int32_t>& tiles)
     }
   }
   if (ti != T) pp.ok = 0;
+  // ---- units.  A family = a patch of the LAST aux level that has children + the main patches that hold them: the main
+  // patches write the pooled child sums of their 2 x 2 blocks (pool_rel), the aux patch reads them (cls 3).  Needs the
+  // parents of a main patch inside ONE aux patch: crop a multiple of 8 (224 / 7: 8, 448 / 8: 16); otherwise every patch
+  // with children keeps the direct loads.  EG_PATCH_FAMILIES=0 switches the families off (A/B timing).
+  const char* fam_env = getenv("EG_PATCH_FAMILIES");
+  const bool families = !(fam_env && fam_env[0] == '0') && !t.main_only && t.lsize[main_l] % 16 == 0 &&
+                        t.naux >= 1 && t.lsize[t.naux - 1] % 16 == 0 && t.crop % 8 == 0;
+  std::vector<int> tile_at_main, tile_at_aux;  // tile id of the patch at (row, column) of the main / last aux level
+  std::vector<char> in_family(T, 0);
+  if (families) {
+    const int pm = t.lsize[main_l], pa = t.lsize[t.naux - 1];
+    tile_at_main.assign((pm / 8) * (pm / 16), -1);
+    tile_at_aux.assign((pa / 8) * (pa / 16), -1);
+    for (int i = 0; i < T; ++i) {
+      const PatchTile& pt = pp.tiles[i];
+      if (pt.cls == 2) continue;
+      if (pt.level == main_l) tile_at_main[(pt.y0 / 8) * (pm / 16) + pt.x0 / 16] = i;
+      if (pt.level == t.naux - 1) tile_at_aux[(pt.y0 / 8) * (pa / 16) + pt.x0 / 16] = i;
+    }
+  }
+  auto push_unit = [&](const std::vector<int>& members) {
+    pp.unit_off.push_back((int)pp.seq.size());
+    for (int m : members) pp.seq.push_back(m);
+  };
+  std::vector<std::vector<int>> fam_units;
+  if (families) {
+    const int pm = t.lsize[main_l], pa = t.lsize[t.naux - 1];
+    for (int ty = 0; ty < pa / 8; ++ty)
+      for (int tx = 0; tx < pa / 16; ++tx) {
+        const int ai = tile_at_aux[ty * (pa / 16) + tx];
+        if (ai < 0 || pp.tiles[ai].cls != 1) continue;
+        std::vector<int> members;
+        for (int my = 0; my < pm / 8; ++my)
+          for (int mx = 0; mx < pm / 16; ++mx) {
+            const int qy = t.crop + (my * 8) / 2, qx = t.crop + (mx * 16) / 2;  // parents of the main patch: [qy, qy+4) x [qx, qx+8)
+            if (qy / 8 != ty || qx / 16 != tx) continue;
+            const int mi = tile_at_main[my * (pm / 16) + mx];
+            if (mi < 0) continue;
+            pp.tiles[mi].pool_rel = (qy - ty * 8) * 16 + (qx - tx * 16);
+            in_family[mi] = 1;
+            members.push_back(mi);
+          }
+        members.push_back(ai);
+        pp.tiles[ai].cls = 3;
+        in_family[ai] = 1;
+        fam_units.push_back(members);
+      }
+  }
+  for (int i = 0; i < T; ++i)
+    if (!in_family[i]) push_unit({i});  // singles first, in table order (coarse levels, childless aux patches, ...)
+  for (const auto& m : fam_units) push_unit(m);
+  pp.unit_off.push_back((int)pp.seq.size());
+  if ((int)pp.seq.size() != T) pp.ok = 0;
   return pp;
 }
 
@@ -545,6 +611,9 @@ int eg_graph_create(const eg_graph_spec* spec, int device, eg_graph** out) {
     if (pp.ok) {
       EG_TRY(up(pp.tiles.data(), pp.tiles.size() * sizeof(PatchTile), (void**)&g->patch.tiles));
       EG_TRY(up(pp.blocks.data(), pp.blocks.size() * sizeof(PatchBlockW), (void**)&g->patch.blocks));
+      EG_TRY(up(pp.seq.data(), pp.seq.size() * sizeof(int32_t), (void**)&g->patch.seq));
+      EG_TRY(up(pp.unit_off.data(), pp.unit_off.size() * sizeof(int32_t), (void**)&g->patch.unit_off));
+      g->patch.units_per_frame = (int)pp.unit_off.size() - 1;
     }
   }
   std::vector<int32_t> hdeg(t.N);
@@ -574,6 +643,9 @@ void eg_graph_destroy(eg_graph* g) {
   cudaFree((void*)g->plan.rows);
   cudaFree((void*)g->patch.tiles);
   cudaFree((void*)g->patch.blocks);
+  cudaFree((void*)g->patch.seq);
+  cudaFree((void*)g->patch.unit_off);
+  for (auto& ps : g->pool) cudaFree(ps.pool);
   delete g;
 }
 
@@ -693,9 +765,12 @@ int eg_graph_plan_check(const eg_graph_spec* spec, int64_t* stats) {
 }
 
 // Host-only self check of the patch plan (TMA path of the fused kernel): replays, for every patch tile and node, the
-// sources the kernel reads -- box position -> node id, exactly as the tensor-map coordinates address them -- and
-// compares the (source, weight) set with the CSR row.  stats (optional, int64[4]): plan usable (0/1), plain patch
-// tiles, patch tiles with children, CSR tiles.  Returns the number of violations or a negative error code.
+// sources the kernel reads -- box position -> node id, exactly as the tensor-map coordinates address them; children
+// either through the direct 4 x 4 window or through the pool rows the members of the tile's unit write -- and compares
+// the (source, weight) set with the CSR row.  Also: the sequence is a permutation of the tiles, and a unit of more than
+// one tile is a family (pool writers, then their reader).  stats (optional, int64[6]): plan usable (0/1), plain patch
+// tiles, patch tiles with children (direct loads), CSR tiles, patch tiles reading the pool, units per frame.
+// Returns the number of violations or a negative error code.
 int eg_graph_patch_check(const eg_graph_spec* spec, int64_t* stats) {
   Topo t;
   int rc = init_topo(spec, t);
@@ -703,8 +778,8 @@ int eg_graph_patch_check(const eg_graph_spec* spec, int64_t* stats) {
   const std::vector<int32_t> tiles = build_tiles(t);
   const HostPatchPlan pp = build_patch_plan(t, tiles);
   const int T = (int)(tiles.size() / 128);
-  long long bad = 0, cls[3] = {0, 0, 0};
-  if (stats) stats[0] = pp.ok, stats[1] = stats[2] = stats[3] = 0;
+  long long bad = 0, cls[4] = {0, 0, 0, 0};
+  if (stats) stats[0] = pp.ok, stats[1] = stats[2] = stats[3] = stats[4] = stats[5] = 0;
   if (!pp.ok) return 0;
   std::vector<float> dis(t.N);
   for (int u = 0; u < t.N; ++u) dis[u] = (float)(1.0 / sqrt((double)(degree_of(t, u) + 1)));
@@ -712,16 +787,55 @@ int eg_graph_patch_check(const eg_graph_spec* spec, int64_t* stats) {
     const int p = t.lsize[level];
     return (y < 0 || x < 0 || y >= p || x >= p) ? -1 : t.loff[level] + y * p + x;
   };
+  // sequence: permutation; units; pool contents per family reader
+  struct PoolTerm { int node; float w; };
+  std::vector<std::vector<std::vector<PoolTerm>>> pool_of(T);  // reader tile -> pool row -> terms
+  {
+    std::vector<int> seen(T, 0);
+    bad += (int)pp.seq.size() != T || pp.unit_off.empty() || pp.unit_off.front() != 0 || pp.unit_off.back() != T;
+    for (int32_t v : pp.seq)
+      if (v < 0 || v >= T) ++bad;
+      else ++seen[v];
+    for (int i = 0; i < T; ++i) bad += seen[i] != 1;
+    for (size_t u = 0; u + 1 < pp.unit_off.size() && !bad; ++u) {
+      const int i0 = pp.unit_off[u], i1 = pp.unit_off[u + 1];
+      bad += i1 <= i0;
+      if (i1 - i0 == 1) {
+        const PatchTile& pt = pp.tiles[pp.seq[i0]];
+        bad += pt.cls == 3 || pt.pool_rel >= 0;  // pool traffic only inside a family
+        continue;
+      }
+      const int reader = pp.seq[i1 - 1];
+      bad += pp.tiles[reader].cls != 3;
+      pool_of[reader].assign(kPoolRows, {});
+      for (int i = i0; i < i1 - 1; ++i) {
+        const int w = pp.seq[i];
+        const PatchTile& pt = pp.tiles[w];
+        bad += pt.cls != 0 || pt.pool_rel < 0;
+        for (int q = 0; q < 32; ++q) {
+          const int row = pt.pool_rel + 16 * (q >> 3) + (q & 7);
+          if (row < 0 || row >= kPoolRows) {
+            ++bad;
+            continue;
+          }
+          const PatchBlockW& bw = pp.blocks[(size_t)w * 32 + q];
+          for (int n = 0; n < 4; ++n)
+            pool_of[reader][row].push_back({at(pt.level, pt.y0 + 2 * (q >> 3) + (n >> 1), pt.x0 + 2 * (q & 7) + (n & 1)), bw.dv[n]});
+        }
+      }
+    }
+  }
   std::vector<std::pair<int, float>> want, got;
   for (int ti = 0; ti < T; ++ti) {
     const PatchTile& pt = pp.tiles[ti];
-    if (pt.cls < 0 || pt.cls > 2) {
+    if (pt.cls < 0 || pt.cls > 3) {
       ++bad;
       continue;
     }
     ++cls[pt.cls];
     if (pt.cls == 2) continue;
-    bad += pt.node0 != t.loff[pt.level] || pt.side != t.lsize[pt.level] || (pt.cls == 1) != (pt.clevel >= 0);
+    bad += pt.node0 != t.loff[pt.level] || pt.side != t.lsize[pt.level] || (pt.cls == 1 || pt.cls == 3) != (pt.clevel >= 0);
+    if (pt.clevel >= 0) bad += pt.cnode0 != t.loff[pt.clevel] || pt.cside != t.lsize[pt.clevel];
     for (int q = 0; q < 32; ++q) {
       const PatchBlockW& bw = pp.blocks[(size_t)ti * 32 + q];
       const int by = q >> 3, bx = q & 7;
@@ -742,10 +856,21 @@ int eg_graph_patch_check(const eg_graph_spec* spec, int64_t* stats) {
         add(bw.wl[n][3], at(pt.level, y + 1, x));
         add(bw.wl[n][4], pt.qlevel >= 0 ? at(pt.qlevel, pt.qy + by, pt.qx + bx) : -1);
         add(bw.wl[n][5], v);
-        for (int i = 0; i < 2; ++i)
-          for (int j = 0; j < 2; ++j)
-            add(bw.wc[n][i * 2 + j],
-                pt.clevel >= 0 ? at(pt.clevel, pt.cy + 4 * by + 2 * ny + i, pt.cx + 4 * bx + 2 * nx + j) : -1);
+        if (v >= 0) bad += bw.dv[n] != dis[v];
+        if (pt.cls == 3) {  // children through the pool row of the node itself: row (2 by + ny) * 16 + 2 bx + nx
+          if (bw.wp[n] != 0.f) {
+            bad += v < 0 || bw.wp[n] != dis[v];
+            const auto& terms = pool_of[ti].empty() ? std::vector<PoolTerm>() : pool_of[ti][(2 * by + ny) * 16 + 2 * bx + nx];
+            bad += terms.size() != 4;
+            for (const PoolTerm& tm : terms) add(tm.w * bw.wp[n], tm.node);
+          }
+        } else {
+          bad += bw.wp[n] != 0.f && pt.cls != 1;
+          for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j)
+              add(bw.wc[n][i * 2 + j],
+                  pt.clevel >= 0 ? at(pt.clevel, pt.cy + 4 * by + 2 * ny + i, pt.cx + 4 * bx + 2 * nx + j) : -1);
+        }
         if (v < 0) continue;
         want.clear();
         for_each_neighbor(t, v, true, [&](int u) { want.emplace_back(u, dis[u] * dis[v]); });
@@ -756,7 +881,10 @@ int eg_graph_patch_check(const eg_graph_spec* spec, int64_t* stats) {
       }
     }
   }
-  if (stats) stats[1] = cls[0], stats[2] = cls[1], stats[3] = cls[2];
+  if (stats) {
+    stats[1] = cls[0], stats[2] = cls[1], stats[3] = cls[2], stats[4] = cls[3];
+    stats[5] = (long long)pp.unit_off.size() - 1;
+  }
   return (int)std::min<long long>(bad, 1 << 30);
 }
 
@@ -804,4 +932,23 @@ int graph_tiles_per_frame(const eg_graph* g) { return g->tiles_per_frame; }
 const int32_t* graph_tile_groups(const eg_graph* g) { return g->tile_groups; }
 const TilePlan& graph_plan(const eg_graph* g) { return g->plan; }
 const PatchPlan& graph_patch_plan(const eg_graph* g) { return g->patch; }
+
+// Pool scratch of the patch path for launches on stream s (allocated on first use, zero-filled: rows of nodes without
+// children are read -- with weight 0 -- but never written).
+int graph_pool_scratch(const eg_graph* gc, cudaStream_t s, float** pool) {
+  eg_graph* g = const_cast<eg_graph*>(gc);
+  std::lock_guard<std::mutex> lock(g->pool_mu);
+  for (auto& e : g->pool)
+    if (e.stream == s) {
+      *pool = e.pool;
+      return EG_OK;
+    }
+  const size_t bytes = (size_t)kNumSMs * 2 * kPoolRows * 128 * sizeof(float);
+  float* ptr = nullptr;
+  EG_CUDA(cudaMalloc(&ptr, bytes));
+  EG_CUDA(cudaMemsetAsync(ptr, 0, bytes, s));
+  g->pool.push_back({s, ptr});
+  *pool = ptr;
+  return EG_OK;
+}
 }  // namespace eg

@@ -93,10 +93,13 @@ int eg_graph_plan_check(const eg_graph_spec* spec, int64_t* stats);
  * a test / A-B hook, not a tuning knob. */
 int eg_gcn_plan_select(int mode);
 /* Host-only consistency check of the PATCH plan (the TMA path of the fused kernel on regular 4-neighbour lattices:
- * haloed 8x16 patch + parents + children staged by tensor-map box copies, one 2x2 node block per half-warp): the
- * sources every patch node reads through its box positions and their weights against the closed-form neighbour
- * lists and gcn_norm weights (no GPU needed).  stats (optional): int64[4] = plan usable for this spec (0/1), plain
- * patch tiles, patch tiles with children, CSR tiles.  Returns the number of violations or a negative EG_ERR_* code. */
+ * haloed 8x16 patch + parents staged by tensor-map box copies, one 2x2 node block per half-warp; children either read
+ * directly or -- for the patches of the last aux level -- as ONE pooled row per node written by the main patches of the
+ * same processing unit): the sources every patch node reads through its box positions / child window / pool rows and
+ * their weights against the closed-form neighbour lists and gcn_norm weights, and the unit sequence (a permutation of
+ * the tiles; a unit of several tiles = pool writers followed by their reader).  No GPU needed.  stats (optional):
+ * int64[6] = plan usable for this spec (0/1), plain patch tiles, patch tiles with directly loaded children, CSR tiles,
+ * patch tiles reading their unit's pool, units per frame.  Returns the number of violations or a negative EG_ERR_* code. */
 int eg_graph_patch_check(const eg_graph_spec* spec, int64_t* stats);
 /* edge_index exactly as the reference's loader produces it for a batch of `batch` frames:
  * int64[2, batch*num_edges], grouped by source in the networkx insertion order, frame b offset by

@@ -115,13 +115,14 @@ def test_gather_plan_is_consistent_and_tiles_land_in_their_kernel_class(eg, kw, 
 
 
 @pytest.mark.parametrize("kw,want", [
-    (dict(), (1, 408, 154, 1)),                               # default.yml: one ragged tile (levels 2, 4, 8) stays a CSR tile
-    (dict(use_main_graph_only=True), (1, 392, 0, 0)),
-    (dict(frame_size=448, num_aux_graphs=8), (1, 1688, 562, 1)),
-    (dict(use_coordinate_graph=True), (1, 408, 154, 1)),
-    (dict(use_connection_nodes=True), (0, 0, 0, 0)),          # hubs: the gather plan runs instead
+    # (usable, plain patches, patches with children by direct loads, CSR tiles, patches reading their unit's pool, units)
+    (dict(), (1, 408, 42, 1, 112, 171)),                      # default.yml: 112 families (aux-128 patch + its main patches)
+    (dict(use_main_graph_only=True), (1, 392, 0, 0, 0, 392)),
+    (dict(frame_size=448, num_aux_graphs=8), (1, 1688, 170, 1, 392, 683)),
+    (dict(use_coordinate_graph=True), (1, 408, 42, 1, 112, 171)),
+    (dict(use_connection_nodes=True), (0, 0, 0, 0, 0, 0)),    # hubs: the gather plan runs instead
     (dict(frame_size=64, num_aux_graphs=5), None),
-    (dict(frame_size=32, num_aux_graphs=4, main_graph_type="grid-diagonal", aux_graph_type="grid-diagonal"), (0, 0, 0, 0)),
+    (dict(frame_size=32, num_aux_graphs=4, main_graph_type="grid-diagonal", aux_graph_type="grid-diagonal"), (0, 0, 0, 0, 0, 0)),
     (dict(frame_size=12, num_aux_graphs=3), None),
     (dict(frame_size=96, num_aux_graphs=6), None),
 ])
@@ -130,14 +131,14 @@ def test_patch_plan_reproduces_the_csr(eg, kw, want):
     patch tile against the closed-form neighbour list and gcn_norm weights (bit-equal floats)."""
     from echoglad_b200._lib import lib
     spec = eg.HierGraphSpec(**kw)
-    stats = (ctypes.c_int64 * 4)()
+    stats = (ctypes.c_int64 * 6)()
     assert lib.eg_graph_patch_check(ctypes.byref(spec.c_spec()), stats) == 0
     if want is not None:
         assert tuple(stats) == want
     if stats[0]:
         full = (ctypes.c_int64 * 8)()
         lib.eg_graph_plan_check(ctypes.byref(spec.c_spec()), full)
-        assert stats[1] + stats[2] + stats[3] == full[0]
+        assert stats[1] + stats[2] + stats[3] + stats[4] == full[0]
 
 
 def test_malformed_spec_is_rejected(eg):
