@@ -40,10 +40,13 @@ def main():
     ap.add_argument("--main-only", action="store_true", help="use_main_graph_only graph (all tiles are lattice tiles)")
     ap.add_argument("--frame", type=int, default=224, help="frame size (BASELINE configs[3]: 448 with --naux 8)")
     ap.add_argument("--naux", type=int, default=7)
+    ap.add_argument("--conn", action="store_true", help="use_connection_nodes (hub rows: gather plan, CSR rows)")
+    ap.add_argument("--diag", action="store_true", help="grid-diagonal lattices (gather plan, 8-neighbour rows)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
+    kw = dict(main_graph_type="grid-diagonal", aux_graph_type="grid-diagonal") if args.diag else {}
     g = eg.DeviceGraph.get(eg.HierGraphSpec(frame_size=args.frame, num_aux_graphs=args.naux,
-                                            use_main_graph_only=args.main_only), dev)
+                                            use_main_graph_only=args.main_only, use_connection_nodes=args.conn, **kw), dev)
     B, N = args.batch, g.meta.num_nodes
     rows = B * N
     U = rows * 128 * 4
