@@ -1578,7 +1578,7 @@ int launch_gcn_tc(const eg_graph* g, int batch, const float* X, const float* W, 
   p.Out = Out;
   p.AggOut = AggOut;
   const PatchPlan& pp = graph_patch_plan(g);
-  if (pp.ok && patch_plan_enabled()) {
+  if (pp.ok && patch_plan_enabled() && encode_tiled_fn() != nullptr) {  // (no tensor-map encoder in the driver: gather plan)
     p.patch = pp;
     p.batch = batch;
     if (int rc = graph_pool_scratch(g, s, &p.pool)) return rc;
