@@ -4,41 +4,42 @@
 //
 // Replaces PyG GCNConv = propagate(scatter_add) + nn.Linear (src/core/models.py:330,431) with the
 // re-association A_hat (X W^T) = (A_hat X) W^T (4e-7 rms), so the aggregated rows never
-// touch HBM: producer warps gather/weight/sum the neighbour rows of a 128-node tile (atomic-free,
-// ascending source order, self loop last), split them into tf32 hi/lo parts and write them straight into
-// swizzled shared-memory operand tiles; one elected thread issues 3xTF32 tcgen05.mma into a
-// double-buffered TMEM accumulator; epilogue warps drain it (tcgen05.ld), add bias / residual gradient,
-// accumulate the BatchNorm column statistics and store rows.  With GATHER = false the same pipeline is
-// the plain per-node transform (classifier layer 0 and its input gradient).
+// touch HBM: compute warps gather / weight / sum the neighbour rows of a 128-node tile (atomic-free, fixed order),
+// split the sums into a tf32 part and a bf16 correction part and write them straight into swizzled shared-memory
+// operand tiles; one elected thread issues tcgen05.mma (tf32 main term + one bf16 MMA for both correction terms) into a
+// double-buffered TMEM accumulator; epilogue warps drain it (tcgen05.ld), add bias / residual gradient, accumulate the
+// BatchNorm column statistics and store rows.
+//
+// One body, three MODES that share the MMA issuer, the epilogue and the operand / accumulator rings:
+//   kLinear  plain per-node transform (classifier layer 0 and its input gradient): the tile's own rows are staged;
+//   kGather  any graph (round 1): three LOADER warps copy the tile's unique source rows (own rows + lattice halo +
+//            parents, <= 216 rows x 128 B, eg::TilePlan) with cp.async into a 3-stage raw ring; a lane group of 8 owns a
+//            row (6 LDS.128 + 12 FFMA2 on lattice tiles); the 2x2 children of an aux node are read from global one row
+//            group ahead; hub rows through the device CSR.  Runs graphs with hubs / diagonal lattices;
+//   kPatch   regular 4-neighbour lattices (round 2, see PatchTile in common.cuh): ONE thread stages the haloed 8x16 patch
+//            and the parents with two TMA box copies per chunk (4-deep ring); a half-warp owns a 2x2 node block (13 LDS.64
+//            + 24 FFMA2 per 4 rows); children arrive pooled through the tile's unit (families) or by direct loads issued
+//            one chunk ahead; tiles are walked unit by unit.
 //
 // The product is computed TRANSPOSED, D^T[f][r] = sum_k Wop[f][k] * A[r][k]:
-//   * the weight (hi and lo parts, 2 x 128 TMEM columns) is the M-side operand and lives in TENSOR MEMORY
-//     for the whole kernel, so each MMA reads only the 4 KB node-tile slice from shared memory (half the
+//   * the weight (tf32 part and bf16 correction part, 2 x 128 TMEM columns) is the M-side operand and lives in TENSOR
+//     MEMORY for the whole kernel, so each MMA reads only the 4 KB node-tile slice from shared memory (half the
 //     shared-memory traffic of an SS-mode MMA) and all of shared memory is a ring of operand stages;
 //   * the accumulator has one output feature per TMEM lane and one tile row per column, so an epilogue
 //     thread owns a feature: bias and the column statistics are per-thread scalars, and for a fixed row
 //     the 32 lanes of a warp hold 32 consecutive features = one coalesced 128-byte store.  No staging.
 //
-// Work decomposition.  Tile = 128 output rows (8x16 lattice patches, see eg_graph::tile_nodes); K is
-// consumed in 4 chunks of 32 features.  Per chunk, three LOADER warps copy the tile's unique source rows
-// (own rows + lattice halo + parents, <= 216 rows x 128 B, eg::TilePlan) from global into a 3-stage RAW
-// ring with cp.async -- no registers are held, so ~80 KB per SM are in flight and every neighbour row
-// crosses L2 -> SM once per tile instead of once per edge; 16 COMPUTE warps then gather / weight / sum
-// from shared memory.  A lattice tile (every main-level tile: <= 5 staged neighbours + the row itself) keeps
-// its slot offsets and weights in registers for the whole tile; its inner loop is 6 LDS.128 + 12 FFMA2
-// (packed fp32 pairs) per row.  The 2x2 children of an aux node are not staged (512 rows per tile) and are read
-// from global one row group ahead (general tile class).  The sums are split into tf32 hi/lo and fill a 3-stage
-// OPERAND ring ([128 rows x 128 B] hi + lo = 32 KB).  The compute warps are the critical resource of the
-// kernel (measured: they are busy > 80 % of the time while loaders, MMA and epilogue wait), so everything
-// that can live elsewhere does: row copies in the loader warps, waits with a suspend hint.
+// Tile = 128 output rows (8x16 lattice patches, see eg_graph::tile_nodes); K is consumed in 4 chunks of 32 features; the
+// split sums fill a 3-stage OPERAND ring ([128 rows x 128 B] tf32 + correction = 32 KB per stage).
 // TMEM: 256 columns of weight + 2 x 128 of accumulator.
-// Warps: 0-3 epilogue (TMEM lane quadrant = warp id), 4 MMA issuer, 5-7 loaders, 8-23 compute; the compute
-// warpgroups raise their register budget to 88 with setmaxnreg, the epilogue drops to 72, MMA + loaders to 56.
+// Warps: 0-3 epilogue (TMEM lane quadrant = warp id), 4 MMA issuer, 5-7 loaders (patch mode: 5 = the TMA thread), 8-23
+// compute; register budgets per warpgroup with setmaxnreg (RegBudget below).
 //
-// Development switches (never defined in the shipped build; `EG_NVCC_EXTRA=-D... python echoglad_b200/build.py`,
-// A/B driver tools/gpu_ab.sh): EG_TC_TIMING adds per-role wait-cycle counters (eg_tc_debug_read, printed by
-// tools/kernel_bench.py); EG_DBG_NOGATHER / NOEMIT / NOFENCE / NOCOMPUTE / NOLOAD / NOMMA / NOSTORE / NOEPI /
-// SMALLOUT each remove one piece of work (WRONG results, timing only: the knock-out table of DESIGN.md 4.1).
+// Development switches (never defined in the shipped build; `EG_NVCC_EXTRA=-D... python echoglad_b200/build.py`, prebuilt
+// variants tools/build_variants.sh + tools/gpu_pd.sh): EG_TC_TIMING adds per-role wait-cycle counters (eg_tc_debug_read,
+// printed by tools/kernel_bench.py); EG_DBG_NOGATHER / NOEMIT / NOFENCE / NOCOMPUTE / NOLOAD / NOMMA / NOSTORE / NOEPI /
+// SMALLOUT and EG_PD_NOGATHER / NOCHILD / PLAINAUX / NOPOOLOUT / NOTMA each remove one piece of work (WRONG results,
+// timing only: the knock-out tables of DESIGN.md 4.1); EG_TF32X3 restores the three-MMA tf32 split.
 #include <cuda.h>  // CUtensorMap (the encode function is fetched through cudaGetDriverEntryPoint: no -lcuda)
 
 #include <stdlib.h>
