@@ -79,13 +79,20 @@ bce_kernel(long long n4, long long n, const float* __restrict__ x, const float* 
   }
 }
 
-__global__ void bce_finalize_kernel(int nparts, const double* __restrict__ parts, float loss_weight,
-                                    float* __restrict__ loss_out, float* __restrict__ scale_out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// one block of kThreads: thread t sums partials t, t + kThreads, ... (ascending), block_sum combines in fixed order
+// (a single thread walking all <= 592 partials took 42 us)
+__global__ void __launch_bounds__(kThreads)
+bce_finalize_kernel(int nparts, const double* __restrict__ parts, float loss_weight,
+                    float* __restrict__ loss_out, float* __restrict__ scale_out) {
+  __shared__ double sh[8];
   double num = 0.0, den = 0.0;
-  for (int p = 0; p < nparts; ++p) { num += parts[2 * p]; den += parts[2 * p + 1]; }
-  *loss_out = (float)((double)loss_weight * num / den);
-  *scale_out = (float)((double)loss_weight / den);
+  for (int p = threadIdx.x; p < nparts; p += blockDim.x) { num += parts[2 * p]; den += parts[2 * p + 1]; }
+  num = block_sum(num, sh);
+  den = block_sum(den, sh);
+  if (threadIdx.x == 0) {
+    *loss_out = (float)((double)loss_weight * num / den);
+    *scale_out = (float)((double)loss_weight / den);
+  }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -128,20 +135,32 @@ struct Levels {
   int total;
 };
 
-// grid = batch * levels; block handles one level of one frame, all 4 channels.
+// Softmax moments of one (frame, level) segment, all 4 channels.  grid = (batch * levels, kSegSplits): a segment of more
+// than kSplitMin nodes is cut into kSegSplits slices, one block each (one block per segment left 84 of 148 SMs idle
+// while 64 blocks walked the 50176-node main level three times: 0.26 ms); every block keeps its own running maximum
+// ("online softmax") and elmse_combine_kernel merges the slices in fixed order.
+constexpr int kSegSplits = 8, kSplitMin = 4096;
+struct SegPart {  // one slice
+  float xmax[4], ymax[4], sumexp[4], sum_h[4], sum_w[4], vsum[4];
+  int min_h[4], min_w[4];
+};
+
 __global__ void __launch_bounds__(kThreads)
 elmse_stats_kernel(Levels lv, const float* __restrict__ x, const float* __restrict__ y,
-                   const float* __restrict__ valid, SegStat* __restrict__ seg) {
+                   const float* __restrict__ valid, SegPart* __restrict__ part) {
   __shared__ double shd[8];
   __shared__ float shf[8];
   __shared__ int shi[8];
   const int b = blockIdx.x / lv.n, l = blockIdx.x % lv.n;
   const int g = lv.size[l], n = g * g;
+  const int splits = n > kSplitMin ? kSegSplits : 1;
+  if ((int)blockIdx.y >= splits) return;
+  const int per = (n + splits - 1) / splits, i0 = blockIdx.y * per, i1 = min(n, i0 + per);
   const long long base = ((long long)b * lv.total + lv.start[l]) * 4;
   float xm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   float ym[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   float vs[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     float4 a = ldg4(x + base + (long long)i * 4), c = ldg4(y + base + (long long)i * 4);
     float4 d = ldg4(valid + base + (long long)i * 4);
     xm[0] = fmaxf(xm[0], a.x); xm[1] = fmaxf(xm[1], a.y); xm[2] = fmaxf(xm[2], a.z); xm[3] = fmaxf(xm[3], a.w);
@@ -157,7 +176,7 @@ elmse_stats_kernel(Levels lv, const float* __restrict__ x, const float* __restri
   }
   float se[4] = {0.f, 0.f, 0.f, 0.f}, sh_[4] = {0.f, 0.f, 0.f, 0.f}, sw_[4] = {0.f, 0.f, 0.f, 0.f};
   int mh[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX}, mw[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX};
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {  // (the slice is L2-resident from the first pass)
     float4 a = ldg4(x + base + (long long)i * 4), c = ldg4(y + base + (long long)i * 4);
     const int h = i / g, w = i - h * g;
     float av[4] = {a.x, a.y, a.z, a.w}, cv[4] = {c.x, c.y, c.z, c.w};
@@ -170,6 +189,7 @@ elmse_stats_kernel(Levels lv, const float* __restrict__ x, const float* __restri
       if (cv[k] == ym[k]) { mh[k] = min(mh[k], h); mw[k] = min(mw[k], w); }
     }
   }
+  SegPart& o = part[(size_t)blockIdx.x * kSegSplits + blockIdx.y];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     double s = block_sum((double)se[k], shd);
@@ -177,31 +197,61 @@ elmse_stats_kernel(Levels lv, const float* __restrict__ x, const float* __restri
     double ew = block_sum((double)sw_[k], shd);
     int gh = block_min(mh[k], shi), gw = block_min(mw[k], shi);
     if (threadIdx.x == 0) {
-      SegStat& o = seg[blockIdx.x];
-      o.e_h[k] = (float)(eh / s);
-      o.e_w[k] = (float)(ew / s);
-      o.gt_h[k] = (float)gh;
-      o.gt_w[k] = (float)gw;
-      o.v[k] = (float)(vsum[k] / (double)n);
-      o.xmax[k] = xm[k];
-      o.sumexp[k] = (float)s;
+      o.xmax[k] = xm[k], o.ymax[k] = ym[k];
+      o.sumexp[k] = (float)s, o.sum_h[k] = (float)eh, o.sum_w[k] = (float)ew;
+      o.vsum[k] = (float)vsum[k];
+      o.min_h[k] = gh, o.min_w[k] = gw;
     }
   }
 }
 
-// one block: loss and the per-segment gradient coefficients
-__global__ void elmse_finalize_kernel(Levels lv, int batch, float loss_weight, SegStat* __restrict__ seg,
-                                      float* __restrict__ loss_out) {
+// thread = (segment, channel): merges the slices of a segment in ascending order (double), rescaling every slice's sums
+// to the segment maximum
+__global__ void elmse_combine_kernel(Levels lv, int nseg, const SegPart* __restrict__ part, SegStat* __restrict__ seg) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nseg * 4) return;
+  const int sgi = idx >> 2, k = idx & 3, l = sgi % lv.n;
+  const int n = lv.size[l] * lv.size[l], splits = n > kSplitMin ? kSegSplits : 1;
+  const SegPart* p = part + (size_t)sgi * kSegSplits;
+  float xm = -INFINITY, ym = -INFINITY;
+  for (int j = 0; j < splits; ++j) xm = fmaxf(xm, p[j].xmax[k]), ym = fmaxf(ym, p[j].ymax[k]);
+  double s = 0.0, eh = 0.0, ew = 0.0, vs = 0.0;
+  int gh = INT_MAX, gw = INT_MAX;
+  for (int j = 0; j < splits; ++j) {
+    const double r = (double)expf(p[j].xmax[k] - xm);  // 1 for the slice that holds the maximum
+    s += r * (double)p[j].sumexp[k];
+    eh += r * (double)p[j].sum_h[k];
+    ew += r * (double)p[j].sum_w[k];
+    vs += (double)p[j].vsum[k];
+    if (p[j].ymax[k] == ym) gh = min(gh, p[j].min_h[k]), gw = min(gw, p[j].min_w[k]);
+  }
+  SegStat& o = seg[sgi];
+  o.e_h[k] = (float)(eh / s);
+  o.e_w[k] = (float)(ew / s);
+  o.gt_h[k] = (float)gh;
+  o.gt_w[k] = (float)gw;
+  o.v[k] = (float)(vs / (double)n);
+  o.xmax[k] = xm;
+  o.sumexp[k] = (float)s;
+}
+
+// one block: loss and the per-segment gradient coefficients.  A WARP per (level, channel), its lanes over the frames
+// (64 threads walking the frames one by one took 95 us); sums in fixed order (lane-strided partials, xor tree).
+__global__ void __launch_bounds__(kThreads)
+elmse_finalize_kernel(Levels lv, int batch, float loss_weight, SegStat* __restrict__ seg,
+                      float* __restrict__ loss_out) {
   __shared__ double sh[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   double total = 0.0;
-  for (int idx = threadIdx.x; idx < lv.n * 4; idx += blockDim.x) {
+  for (int idx = warp; idx < lv.n * 4; idx += nwarps) {
     const int l = idx / 4, k = idx % 4;
     const double g = (double)lv.size[l];
     double nv = 0.0;
-    for (int b = 0; b < batch; ++b) nv += (double)seg[b * lv.n + l].v[k];
+    for (int b = lane; b < batch; b += 32) nv += (double)seg[b * lv.n + l].v[k];
+    for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
     if (nv == 0.0) nv = 1.0;
     double acc = 0.0;
-    for (int b = 0; b < batch; ++b) {
+    for (int b = lane; b < batch; b += 32) {
       SegStat& s = seg[b * lv.n + l];
       const double dh = (double)s.e_h[k] / g - (double)s.gt_h[k] / g;
       const double dw = (double)s.e_w[k] / g - (double)s.gt_w[k] / g;
@@ -209,7 +259,8 @@ __global__ void elmse_finalize_kernel(Levels lv, int batch, float loss_weight, S
       s.c_h[k] = (float)((double)loss_weight * 2.0 * dh / g * (double)s.v[k] / nv);
       s.c_w[k] = (float)((double)loss_weight * 2.0 * dw / g * (double)s.v[k] / nv);
     }
-    total += acc / nv;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) total += acc / nv;
   }
   total = block_sum(total, sh);
   if (threadIdx.x == 0) *loss_out = (float)((double)loss_weight * total);
@@ -377,7 +428,7 @@ int eg_bce_multilevel(int64_t n, const float* logits, const float* y, const floa
   ProfileScope prof("bce", s);
   bce_kernel<<<grid, kThreads, 0, s>>>(n4, n, logits, y, valid, ones_weight, dlogits, parts);
   EG_LAUNCH_CHECK();
-  bce_finalize_kernel<<<1, 32, 0, s>>>(grid, parts, loss_weight, loss_out, scale);
+  bce_finalize_kernel<<<1, kThreads, 0, s>>>(grid, parts, loss_weight, loss_out, scale);
   EG_LAUNCH_CHECK();
   if (dlogits) {
     scale_kernel<<<grid, kThreads, 0, s>>>(n, dlogits, scale);
@@ -394,17 +445,22 @@ int eg_expected_landmark_mse(int batch, int channels, int num_levels, const int3
                channels);
   Levels lv;
   EG_CHECK_ARG(make_levels(num_levels, level_size, lv) == 0, "eg_expected_landmark_mse: bad level list");
-  const size_t need = sizeof(SegStat) * (size_t)batch * num_levels;
+  const size_t nseg = (size_t)batch * num_levels;
+  const size_t seg_bytes = (sizeof(SegStat) * nseg + 255) / 256 * 256;
+  const size_t need = seg_bytes + sizeof(SegPart) * nseg * kSegSplits;
   if (!ws || ws_bytes < need || ws_bytes < kWorkspaceBytes) {
     set_error("workspace too small: need %zu bytes", need > kWorkspaceBytes ? need : kWorkspaceBytes);
     return EG_ERR_WORKSPACE;
   }
   cudaStream_t s = as_stream(stream);
   SegStat* seg = reinterpret_cast<SegStat*>(ws);
+  SegPart* part = reinterpret_cast<SegPart*>(reinterpret_cast<char*>(ws) + seg_bytes);
   ProfileScope prof("elmse", s);
-  elmse_stats_kernel<<<batch * num_levels, kThreads, 0, s>>>(lv, logits, y, valid, seg);
+  elmse_stats_kernel<<<dim3((unsigned)nseg, kSegSplits), kThreads, 0, s>>>(lv, logits, y, valid, part);
   EG_LAUNCH_CHECK();
-  elmse_finalize_kernel<<<1, 64, 0, s>>>(lv, batch, loss_weight, seg, loss_out);
+  elmse_combine_kernel<<<(unsigned)((nseg * 4 + 127) / 128), 128, 0, s>>>(lv, (int)nseg, part, seg);
+  EG_LAUNCH_CHECK();
+  elmse_finalize_kernel<<<1, kThreads, 0, s>>>(lv, batch, loss_weight, seg, loss_out);
   EG_LAUNCH_CHECK();
   if (dlogits) {
     dim3 grid(batch * num_levels, 8);
