@@ -144,38 +144,41 @@ bn_act_bwd_reduce_kernel(long long rows, int cols, const float* __restrict__ dY,
 
 // Fixed-order sum of per-CTA partials parts[p][2][stride] (p < nparts) for column c, split over kSplit threads:
 // thread k sums p = k, k + kSplit, ... in order, the kSplit sub-sums are combined in order through shared memory.
-// Deterministic for a given nparts; 8x fewer dependent L2 round trips than one thread per column.
-constexpr int kSplit = 8;
+// Deterministic for a given nparts.  Blocks of kFinCols columns x kSplit splits (one block of 128 x 8 walked up to 74
+// dependent L2 round trips per thread: 51 us for 592 partials; 32 splits over 4 blocks: 19).
+constexpr int kSplit = 32, kFinCols = 32;
 __device__ __forceinline__ void split_sum2(int nparts, int stride, const double* __restrict__ parts, int c, int k,
-                                           double (*red)[2][128], double& a, double& b) {
+                                           double (*red)[2][kFinCols], double& a, double& b) {
+  const int cl = threadIdx.x;  // column inside the block
   double sa = 0.0, sb = 0.0;
   for (int p = k; p < nparts; p += kSplit) {
     sa += parts[(size_t)p * 2 * stride + c];
     sb += parts[(size_t)p * 2 * stride + stride + c];
   }
-  red[k][0][c] = sa;
-  red[k][1][c] = sb;
+  red[k][0][cl] = sa;
+  red[k][1][cl] = sb;
   __syncthreads();
   a = b = 0.0;
   if (k == 0) {
 #pragma unroll
     for (int q = 0; q < kSplit; ++q) {
-      a += red[q][0][c];
-      b += red[q][1][c];
+      a += red[q][0][cl];
+      b += red[q][1][cl];
     }
   }
 }
 
 // finalize: dbeta = sum dA, dgamma = sum dA*xhat, coef = (sum dA / rows, sum dA*xhat / rows)
-// launch: <<<1, dim3(128, kSplit)>>>
+// launch: <<<(cols + kFinCols - 1) / kFinCols, dim3(kFinCols, kSplit)>>>
 __global__ void bn_bwd_finalize_kernel(int nparts, int cols, long long rows, const double* __restrict__ parts,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ coef) {
-  __shared__ double red[kSplit][2][128];
-  const int c = threadIdx.x < cols ? threadIdx.x : cols - 1, k = threadIdx.y;
+  __shared__ double red[kSplit][2][kFinCols];
+  const int cg = blockIdx.x * kFinCols + threadIdx.x;
+  const int c = cg < cols ? cg : cols - 1, k = threadIdx.y;
   double a, b;
   split_sum2(nparts, cols, parts, c, k, red, a, b);
-  if (k != 0 || threadIdx.x >= cols) return;
+  if (k != 0 || cg >= cols) return;
   if (dbeta) dbeta[c] = (float)a;
   if (dgamma) dgamma[c] = (float)b;
   coef[c] = (float)(a / (double)rows);
@@ -265,15 +268,16 @@ col_stats_kernel(long long rows, int cols, const float* __restrict__ Z, double* 
   }
 }
 
-// launch: <<<1, dim3(128, kSplit)>>>
+// launch: <<<(cols + kFinCols - 1) / kFinCols, dim3(kFinCols, kSplit)>>>
 __global__ void stats_finalize_kernel(int nparts, int cols, int stride, long long rows,
                                       const double* __restrict__ parts, float* __restrict__ mean,
                                       float* __restrict__ var) {
-  __shared__ double red[kSplit][2][128];
-  const int c = threadIdx.x < cols ? threadIdx.x : cols - 1, k = threadIdx.y;
+  __shared__ double red[kSplit][2][kFinCols];
+  const int cg = blockIdx.x * kFinCols + threadIdx.x;
+  const int c = cg < cols ? cg : cols - 1, k = threadIdx.y;
   double s, q;
   split_sum2(nparts, stride, parts, c, k, red, s, q);
-  if (k != 0 || threadIdx.x >= cols) return;
+  if (k != 0 || cg >= cols) return;
   double m = s / (double)rows;
   double v = q / (double)rows - m * m;
   mean[c] = (float)m;
@@ -319,7 +323,7 @@ inline int reduce_grid(long long rows, int cols, int blocks_per_sm = kMaxParts /
 namespace eg {
 int launch_stats_finalize(int nparts, int cols, int stride, long long rows, const double* parts, float* mean,
                           float* var, cudaStream_t s) {
-  stats_finalize_kernel<<<1, dim3(128, kSplit), 0, s>>>(nparts, cols, stride, rows, parts, mean, var);
+  stats_finalize_kernel<<<(cols + kFinCols - 1) / kFinCols, dim3(kFinCols, kSplit), 0, s>>>(nparts, cols, stride, rows, parts, mean, var);
   EG_LAUNCH_CHECK();
   return EG_OK;
 }
@@ -395,7 +399,7 @@ int eg_bn_act_bwd(int64_t rows, int cols, const float* dY, const float* H, const
   bn_act_bwd_reduce_kernel<<<grid, kThreads, 0, s>>>(rows, cols, dY, H, mean, var, gamma, beta, eps, thr, ks, seed,
                                                      relu, batch_stats ? nullptr : dH, parts);
   EG_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<1, dim3(128, kSplit), 0, s>>>(grid, cols, rows, parts, dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(cols + kFinCols - 1) / kFinCols, dim3(kFinCols, kSplit), 0, s>>>(grid, cols, rows, parts, dgamma, dbeta, coef);
   EG_LAUNCH_CHECK();
   if (batch_stats) {
     const long long groups = rows * (cols / 4);
