@@ -97,7 +97,10 @@ def test_tile_table_is_a_permutation_of_the_frame():
 
 @pytest.mark.parametrize("key,batch", [("S12_n3_mo0_co0_cn0_grid_grid", 3), ("S16_n3_mo0_co0_cn1_grid_grid", 2),
                                        ("S32_n4_mo0_co0_cn0_grid_grid", 5), ("S56_n5_mo0_co0_cn0_grid_grid", 2),
-                                       ("S9_n0_mo1_co0_cn0_grid-diagonal_grid", 4)])
+                                       ("S9_n0_mo1_co0_cn0_grid-diagonal_grid", 4),
+                                       # patch plan variants: crop 4 (no families: every coarse patch loads its children
+                                       # directly, also from the main level), crop 8 with 24 families and a 4-level pool-free tail
+                                       ("S48_n5_mo0_co0_cn0_grid_grid", 3), ("S96_n6_mo0_co0_cn0_grid_grid", 2)])
 def test_gcn_conv_fwd_bwd_entry_points(key, batch):
     """eg_gcn_conv_fwd / eg_gcn_conv_bwd (the fused tcgen05 kernel) against the fp64 oracle GCNConv."""
     from echoglad_b200._lib import WORKSPACE_BYTES
