@@ -85,6 +85,7 @@ SIGNATURES = {
     "eg_gcn_aggregate": (_I, [_P, _I, _I, _P, _P, _P]),
     "eg_gcn_conv_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "eg_gcn_conv_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "eg_gcn_layer_eval_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, C.c_float, _I, _I, _P, _P, _SZ, _P]),
     "eg_bn_act_fwd": (_I, [_L, _I, _P, _P, _P, _P, _P, _F, _F, _U64, _I, _P, _P, _P]),
     "eg_bn_act_bwd": (_I, [_L, _I, _P, _P, _P, _P, _P, _P, _F, _F, _U64, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "eg_dropout_mask": (_I, [_L, _I, _F, _U64, _P, _P]),

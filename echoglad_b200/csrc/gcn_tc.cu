@@ -163,6 +163,10 @@ struct TcParams {
   float* Out;
   float* AggOut;              // optional: the aggregated rows A_hat X themselves
   double* stat_parts;         // optional: [gridDim.x][2][128] column sum / sum of squares partials
+  // EPI instances only (inference layer): Out = act(acc * ep_scale[f] + ep_shift[f]) + addend
+  const float* ep_scale;
+  const float* ep_shift;
+  int ep_relu;
 };
 
 #ifdef EG_TC_TIMING
@@ -418,7 +422,10 @@ __device__ EG_AUX_INLINE void patch_aux_tile(AuxTileArgs& a) {
   a.chunk = chunk;
 }
 
-template <int MODE>
+// EPI: the epilogue applies a per-feature affine map and an optional ReLU to the accumulator before the addend -- an
+// eval-mode GNN layer (conv bias + BatchNorm with running statistics + activation + residual) in ONE launch.  A separate
+// instance, so the training kernels' code is exactly what it was.
+template <int MODE, bool EPI = false>
 __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) {
   constexpr bool GATHER = MODE != kLinear;
   using L = Lay<MODE>;
@@ -1257,6 +1264,13 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
     const int ew = warp;             // TMEM lanes [32 ew, 32 ew + 32)
     const int f = ew * 32 + lane;    // output feature owned by this thread
     const float bias = p.bias ? __ldg(p.bias + f) : 0.f;
+    float ep_sc = 1.f, ep_sh = 0.f;
+    if constexpr (EPI) ep_sc = __ldg(p.ep_scale + f), ep_sh = __ldg(p.ep_shift + f);
+    auto ep_map = [&](float v) {
+      const float y = fmaf(v, ep_sc, ep_sh);
+      return p.ep_relu ? fmaxf(y, 0.f) : y;
+    };
+    (void)ep_sc, (void)ep_sh, (void)ep_map;
     double s_sum = 0.0, s_sq = 0.0;
     // row groups of a tile: lane l < 8 holds the first global row of group l (or -1), lane 8 + l its row count.
     // They are fetched ONE TILE AHEAD (the table read is a dependent global load that would otherwise be exposed
@@ -1331,7 +1345,9 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             if (i < cnt) {  // warp-uniform predicate
-              const float o = __uint_as_float(v[i]) + bias + ad[i];
+              float o;
+              if constexpr (EPI) o = ep_map(__uint_as_float(v[i])) + ad[i];
+              else o = __uint_as_float(v[i]) + bias + ad[i];
               out[i * 128] = o;
               if (p.stat_parts) {  // (no caller asks for both today; kept for the ABI)
                 s += o;
@@ -1366,7 +1382,11 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
 #endif
           float s = 0.f, q = 0.f;
           tmem_ld_wait();
-          if (cnt == 16) {
+          if constexpr (EPI) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < cnt) EG_ST_OUT(out + i * 128, ep_map(__uint_as_float(v[i])));  // warp-uniform predicate
+          } else if (cnt == 16) {
             // two rows per packed instruction: o = v + bias, s += o, q += o * o  (24 instead of 48 issue slots)
             const F2 b2 = f2_pack(bias, bias);
             F2 s2 = f2_pack(0.f, 0.f), q2 = s2;
@@ -1437,15 +1457,16 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
   }
 }
 
-template <int MODE>
+template <int MODE, bool EPI>
 __global__ void __launch_bounds__(kThreads, 1) gcn_tc_kernel(const TcParams p) {
-  tc_body<MODE>(p, nullptr);
+  tc_body<MODE, EPI>(p, nullptr);
 }
+template <bool EPI>
 __global__ void __launch_bounds__(kThreads, 1) gcn_patch_kernel(const TcParams p, const __grid_constant__ PatchMaps pm) {
-  tc_body<kPatch>(p, &pm);
+  tc_body<kPatch, EPI>(p, &pm);
 }
 
-template <int MODE>
+template <int MODE, bool EPI = false>
 int launch(const TcParams& p, const PatchMaps* pm, float* mean, float* var, void* ws, size_t ws_bytes, const char* name,
            cudaStream_t s) {
   const bool stats = mean && var;
@@ -1456,9 +1477,9 @@ int launch(const TcParams& p, const PatchMaps* pm, float* mean, float* var, void
   static std::atomic<unsigned long long> attr_mask{0};  // per template instance, one bit per device
   if (first_use_on_current_device(attr_mask)) {
     if (MODE == kPatch)
-      EG_CUDA(cudaFuncSetAttribute(gcn_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<MODE>::kSmemBytes));
+      EG_CUDA(cudaFuncSetAttribute(gcn_patch_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<MODE>::kSmemBytes));
     else
-      EG_CUDA(cudaFuncSetAttribute(gcn_tc_kernel<MODE == kPatch ? kGather : MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      EG_CUDA(cudaFuncSetAttribute(gcn_tc_kernel<MODE == kPatch ? kGather : MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)Lay<MODE>::kSmemBytes));
   }
   const int sms = num_sms();
@@ -1469,9 +1490,9 @@ int launch(const TcParams& p, const PatchMaps* pm, float* mean, float* var, void
   {
     ProfileScope prof(name, s);
     if (MODE == kPatch)
-      gcn_patch_kernel<<<grid, kThreads, Lay<MODE>::kSmemBytes, s>>>(q, *pm);
+      gcn_patch_kernel<EPI><<<grid, kThreads, Lay<MODE>::kSmemBytes, s>>>(q, *pm);
     else
-      gcn_tc_kernel<MODE == kPatch ? kGather : MODE><<<grid, kThreads, Lay<MODE>::kSmemBytes, s>>>(q);
+      gcn_tc_kernel<MODE == kPatch ? kGather : MODE, EPI><<<grid, kThreads, Lay<MODE>::kSmemBytes, s>>>(q);
     EG_LAUNCH_CHECK();
   }
   if (stats) return launch_stats_finalize(grid, 128, 128, p.rows, q.stat_parts, mean, var, s);
@@ -1551,12 +1572,15 @@ extern "C" int eg_tc_debug_read(long long* out) {  // HOST buffer of kNumSMs * 1
 
 namespace eg {
 
-// Out = (A_hat X) op(W) + bias + addend over the batched graph; AggOut (optional) receives A_hat X.
-int launch_gcn_tc(const eg_graph* g, int batch, const float* X, const float* W, int trans_w, const float* bias,
-                  const float* addend, float* Out, float* AggOut, float* mean, float* var, void* ws, size_t ws_bytes,
-                  cudaStream_t s) {
+template <bool EPI>
+static int launch_gcn_any(const eg_graph* g, int batch, const float* X, const float* W, int trans_w, const float* bias,
+                          const float* addend, float* Out, float* AggOut, float* mean, float* var, void* ws,
+                          size_t ws_bytes, const float* ep_scale, const float* ep_shift, int ep_relu, cudaStream_t s) {
   const eg_graph_info& info = graph_info(g);
   TcParams p{};
+  p.ep_scale = ep_scale;
+  p.ep_shift = ep_shift;
+  p.ep_relu = ep_relu;
   p.tile_nodes = graph_tile_nodes(g);
   p.tile_groups = graph_tile_groups(g);
   p.plan = graph_plan(g);
@@ -1585,9 +1609,25 @@ int launch_gcn_tc(const eg_graph* g, int batch, const float* X, const float* W, 
     if (int rc = graph_pool_scratch(g, s, &p.pool)) return rc;
     PatchMaps maps;
     if (int rc = encode_patch_maps(info, batch, X, maps)) return rc;
-    return launch<kPatch>(p, &maps, mean, var, ws, ws_bytes, AggOut ? "gcn_tc_bwd" : "gcn_tc_fwd", s);
+    return launch<kPatch, EPI>(p, &maps, mean, var, ws, ws_bytes, EPI ? "gcn_tc_eval" : AggOut ? "gcn_tc_bwd" : "gcn_tc_fwd", s);
   }
-  return launch<kGather>(p, nullptr, mean, var, ws, ws_bytes, AggOut ? "gcn_tc_bwd" : "gcn_tc_fwd", s);
+  return launch<kGather, EPI>(p, nullptr, mean, var, ws, ws_bytes, EPI ? "gcn_tc_eval" : AggOut ? "gcn_tc_bwd" : "gcn_tc_fwd", s);
+}
+
+// Out = (A_hat X) op(W) + bias + addend over the batched graph; AggOut (optional) receives A_hat X.
+int launch_gcn_tc(const eg_graph* g, int batch, const float* X, const float* W, int trans_w, const float* bias,
+                  const float* addend, float* Out, float* AggOut, float* mean, float* var, void* ws, size_t ws_bytes,
+                  cudaStream_t s) {
+  return launch_gcn_any<false>(g, batch, X, W, trans_w, bias, addend, Out, AggOut, mean, var, ws, ws_bytes, nullptr,
+                               nullptr, 0, s);
+}
+
+// Out = act((A_hat X) W^T * scale + shift) + addend: an eval-mode GNN layer in one launch (scale / shift: device
+// float[128], the conv bias and the BatchNorm running statistics folded by the caller).
+int launch_gcn_tc_eval(const eg_graph* g, int batch, const float* X, const float* W, const float* scale,
+                       const float* shift, int relu, const float* addend, float* Out, cudaStream_t s) {
+  return launch_gcn_any<true>(g, batch, X, W, 1, nullptr, addend, Out, nullptr, nullptr, nullptr, nullptr, 0, scale,
+                              shift, relu, s);
 }
 
 // C = A op(W) + bias + addend (C may alias A: a tile is read completely before its epilogue writes it).

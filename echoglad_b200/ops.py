@@ -416,8 +416,22 @@ class GCNLayer(torch.autograd.Function):
         rows = batch * graph.meta.num_nodes
         if tuple(x.shape) != (rows, F) or tuple(w.shape) != (F, F):
             raise EchogladError(f"GCNLayer: x {tuple(x.shape)} / W {tuple(w.shape)} do not match rows={rows}, F={F}")
-        h = torch.empty_like(x)
         ws = _ws(x.device)
+        if not training and not residual and CAPTURE_RELU is None and not any(ctx.needs_input_grad):
+            # inference (model.eval() under torch.no_grad(), src/engine.py:343-350) of a layer WITHOUT the residual
+            # branch: the whole layer is one launch and the pre-activation is never written (1.22 ms against 2.32 ms at
+            # default.yml / batch 64).  With the residual the epilogue's extra row reads make the single launch the
+            # slower route (2.65 ms, profiles/r02_patch_experiments.txt r02ac/ad), so that case keeps the two launches.
+            mean, var = _f32(mean_in, "running_mean"), _f32(var_in, "running_var")
+            y = torch.empty_like(x)
+            check(lib.eg_gcn_layer_eval_fwd(graph.handle, batch, x.data_ptr(), w.data_ptr(), _ptr(bias),
+                                            _f32(gamma, "gamma").data_ptr(), _f32(beta, "beta").data_ptr(),
+                                            mean.data_ptr(), var.data_ptr(), float(eps), int(relu), int(residual),
+                                            y.data_ptr(), ws.data_ptr(), WORKSPACE_BYTES, _stream(x)),
+                  "eg_gcn_layer_eval_fwd")
+            ctx.mark_non_differentiable(mean, var)
+            return y, mean, var
+        h = torch.empty_like(x)
         if training:
             mean = torch.empty(F, device=x.device)
             var = torch.empty(F, device=x.device)

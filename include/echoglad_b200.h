@@ -160,6 +160,17 @@ int eg_gcn_conv_fwd(const eg_graph* g, int batch, const float* X, const float* W
 int eg_gcn_conv_bwd(const eg_graph* g, int batch, const float* X, const float* W, const float* dH,
                     const float* dX_add, float* dX, float* dW, float* dbias, float* scratch, void* ws,
                     size_t ws_bytes, void* stream);
+/* One whole GNN layer in EVAL mode (model.eval(): BatchNorm1d with its running statistics, Dropout off) as ONE launch of
+ * the fused kernel: Y = act(gamma * (A_hat X W^T + bias - running_mean) / sqrt(running_var + eps) + beta) (+ X if
+ * residual) -- replaces gnn_layers[i].module_0..3 and `h + hidden_embeds[i]` of src/core/models.py:329-335,431-435 when
+ * no gradient is needed (validation / inference under torch.no_grad(), src/engine.py:343-350,383-405).  The pre-activation H is never written:
+ * 2 (+1 with the residual) node tensors cross HBM per layer instead of 5 for eg_gcn_conv_fwd + eg_bn_act_fwd.  Measured
+ * at default.yml / batch 64: 1.22 ms without the residual, 2.65 ms with it (the two launches: 2.32 ms) -- the module takes
+ * this route for residual-free layers only.  bias may be NULL; relu: 1 = ReLU,
+ * 0 = identity (the last layer).  X, Y: float[batch*N,128], not aliased.  ws: at least 1024 bytes of device scratch. */
+int eg_gcn_layer_eval_fwd(const eg_graph* g, int batch, const float* X, const float* W, const float* bias,
+                          const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                          float eps, int relu, int residual, float* Y, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- fused BatchNorm1d-apply + Dropout + ReLU|Identity + residual ----------------------------------
  * replaces gnn_layers[i].module_1..3 and `h + hidden_embeds[i]` (src/core/models.py:332-335,434-435)

@@ -247,6 +247,53 @@ def _fused_vs_csr(kw, batch):
     assert ok, f"dW {worst}"
 
 
+@pytest.mark.parametrize("kw,batch", [(dict(), 2), (dict(frame_size=48, num_aux_graphs=5), 3),
+                                      (dict(use_connection_nodes=True), 1)])
+@pytest.mark.parametrize("relu,residual", [(True, True), (False, True), (True, False)])
+@pytest.mark.parametrize("plan", ["auto", "gather"])
+def test_eval_layer_in_one_launch_equals_the_unfused_eval_route(kw, batch, relu, residual, plan):
+    """`eg_gcn_layer_eval_fwd` (conv bias + running-statistics BatchNorm + activation + residual in the fused kernel's
+    epilogue) against (a) the fp64 formula on the CSR aggregation and (b) the two-launch eval route of the same layer
+    (`eg_gcn_conv_fwd` + `eg_bn_act_fwd`), which `ops.GCNLayer` takes when a gradient is needed.  Values within 1e-3 of
+    zero before the ReLU may land on either side of it: the comparison uses the absolute floor 1e-5 max|b|."""
+    prev = ops.lib.eg_gcn_plan_select(1 if plan == "gather" else 0)
+    try:
+        g = eg.DeviceGraph.get(eg.HierGraphSpec(**kw), DEV)
+        rows = batch * g.meta.num_nodes
+        gen = torch.Generator(device=DEV).manual_seed(rows + 7)
+        x = torch.randn(rows, 128, device=DEV, generator=gen)
+        w = torch.randn(128, 128, device=DEV, generator=gen) * 0.1
+        bias, beta = (torch.randn(128, device=DEV, generator=gen) for _ in range(2))
+        gamma = torch.rand(128, device=DEV, generator=gen) + 0.5
+        rmean = torch.randn(128, device=DEV, generator=gen) * 0.3
+        rvar = torch.rand(128, device=DEV, generator=gen) + 0.25
+        args = (g, batch, x, w, bias, gamma, beta, rmean, rvar, False, 1e-5, 0.5, 123, relu, residual)
+        fused = torch.empty_like(x)
+        ws = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=DEV)
+        ops.check(ops.lib.eg_gcn_layer_eval_fwd(g.handle, batch, x.data_ptr(), w.data_ptr(), bias.data_ptr(),
+                                                gamma.data_ptr(), beta.data_ptr(), rmean.data_ptr(), rvar.data_ptr(),
+                                                1e-5, int(relu), int(residual), fused.data_ptr(), ws.data_ptr(),
+                                                WORKSPACE_BYTES, torch.cuda.current_stream().cuda_stream))
+        with torch.no_grad():  # the module-facing op: one launch for residual-free layers, two otherwise
+            via_op = ops.GCNLayer.apply(*args)[0]
+        ok, worst = close(via_op.cpu(), fused.cpu(), 1e-5, 1e-5)
+        assert ok, f"op vs entry point {worst}"
+        xg = x.clone().requires_grad_()
+        unfused = ops.GCNLayer.apply(g, batch, xg, *args[3:])[0].detach()
+        h = ops.gcn_aggregate(g, batch, x).double() @ w.double().t() + bias.double()
+        want = (h - rmean.double()) / torch.sqrt(rvar.double() + 1e-5) * gamma.double() + beta.double()
+        if relu:
+            want = want.clamp_min(0)
+        if residual:
+            want = want + x.double()
+        ok, worst = close(fused.cpu(), want.cpu(), 1e-4, 1e-5)
+        assert ok, f"fused vs fp64 {worst}"
+        ok, worst = close(fused.cpu(), unfused.cpu(), 1e-5, 1e-5)
+        assert ok, f"fused vs two launches {worst}"
+    finally:
+        ops.lib.eg_gcn_plan_select(prev)
+
+
 # ---- dense transforms -----------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("rows", [1, 127, 128, 1000, 40000])

@@ -72,6 +72,15 @@ def main():
                                                            P(ws), WORKSPACE_BYTES, st)), 2 * U),
         "gcn_conv_bwd": (lambda: check(lib.eg_gcn_conv_bwd(g.handle, B, P(x), P(w), P(dy), P(h), P(out), P(dw), None,
                                                            P(scratch), P(ws), WORKSPACE_BYTES, st)), 6 * U),
+        # eval-mode layer in one launch (reads X twice: gathered + residual rows, writes Y)
+        "gcn_layer_eval": (lambda: check(lib.eg_gcn_layer_eval_fwd(g.handle, B, P(x), P(w), P(bias), P(gamma), P(beta),
+                                                                   P(mean), P(var), 1e-5, 1, 1, P(out), P(ws),
+                                                                   WORKSPACE_BYTES, st)), 3 * U),
+        "gcn_layer_eval_nores": (lambda: check(lib.eg_gcn_layer_eval_fwd(g.handle, B, P(x), P(w), P(bias), P(gamma),
+                                                                         P(beta), P(mean), P(var), 1e-5, 1, 0, P(out),
+                                                                         P(ws), WORKSPACE_BYTES, st)), 2 * U),
+        "gcn_bwd_nowgrad": (lambda: check(lib.eg_gcn_conv_bwd(g.handle, B, P(x), P(w), P(dy), P(h), P(out), None, None,
+                                                              P(scratch), P(ws), WORKSPACE_BYTES, st)), 4 * U),
         "linear128": (lambda: check(lib.eg_linear128(rows, P(x), P(w), 1, P(bias), None, P(h), P(mean), P(var),
                                                      P(ws), WORKSPACE_BYTES, st)), 2 * U),
         "wgrad128": (lambda: check(lib.eg_linear128_wgrad(rows, P(dy), P(x), P(dw), None, P(ws), WORKSPACE_BYTES,
