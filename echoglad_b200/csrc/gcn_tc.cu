@@ -1068,6 +1068,7 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
           emit2(a_hi, so_a + 2048, ac);
           emit2(a_hi, so_b + 2048, ad);
           release_op();
+#ifndef EG_PD_NOAGG
           if (agg_out) {  // A_hat dH side output: stored after the chunk is handed to the MMA
             float* o = agg_a + kc * 32;
             st_f2(o, aa);
@@ -1075,6 +1076,7 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
             st_f2(o + (long long)side * 128, ac);
             st_f2(o + (long long)side * 128 + 128, ad);
           }
+#endif
         }
       }
     }
@@ -1319,7 +1321,12 @@ __device__ __forceinline__ void tc_body(const TcParams& p, const PatchMaps* pm) 
         slab_rows(sl, base, cnt);
         const float* adp = p.addend + max(base, 0LL) * 128 + f;
 #pragma unroll
+#ifdef EG_PD_NORES
+        for (int i = 0; i < 16; ++i) ad[i] = (float)i;
+        (void)adp;
+#else
         for (int i = 0; i < 16; ++i) ad[i] = i < cnt ? __ldg(adp + i * 128) : 0.f;
+#endif
       };
       if (p.addend) load_res(0, adA);  // in flight across the wait for the accumulator
       TC_TIMED_WAIT(0, &acc_full[buf], acc_phase);
