@@ -237,12 +237,33 @@ def run_native(args):
         def step_resident():
             return fwd_bwd(frames_d, y_d, valid_d)
 
+        # e2e: every step copies its frames + landmark coordinates from pinned host memory and reads its loss back.
+        # The copies are double-buffered on a copy stream (what a pinned, prefetching DataLoader does): step i computes
+        # on buffer i % 2 while the input of step i + 1 lands in the other one -- whose last reader, step i - 1, has
+        # finished, because every step ends with the synchronising loss read.  One H2D and one D2H per step.
+        copy_stream = torch.cuda.Stream(device=dev)
+        in_bufs = [(frames_d, coords_d), (torch.empty_like(frames_d), torch.empty_like(coords_d))]
+        in_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        state = {"k": 0, "primed": False}
+
+        def prefetch(k):
+            with torch.cuda.stream(copy_stream):
+                in_bufs[k][0].copy_(frames_h, non_blocking=True)
+                in_bufs[k][1].copy_(coords_h, non_blocking=True)
+                in_ready[k].record(copy_stream)
+
         def step_e2e():
-            frames_d.copy_(frames_h, non_blocking=True)
-            coords_d.copy_(coords_h, non_blocking=True)
-            y, valid = synthetic.device_labels(coords_d, spec)
-            loss = fwd_bwd(frames_d, y, valid)
+            k = state["k"]
+            if not state["primed"]:  # very first call: nothing was prefetched yet
+                prefetch(k)
+                state["primed"] = True
+            prefetch(1 - k)  # the next step's input, in flight during this step
+            torch.cuda.current_stream().wait_event(in_ready[k])
+            frames, coords = in_bufs[k]
+            y, valid = synthetic.device_labels(coords, spec)
+            loss = fwd_bwd(frames, y, valid)
             loss_h.copy_(loss.detach(), non_blocking=False)  # D2H read of the step's result (synchronises)
+            state["k"] = 1 - k
             return loss_h
 
         return step_resident, step_e2e, frames_h, coords_h
