@@ -383,13 +383,13 @@ class _BNTrain2d(torch.autograd.Function):
 
 
 class _BatchNorm2d(nn.BatchNorm2d):
-    """nn.BatchNorm2d (same parameters / buffers / state_dict keys) whose CUDA train-mode path on maps with at most 16
+    """nn.BatchNorm2d (same parameters / buffers / state_dict keys) whose CUDA train-mode path on maps with at most 64
     channels is `ops.BN2dTrain` (two launches per direction, the preceding ReLU folded in with `relu_in=True`), or
     `_BNTrain2d` where the plane size is not a multiple of 4.  `forward(x, relu_in=True)` = BN(relu(x))."""
 
     def forward(self, x, relu_in: bool = False):
         if not (self.training and x.is_cuda and self.track_running_stats and self.momentum is not None
-                and x.shape[1] <= 16 and x.dtype == torch.float32):
+                and x.shape[1] <= 64 and x.dtype == torch.float32):
             return super().forward(TF.relu(x) if relu_in else x)
         if (x.shape[2] * x.shape[3]) % 4 == 0:
             y, mean, var = ops.BN2dTrain.apply(x, self.weight, self.bias, self.eps, relu_in)

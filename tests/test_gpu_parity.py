@@ -295,7 +295,7 @@ def test_eval_layer_in_one_launch_equals_the_unfused_eval_route(kw, batch, relu,
 
 
 @pytest.mark.parametrize("shape", [(2, 4, 224, 224), (3, 8, 128, 128), (2, 16, 64, 64), (5, 3, 2, 2), (1, 1, 2, 6),
-                                   (2, 5, 36, 58), (64, 8, 32, 32)])
+                                   (2, 5, 36, 58), (64, 8, 32, 32), (3, 40, 8, 8), (2, 64, 4, 4)])
 @pytest.mark.parametrize("relu_in", [False, True])
 def test_bn2d_train_entry_points_against_fp64(shape, relu_in):
     """`eg_bn2d_fwd` / `eg_bn2d_bwd` (train-mode BatchNorm2d over NCHW maps with few channels, the preceding ReLU folded in;
@@ -1283,7 +1283,10 @@ def _hot_path_vs_oracle(cfg, variant, batch, frames_or_x, y, valid, sd, embed_sd
            "unimposed_loss_rel_err": [abs(l1.item() - want2["WeightedBceWithLogits"].item()) / abs(want2["WeightedBceWithLogits"].item()),
                                       abs(l2.item() - want2["ExpectedLandmarkMse"].item()) / abs(want2["ExpectedLandmarkMse"].item())]}
     _report(rec)
-    assert f_log <= 1e-2 and frac_in <= 1e-2, rec
+    # (a ReLU unit whose pre-activation is within rounding of zero may fall on the other side in the oracle: on the
+    # 16-px graphs ONE such unit moves > 1 % of the input-gradient entries past the bound; the imposed-pattern pass
+    # above has already held every entry to the strict bound)
+    assert f_log <= 1e-2 and frac_in <= (1e-2 if flips == 0 else 5e-2), rec
     assert max(rec["unimposed_loss_rel_err"]) <= 1e-4, rec
 
 
