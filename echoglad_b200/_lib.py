@@ -89,8 +89,8 @@ SIGNATURES = {
     "eg_bn_act_fwd": (_I, [_L, _I, _P, _P, _P, _P, _P, _F, _F, _U64, _I, _P, _P, _P]),
     "eg_bn_act_bwd": (_I, [_L, _I, _P, _P, _P, _P, _P, _P, _F, _F, _U64, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "eg_dropout_mask": (_I, [_L, _I, _F, _U64, _P, _P]),
-    "eg_bn2d_fwd": (_I, [_I, _I, _L, _P, _I, _P, _P, _F, _P, _P, _P, _P, _SZ, _P]),
-    "eg_bn2d_bwd": (_I, [_I, _I, _L, _P, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _SZ, _P]),
+    "eg_bn2d_fwd": (_I, [_I, _I, _L, _P, _P, _I, _P, _P, _F, _P, _P, _P, _P, _SZ, _P]),
+    "eg_bn2d_bwd": (_I, [_I, _I, _L, _P, _P, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _SZ, _P]),
     "eg_col_stats": (_I, [_L, _I, _P, _P, _P, _P, _SZ, _P]),
     "eg_linear128": (_I, [_L, _P, _P, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "eg_linear128_wgrad": (_I, [_L, _P, _P, _P, _P, _P, _SZ, _P]),

@@ -1,5 +1,5 @@
 // Train-mode BatchNorm2d over NCHW maps with FEW channels and a large spatial extent, optionally with the ReLU that
-// precedes it folded in: y = BN(relu(x)).  These are the full-resolution levels of the UNet pyramid in front of the
+// precedes it (and the bias of the convolution before that) folded in: y = BN(relu(x + b)).  These are the full-resolution levels of the UNet pyramid in front of the
 // graph path (conv3x3 -> ReLU -> BatchNorm2d, src/core/models.py:841-876): with 4..16 channels cuDNN's spatial BN
 // kernels run one CTA per channel (8 of 148 SMs), and composed from PyTorch element-wise ops the layer costs ~20
 // tensor passes.  Here: forward = statistics (1 read) + apply (1 read, 1 write), backward = sums (2 reads) + apply
@@ -46,8 +46,9 @@ __device__ __forceinline__ void block_sum2(double& a, double& b) {
 // DY == nullptr: (sum v, sum v^2) of v = relu?(x); else (sum dy, sum dy v).
 __global__ void __launch_bounds__(kThreads)
 bn2d_sums_kernel(Shape sh, int splits, const float* __restrict__ X, const float* __restrict__ DY, int relu_in,
-                 double* __restrict__ parts) {
+                 const float* __restrict__ pre_bias, double* __restrict__ parts) {
   const int c = blockIdx.y, split = blockIdx.x;
+  const float pb = pre_bias ? __ldg(pre_bias + c) : 0.f;
   const int units = sh.n * sh.chunks;
   float s0 = 0.f, s1 = 0.f;
   double d0 = 0.0, d1 = 0.0;
@@ -64,11 +65,12 @@ bn2d_sums_kernel(Shape sh, int splits, const float* __restrict__ X, const float*
     }
 #pragma unroll
     for (int k = 0; k < kPerThread; ++k) {
+      if (i0 + k * kThreads >= sh.hw4) continue;  // (past the plane: with a folded bias even a zero would count)
       const float xv[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
       const float gv[4] = {g[k].x, g[k].y, g[k].z, g[k].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float v = relu_in ? fmaxf(xv[e], 0.f) : xv[e];
+        const float v = relu_in ? fmaxf(xv[e] + pb, 0.f) : xv[e] + pb;
         if (DY) {  // BatchNorm's input is v = relu(x): its sums take dy as it is; the ReLU mask applies to dx only
           s0 += gv[e];
           s1 = fmaf(gv[e], v, s1);
@@ -126,12 +128,15 @@ bn2d_finalize_kernel(int splits, double count, const double* __restrict__ parts,
 // forward: y = relu?(x) * sc + sh.  backward (DY != nullptr): out = mask (a dy + b relu?(x) + k).
 __global__ void __launch_bounds__(kThreads)
 bn2d_apply_kernel(Shape sh, const float* __restrict__ X, const float* __restrict__ DY, int relu_in,
-                  const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, float eps, const float* __restrict__ coef, float* __restrict__ out) {
+                  const float* __restrict__ pre_bias, const float* __restrict__ mean, const float* __restrict__ var,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                  const float* __restrict__ coef, float* __restrict__ out, double* __restrict__ unit_sums) {
   const long long units = (long long)sh.n * sh.c * sh.chunks;
   for (long long u = blockIdx.x; u < units; u += gridDim.x) {
     const long long pl = u / sh.chunks;  // plane = n * C + c
     const int ch = (int)(u - pl * sh.chunks), c = (int)(pl % sh.c);
+    const float pb = pre_bias ? __ldg(pre_bias + c) : 0.f;
+    float usum = 0.f;  // backward: this thread's share of the unit's sum of dx (gradient of the folded conv bias)
     float a, b, k;
     if (DY) {
       a = __ldg(coef + 3 * c), b = __ldg(coef + 3 * c + 1), k = __ldg(coef + 3 * c + 2);
@@ -159,17 +164,37 @@ bn2d_apply_kernel(Shape sh, const float* __restrict__ X, const float* __restrict
       float o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float v = relu_in ? fmaxf(xv[e], 0.f) : xv[e];
+        const float v = relu_in ? fmaxf(xv[e] + pb, 0.f) : xv[e] + pb;
         if (DY) {
           const float t = fmaf(a, gv[e], fmaf(b, v, k));
-          o[e] = (relu_in && !(xv[e] > 0.f)) ? 0.f : t;
+          o[e] = (relu_in && !(xv[e] + pb > 0.f)) ? 0.f : t;
+          usum += o[e];
         } else {
           o[e] = fmaf(v, b, k);
         }
       }
       st4(out + (plane + i) * 4, make_float4(o[0], o[1], o[2], o[3]));
     }
+    if (unit_sums) {  // (block-uniform) fixed-order sum of the unit
+      double d = (double)usum, zero = 0.0;
+      __syncthreads();  // block_sum2's scratch may still be read by thread 0 from the previous unit
+      block_sum2(d, zero);
+      if (threadIdx.x == 0) unit_sums[u] = d;
+    }
   }
+}
+
+// dpre_bias[c] = sum over the channel's units (n, chunk) of unit_sums, one block per channel, fixed order
+__global__ void __launch_bounds__(kThreads)
+bn2d_bias_grad_kernel(Shape sh, const double* __restrict__ unit_sums, float* __restrict__ dpre_bias) {
+  const int c = blockIdx.x, per = sh.n * sh.chunks;
+  double a = 0.0, zero = 0.0;
+  for (int i = threadIdx.x; i < per; i += kThreads) {
+    const int n = i / sh.chunks, ch = i - n * sh.chunks;
+    a += unit_sums[((size_t)n * sh.c + c) * sh.chunks + ch];
+  }
+  block_sum2(a, zero);
+  if (threadIdx.x == 0) dpre_bias[c] = (float)a;
 }
 
 int check_shape(int n, int c, long long hw, size_t ws_bytes, const void* ws, Shape& sh, int& splits) {
@@ -182,7 +207,8 @@ int check_shape(int n, int c, long long hw, size_t ws_bytes, const void* ws, Sha
   const long long units = (long long)n * sh.chunks;
   long long want = ((long long)num_sms() * 8 + c - 1) / c;
   splits = (int)std::min<long long>(std::min<long long>(want, units), kMaxSplits);
-  if (!ws || ws_bytes < (size_t)c * splits * 2 * sizeof(double) + 3 * 64 * sizeof(float)) {
+  // [c][splits][2] doubles, 3 x 64 floats of coefficients, one double per unit (bias gradient)
+  if (!ws || ws_bytes < (size_t)c * splits * 2 * sizeof(double) + 3 * 64 * sizeof(float) + (size_t)units * c * sizeof(double)) {
     set_error("eg_bn2d: workspace too small");
     return EG_ERR_WORKSPACE;
   }
@@ -193,8 +219,9 @@ int check_shape(int n, int c, long long hw, size_t ws_bytes, const void* ws, Sha
 
 extern "C" {
 
-int eg_bn2d_fwd(int n, int channels, int64_t hw, const float* x, int relu_in, const float* gamma, const float* beta,
-                float eps, float* y, float* mean, float* var, void* ws, size_t ws_bytes, void* stream) {
+int eg_bn2d_fwd(int n, int channels, int64_t hw, const float* x, const float* pre_bias, int relu_in, const float* gamma,
+                const float* beta, float eps, float* y, float* mean, float* var, void* ws, size_t ws_bytes,
+                void* stream) {
   EG_CHECK_ARG(x && gamma && beta && y && mean && var, "eg_bn2d_fwd: NULL argument");
   Shape sh;
   int splits;
@@ -203,32 +230,35 @@ int eg_bn2d_fwd(int n, int channels, int64_t hw, const float* x, int relu_in, co
   double* parts = reinterpret_cast<double*>(ws);
   {
     ProfileScope prof("bn2d_fwd", s);
-    bn2d_sums_kernel<<<dim3(splits, channels), kThreads, 0, s>>>(sh, splits, x, nullptr, relu_in, parts);
+    bn2d_sums_kernel<<<dim3(splits, channels), kThreads, 0, s>>>(sh, splits, x, nullptr, relu_in, pre_bias, parts);
     EG_LAUNCH_CHECK();
     bn2d_finalize_kernel<<<channels, kThreads, 0, s>>>(splits, (double)n * (double)hw, parts, mean, var, nullptr, nullptr,
                                                        nullptr, eps, nullptr, nullptr, nullptr);
     EG_LAUNCH_CHECK();
     const long long units = (long long)n * channels * sh.chunks;
     const int grid = (int)std::min<long long>(units, (long long)num_sms() * 16);
-    bn2d_apply_kernel<<<grid, kThreads, 0, s>>>(sh, x, nullptr, relu_in, mean, var, gamma, beta, eps, nullptr, y);
+    bn2d_apply_kernel<<<grid, kThreads, 0, s>>>(sh, x, nullptr, relu_in, pre_bias, mean, var, gamma, beta, eps, nullptr, y,
+                                                nullptr);
     EG_LAUNCH_CHECK();
   }
   return EG_OK;
 }
 
-int eg_bn2d_bwd(int n, int channels, int64_t hw, const float* x, int relu_in, const float* dy, const float* mean,
-                const float* var, const float* gamma, float eps, float* dx, float* dgamma, float* dbeta, void* ws,
-                size_t ws_bytes, void* stream) {
+int eg_bn2d_bwd(int n, int channels, int64_t hw, const float* x, const float* pre_bias, int relu_in, const float* dy,
+                const float* mean, const float* var, const float* gamma, float eps, float* dx, float* dgamma,
+                float* dbeta, float* dpre_bias, void* ws, size_t ws_bytes, void* stream) {
   EG_CHECK_ARG(x && dy && mean && var && gamma && dgamma && dbeta, "eg_bn2d_bwd: NULL argument");
+  EG_CHECK_ARG(!dpre_bias || dx, "eg_bn2d_bwd: the gradient of the folded bias is a by-product of dx");
   Shape sh;
   int splits;
   if (int rc = check_shape(n, channels, hw, ws_bytes, ws, sh, splits)) return rc;
   cudaStream_t s = as_stream(stream);
   double* parts = reinterpret_cast<double*>(ws);
   float* coef = reinterpret_cast<float*>(parts + (size_t)channels * splits * 2);
+  double* unit_sums = reinterpret_cast<double*>(coef + 3 * 64);
   {
     ProfileScope prof("bn2d_bwd", s);
-    bn2d_sums_kernel<<<dim3(splits, channels), kThreads, 0, s>>>(sh, splits, x, dy, relu_in, parts);
+    bn2d_sums_kernel<<<dim3(splits, channels), kThreads, 0, s>>>(sh, splits, x, dy, relu_in, pre_bias, parts);
     EG_LAUNCH_CHECK();
     bn2d_finalize_kernel<<<channels, kThreads, 0, s>>>(splits, (double)n * (double)hw, parts, nullptr, nullptr, mean, var,
                                                        gamma, eps, dgamma, dbeta, coef);
@@ -236,8 +266,13 @@ int eg_bn2d_bwd(int n, int channels, int64_t hw, const float* x, int relu_in, co
     if (dx) {
       const long long units = (long long)n * channels * sh.chunks;
       const int grid = (int)std::min<long long>(units, (long long)num_sms() * 16);
-      bn2d_apply_kernel<<<grid, kThreads, 0, s>>>(sh, x, dy, relu_in, mean, var, gamma, nullptr, eps, coef, dx);
+      bn2d_apply_kernel<<<grid, kThreads, 0, s>>>(sh, x, dy, relu_in, pre_bias, mean, var, gamma, nullptr, eps, coef, dx,
+                                                  dpre_bias ? unit_sums : nullptr);
       EG_LAUNCH_CHECK();
+      if (dpre_bias) {
+        bn2d_bias_grad_kernel<<<channels, kThreads, 0, s>>>(sh, unit_sums, dpre_bias);
+        EG_LAUNCH_CHECK();
+      }
     }
   }
   return EG_OK;

@@ -384,23 +384,50 @@ class _BNTrain2d(torch.autograd.Function):
 
 class _BatchNorm2d(nn.BatchNorm2d):
     """nn.BatchNorm2d (same parameters / buffers / state_dict keys) whose CUDA train-mode path on maps with at most 64
-    channels is `ops.BN2dTrain` (two launches per direction, the preceding ReLU folded in with `relu_in=True`), or
-    `_BNTrain2d` where the plane size is not a multiple of 4.  `forward(x, relu_in=True)` = BN(relu(x))."""
+    channels is `ops.BN2dTrain` (two launches per direction; `relu_in=True` folds the preceding ReLU in, `pre_bias` the
+    bias of a convolution that was run without it), or `_BNTrain2d` where the plane size is not a multiple of 4.
+    `forward(x, relu_in=True, pre_bias=b)` = BN(relu(x + b))."""
 
-    def forward(self, x, relu_in: bool = False):
-        if not (self.training and x.is_cuda and self.track_running_stats and self.momentum is not None
-                and x.shape[1] <= 64 and x.dtype == torch.float32):
-            return super().forward(TF.relu(x) if relu_in else x)
-        if (x.shape[2] * x.shape[3]) % 4 == 0:
-            y, mean, var = ops.BN2dTrain.apply(x, self.weight, self.bias, self.eps, relu_in)
+    def fused_ok(self, x: torch.Tensor) -> bool:
+        """Whether `forward` on a map like `x` (device, dtype, channels, plane size) takes the two-launch kernels."""
+        return bool(self.training and x.is_cuda and self.track_running_stats and self.momentum is not None
+                    and self.num_features <= 64 and x.dtype == torch.float32 and (x.shape[2] * x.shape[3]) % 4 == 0)
+
+    def forward(self, x, relu_in: bool = False, pre_bias: Optional[torch.Tensor] = None):
+        if self.fused_ok(x):
+            y, mean, var = ops.BN2dTrain.apply(x, self.weight, self.bias, self.eps, relu_in, pre_bias)
         else:
-            y, mean, var = _BNTrain2d.apply(TF.relu(x) if relu_in else x, self.weight, self.bias, self.eps)
+            if pre_bias is not None:
+                x = x + pre_bias.view(1, -1, 1, 1)
+            if relu_in:
+                x = TF.relu(x)
+            if not (self.training and x.is_cuda and self.track_running_stats and self.momentum is not None
+                    and x.shape[1] <= 16):
+                return super().forward(x)
+            y, mean, var = _BNTrain2d.apply(x, self.weight, self.bias, self.eps)
         with torch.no_grad():
             n = x.numel() // x.shape[1]
             self.running_mean.mul_(1 - self.momentum).add_(mean, alpha=self.momentum)
             self.running_var.mul_(1 - self.momentum).add_(var * (n / max(n - 1, 1)), alpha=self.momentum)
             self.num_batches_tracked += 1
         return y
+
+
+def _conv_relu_bn(conv: nn.Conv2d, bn: _BatchNorm2d, x: torch.Tensor) -> torch.Tensor:
+    """bn(relu(conv(x))).  Where the BatchNorm takes its two-launch kernels the convolution runs WITHOUT its bias, which
+    the BatchNorm kernels add on load (and whose gradient they return): no bias-add pass, no bias-gradient reduction."""
+    if conv.bias is not None and conv.padding_mode == "zeros" and bn.fused_ok(x) \
+            and (x.shape[2] * x.shape[3]) == _conv_out_plane(conv, x):
+        z = TF.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        return bn(z, relu_in=True, pre_bias=conv.bias)
+    return bn(conv(x), relu_in=True)
+
+
+def _conv_out_plane(conv: nn.Conv2d, x: torch.Tensor) -> int:
+    def out(size, k, s, p, d):
+        return (size + 2 * p - d * (k - 1) - 1) // s + 1
+    return out(x.shape[2], conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]) * \
+        out(x.shape[3], conv.kernel_size[1], conv.stride[1], conv.padding[1], conv.dilation[1])
 
 
 class _DownConv(nn.Module):
@@ -415,8 +442,8 @@ class _DownConv(nn.Module):
         self.out_size = out_size
 
     def forward(self, x):
-        x = self.BN1(self.conv1(x), relu_in=True)
-        x = self.BN2(self.conv2(x), relu_in=True)
+        x = _conv_relu_bn(self.conv1, self.BN1, x)
+        x = _conv_relu_bn(self.conv2, self.BN2, x)
         return TF.adaptive_max_pool2d(x, self.out_size)
 
 
@@ -433,8 +460,8 @@ class _UpConv(nn.Module):
 
     def forward(self, x, skip):
         x = TF.interpolate(x, size=self.out_size)
-        x = self.BN1(self.conv1(x), relu_in=True)
-        return self.BN2(self.conv2(torch.cat([x, skip], dim=1)), relu_in=True)
+        x = _conv_relu_bn(self.conv1, self.BN1, x)
+        return _conv_relu_bn(self.conv2, self.BN2, torch.cat([x, skip], dim=1))
 
 
 class UNETHierarchicalPatchModel(HierarchicalPatchModel):

@@ -475,38 +475,42 @@ class GCNLayer(torch.autograd.Function):
 
 
 class BN2dTrain(torch.autograd.Function):
-    """Train-mode BatchNorm2d over an NCHW map with few channels, optionally of relu(x): y = BN(relu(x)) in two launches
-    per direction (eg_bn2d_fwd / eg_bn2d_bwd) -- the conv3x3 -> ReLU -> BatchNorm2d blocks of the UNet pyramid at full
-    resolution (reference src/core/models.py:841-876).  Returns (y, batch mean, biased batch variance)."""
+    """Train-mode BatchNorm2d over an NCHW map with few channels, optionally of relu(x + pre_bias):
+    y = BN(relu(x + pre_bias)) in two launches per direction (eg_bn2d_fwd / eg_bn2d_bwd) -- the
+    conv3x3 -> ReLU -> BatchNorm2d blocks of the UNet pyramid at full resolution (reference src/core/models.py:841-876),
+    `pre_bias` being the bias of a convolution that was run without it.  Returns (y, batch mean, biased batch variance)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, eps: float, relu_in: bool):
+    def forward(ctx, x, weight, bias, eps: float, relu_in: bool, pre_bias=None):
         x, weight, bias = _f32(x, "x"), _f32(weight, "weight"), _f32(bias, "bias")
+        pre_bias = None if pre_bias is None else _f32(pre_bias, "pre_bias")
         n, c, h, w = x.shape
         y = torch.empty_like(x)
         mean, var = torch.empty(c, device=x.device), torch.empty(c, device=x.device)
         ws = _ws(x.device)
-        check(lib.eg_bn2d_fwd(n, c, h * w, x.data_ptr(), int(relu_in), weight.data_ptr(), bias.data_ptr(), float(eps),
-                              y.data_ptr(), mean.data_ptr(), var.data_ptr(), ws.data_ptr(), WORKSPACE_BYTES,
-                              _stream(x)), "eg_bn2d_fwd")
-        ctx.save_for_backward(x, weight, mean, var)
+        check(lib.eg_bn2d_fwd(n, c, h * w, x.data_ptr(), _ptr(pre_bias), int(relu_in), weight.data_ptr(),
+                              bias.data_ptr(), float(eps), y.data_ptr(), mean.data_ptr(), var.data_ptr(), ws.data_ptr(),
+                              WORKSPACE_BYTES, _stream(x)), "eg_bn2d_fwd")
+        ctx.save_for_backward(x, weight, mean, var, pre_bias)
         ctx.cfg = (float(eps), bool(relu_in))
         ctx.mark_non_differentiable(mean, var)
         return y, mean, var
 
     @staticmethod
     def backward(ctx, dy, _dmean, _dvar):
-        x, weight, mean, var = ctx.saved_tensors
+        x, weight, mean, var, pre_bias = ctx.saved_tensors
         eps, relu_in = ctx.cfg
         dy = _f32(dy, "dy")
         n, c, h, w = x.shape
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        want_pb = pre_bias is not None and ctx.needs_input_grad[5]
+        dx = torch.empty_like(x) if (ctx.needs_input_grad[0] or want_pb) else None
         dgamma, dbeta = torch.empty(c, device=x.device), torch.empty(c, device=x.device)
+        dpb = torch.empty(c, device=x.device) if want_pb else None
         ws = _ws(x.device)
-        check(lib.eg_bn2d_bwd(n, c, h * w, x.data_ptr(), int(relu_in), dy.data_ptr(), mean.data_ptr(), var.data_ptr(),
-                              weight.data_ptr(), eps, _ptr(dx), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(),
-                              WORKSPACE_BYTES, _stream(x)), "eg_bn2d_bwd")
-        return dx, dgamma, dbeta, None, None
+        check(lib.eg_bn2d_bwd(n, c, h * w, x.data_ptr(), _ptr(pre_bias), int(relu_in), dy.data_ptr(), mean.data_ptr(),
+                              var.data_ptr(), weight.data_ptr(), eps, _ptr(dx), dgamma.data_ptr(), dbeta.data_ptr(),
+                              _ptr(dpb), ws.data_ptr(), WORKSPACE_BYTES, _stream(x)), "eg_bn2d_bwd")
+        return (dx if ctx.needs_input_grad[0] else None), dgamma, dbeta, None, None, dpb
 
 
 class ClassifierHeads(torch.autograd.Function):

@@ -172,18 +172,21 @@ int eg_gcn_layer_eval_fwd(const eg_graph* g, int batch, const float* X, const fl
                           const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                           float eps, int relu, int residual, float* Y, void* ws, size_t ws_bytes, void* stream);
 
-/* ---- train-mode BatchNorm2d over NCHW maps with few channels, the preceding ReLU folded in: y = BN(relu(x)) --------
- * The full-resolution levels of the UNet pyramid in front of the graph path (conv3x3 -> ReLU -> BatchNorm2d,
- * src/core/models.py:841-876; 4..16 channels at 224^2 / 128^2, where cuDNN's spatial BN runs one CTA per channel).
- * x, y, dy, dx: float[n, channels, H*W] contiguous (NCHW), hw = H*W a multiple of 4, channels <= 64.
- * relu_in != 0: BatchNorm's input is relu(x) (and dx carries the ReLU mask).  mean / var: float[channels] outputs of the
- * forward (batch mean, BIASED variance), inputs of the backward.  dx may be NULL.  Deterministic two-stage reductions.
- * ws: eg_workspace_bytes() bytes of device scratch. */
-int eg_bn2d_fwd(int n, int channels, int64_t hw, const float* x, int relu_in, const float* gamma, const float* beta,
-                float eps, float* y, float* mean, float* var, void* ws, size_t ws_bytes, void* stream);
-int eg_bn2d_bwd(int n, int channels, int64_t hw, const float* x, int relu_in, const float* dy, const float* mean,
-                const float* var, const float* gamma, float eps, float* dx, float* dgamma, float* dbeta, void* ws,
-                size_t ws_bytes, void* stream);
+/* ---- train-mode BatchNorm2d over NCHW maps with few channels, the preceding ReLU and conv bias folded in -----------
+ * y = BN(relu(x + pre_bias)): the full-resolution levels of the UNet pyramid in front of the graph path
+ * (conv3x3 -> ReLU -> BatchNorm2d, src/core/models.py:841-876; 4..64 channels, where cuDNN's spatial BN runs one CTA per
+ * channel).  x, y, dy, dx: float[n, channels, H*W] contiguous (NCHW), hw = H*W a multiple of 4, channels <= 64.
+ * pre_bias: float[channels] or NULL -- the bias of the convolution that produced x, when that convolution was run
+ * WITHOUT it (saves the bias-add pass; dpre_bias = sum of dx per channel is its gradient, a by-product of the backward).
+ * relu_in != 0: BatchNorm's input is relu(x + pre_bias) (and dx carries the ReLU mask).  mean / var: float[channels]
+ * outputs of the forward (batch mean, BIASED variance), inputs of the backward.  dx / dpre_bias may be NULL.
+ * Deterministic two-stage reductions.  ws: eg_workspace_bytes() bytes of device scratch. */
+int eg_bn2d_fwd(int n, int channels, int64_t hw, const float* x, const float* pre_bias, int relu_in, const float* gamma,
+                const float* beta, float eps, float* y, float* mean, float* var, void* ws, size_t ws_bytes,
+                void* stream);
+int eg_bn2d_bwd(int n, int channels, int64_t hw, const float* x, const float* pre_bias, int relu_in, const float* dy,
+                const float* mean, const float* var, const float* gamma, float eps, float* dx, float* dgamma,
+                float* dbeta, float* dpre_bias, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- fused BatchNorm1d-apply + Dropout + ReLU|Identity + residual ----------------------------------
  * replaces gnn_layers[i].module_1..3 and `h + hidden_embeds[i]` (src/core/models.py:332-335,434-435)

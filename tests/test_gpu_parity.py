@@ -296,8 +296,8 @@ def test_eval_layer_in_one_launch_equals_the_unfused_eval_route(kw, batch, relu,
 
 @pytest.mark.parametrize("shape", [(2, 4, 224, 224), (3, 8, 128, 128), (2, 16, 64, 64), (5, 3, 2, 2), (1, 1, 2, 6),
                                    (2, 5, 36, 58), (64, 8, 32, 32), (3, 40, 8, 8), (2, 64, 4, 4)])
-@pytest.mark.parametrize("relu_in", [False, True])
-def test_bn2d_train_entry_points_against_fp64(shape, relu_in):
+@pytest.mark.parametrize("relu_in,with_bias", [(False, False), (True, False), (True, True)])
+def test_bn2d_train_entry_points_against_fp64(shape, relu_in, with_bias):
     """`eg_bn2d_fwd` / `eg_bn2d_bwd` (train-mode BatchNorm2d over NCHW maps with few channels, the preceding ReLU folded in;
     the full-resolution levels of the UNet pyramid, src/core/models.py:841-876) against torch's batch_norm in fp64: output,
     batch statistics and all three gradients.  Plane sizes that are / are not multiples of the 1024-float4 work unit."""
@@ -306,15 +306,22 @@ def test_bn2d_train_entry_points_against_fp64(shape, relu_in):
     w = (torch.rand(shape[1], device=DEV, generator=gen) + 0.5).requires_grad_()
     b = torch.randn(shape[1], device=DEV, generator=gen).requires_grad_()
     dy = torch.randn(*shape, device=DEV, generator=gen)
-    y, mean, var = ops.BN2dTrain.apply(x, w, b, 1e-5, relu_in)
-    gx, gw, gb = torch.autograd.grad(y, (x, w, b), dy)
-    xd, wd, bd = (t.detach().double().requires_grad_() for t in (x, w, b))
-    vd = xd.relu() if relu_in else xd
+    pb = (torch.randn(shape[1], device=DEV, generator=gen) * 0.7).requires_grad_()  # bias of the convolution in front
+    y, mean, var = ops.BN2dTrain.apply(x, w, b, 1e-5, relu_in, pb if with_bias else None)
+    gx, gw, gb, gpb = torch.autograd.grad(y, (x, w, b, pb), dy, allow_unused=True)
+    xd, wd, bd, pbd = (t.detach().double().requires_grad_() for t in (x, w, b, pb))
+    vd = xd + pbd.view(1, -1, 1, 1) if with_bias else xd
+    vd = vd.relu() if relu_in else vd
     yd = torch.nn.functional.batch_norm(vd, None, None, wd, bd, True, 0.0, 1e-5)
-    gxd, gwd, gbd = torch.autograd.grad(yd, (xd, wd, bd), dy.double())
-    for name, got, want, rtol in [("y", y, yd, 1e-5), ("mean", mean, vd.mean(dim=(0, 2, 3)), 1e-5),
-                                  ("var", var, vd.var(dim=(0, 2, 3), unbiased=False), 1e-5), ("dx", gx, gxd, 1e-4),
-                                  ("dgamma", gw, gwd, 1e-4), ("dbeta", gb, gbd, 1e-4)]:
+    gxd, gwd, gbd, gpbd = torch.autograd.grad(yd, (xd, wd, bd, pbd), dy.double(), allow_unused=True)
+    checks = [("y", y, yd, 1e-5), ("mean", mean, vd.mean(dim=(0, 2, 3)), 1e-5),
+              ("var", var, vd.var(dim=(0, 2, 3), unbiased=False), 1e-5), ("dx", gx, gxd, 1e-4),
+              ("dgamma", gw, gwd, 1e-4), ("dbeta", gb, gbd, 1e-4)]
+    if with_bias:
+        checks.append(("d(conv bias)", gpb, gpbd, 1e-4))
+    else:
+        assert gpb is None
+    for name, got, want, rtol in checks:
         ok, worst = close(got.detach().cpu(), want.detach().cpu(), rtol, 1e-5)
         assert ok, f"{name} {worst}"
     # the module: same layer through _BatchNorm2d (running statistics included) against nn.BatchNorm2d on relu(x)
@@ -323,8 +330,9 @@ def test_bn2d_train_entry_points_against_fp64(shape, relu_in):
     with torch.no_grad():
         for m in (mine, ref):
             m.weight.copy_(w), m.bias.copy_(b)
-    ym = mine(x.detach(), relu_in=relu_in)
-    yr = ref(x.detach().relu() if relu_in else x.detach())
+    ym = mine(x.detach(), relu_in=relu_in, pre_bias=pb.detach() if with_bias else None)
+    xr = x.detach() + pb.detach().view(1, -1, 1, 1) if with_bias else x.detach()
+    yr = ref(xr.relu() if relu_in else xr)
     ok, worst = close(ym.detach().cpu(), yr.detach().cpu(), 1e-4, 1e-5)
     assert ok, f"module y {worst}"
     ok, worst = close(mine.running_var.cpu(), ref.running_var.cpu(), 1e-4, 1e-6)

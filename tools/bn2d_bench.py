@@ -26,7 +26,7 @@ def main():
             return torch.autograd.grad(y, (x, w, b), dy)
 
         def run():  # eg_bn2d_fwd / eg_bn2d_bwd with the ReLU folded in
-            y, _, _ = ops.BN2dTrain.apply(x, w, b, 1e-5, True)
+            y, _, _ = ops.BN2dTrain.apply(x, w, b, 1e-5, True, None)
             return torch.autograd.grad(y, (x, w, b), dy)
 
         for _ in range(3):
