@@ -1,10 +1,11 @@
-// Train-mode BatchNorm2d over NCHW maps with FEW channels and a large spatial extent, optionally with the ReLU that
-// precedes it (and the bias of the convolution before that) folded in: y = BN(relu(x + b)).  These are the full-resolution levels of the UNet pyramid in front of the
-// graph path (conv3x3 -> ReLU -> BatchNorm2d, src/core/models.py:841-876): with 4..16 channels cuDNN's spatial BN
-// kernels run one CTA per channel (8 of 148 SMs), and composed from PyTorch element-wise ops the layer costs ~20
-// tensor passes.  Here: forward = statistics (1 read) + apply (1 read, 1 write), backward = sums (2 reads) + apply
-// (2 reads, 1 write); the ReLU costs no pass of its own.  HBM / L2 bound element-wise work: 128-bit accesses, fixed-order
-// two-stage reductions in double (deterministic).
+// Train-mode BatchNorm2d over NCHW maps with FEW channels and a large spatial extent, with the ReLU that precedes it and
+// the bias of the convolution before that folded in: y = BN(relu(x + b)).  These are the conv3x3 -> ReLU -> BatchNorm2d
+// blocks of the UNet pyramid in front of the graph path (src/core/models.py:841-876): with 4..64 channels cuDNN's
+// spatial BN kernels run one CTA per channel (8..64 of 148 SMs), and composed from PyTorch element-wise ops the layer
+// costs ~23 tensor passes.  Here: forward = statistics (1 read) + apply (1 read, 1 write), backward = sums (2 reads) +
+// apply (2 reads, 1 write); the ReLU and the bias cost no pass of their own, the bias gradient is a by-product of the
+// backward apply.  HBM / L2 bound element-wise work: 128-bit accesses, fixed-order two-stage reductions in double
+// (deterministic).
 // Work unit = (frame n, channel c, chunk of kChunk float4 of the H*W plane); plane size must be a multiple of 4.
 #include "common.cuh"
 
@@ -20,10 +21,6 @@ constexpr int kMaxSplits = 1024;                  // partial sums per channel
 struct Shape {
   int n, c, hw4, chunks;  // frames, channels, float4 per plane, units per plane
 };
-
-__device__ __forceinline__ float4 relu4(float4 v) {
-  return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
-}
 
 // block-wide sum of two doubles in a fixed order; result valid in thread 0
 __device__ __forceinline__ void block_sum2(double& a, double& b) {
