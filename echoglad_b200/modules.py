@@ -413,14 +413,15 @@ class _BatchNorm2d(nn.BatchNorm2d):
         return y
 
 
-def _conv_relu_bn(conv: nn.Conv2d, bn: _BatchNorm2d, x: torch.Tensor) -> torch.Tensor:
-    """bn(relu(conv(x))).  Where the BatchNorm takes its two-launch kernels the convolution runs WITHOUT its bias, which
-    the BatchNorm kernels add on load (and whose gradient they return): no bias-add pass, no bias-gradient reduction."""
+def _conv_relu_bn(conv: nn.Conv2d, bn: _BatchNorm2d, x: torch.Tensor, relu: bool = True) -> torch.Tensor:
+    """bn(relu(conv(x))) (`relu=False`: bn(conv(x))).  Where the BatchNorm takes its two-launch kernels the convolution
+    runs WITHOUT its bias, which the BatchNorm kernels add on load (and whose gradient they return): no bias-add pass, no
+    bias-gradient reduction."""
     if conv.bias is not None and conv.padding_mode == "zeros" and bn.fused_ok(x) \
             and (x.shape[2] * x.shape[3]) == _conv_out_plane(conv, x):
         z = TF.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
-        return bn(z, relu_in=True, pre_bias=conv.bias)
-    return bn(conv(x), relu_in=True)
+        return bn(z, relu_in=relu, pre_bias=conv.bias)
+    return bn(conv(x), relu_in=relu)
 
 
 def _conv_out_plane(conv: nn.Conv2d, x: torch.Tensor) -> int:
@@ -534,11 +535,15 @@ class CNN(nn.Module):
             self.conv = nn.Conv2d(cin, cout, k, padding=(k - 1) // 2)
             self.bn = _BatchNorm2d(cout)
             self.pool = nn.MaxPool2d(pool)
+            self.pool_size = pool
             self.dropout = nn.Dropout2d(p)
 
         def forward(self, x):
             res = x if self.one_by_one_cnn is None else self.one_by_one_cnn(x)
-            return self.dropout(TF.relu(self.pool(self.bn(self.conv(x)) + res)))
+            y = _conv_relu_bn(self.conv, self.bn, x, relu=False) + res
+            if self.pool_size != 1:  # (MaxPool2d(1) is the identity, but costs a pass, an int64 index map and a backward)
+                y = self.pool(y)
+            return self.dropout(TF.relu(y))
 
     def __init__(self, out_channels: list, kernel_sizes: list = None, pool_sizes: list = None,
                  fc_output_dim: list = None, cnn_dropout_p: float = 0.0):

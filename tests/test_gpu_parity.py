@@ -10,6 +10,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as TF
 
 from oracle import restated as R
 from tests._golden import GOLDEN, MODEL_CASES, close, grads_close, load_case
@@ -339,6 +340,39 @@ def test_bn2d_train_entry_points_against_fp64(shape, relu_in, with_bias):
     assert ok, f"running_var {worst}"
     ok, worst = close(mine.running_mean.cpu(), ref.running_mean.cpu(), 1e-4, 1e-6)
     assert ok, f"running_mean {worst}"
+
+
+def test_cnn_embedder_block_against_fp64_restatement():
+    """The default.yml embedder block (src/core/models.py:71-260: conv3x3 -> BatchNorm2d, + 1x1-conv residual, MaxPool2d(1),
+    ReLU) as the module runs it on the device -- convolution without its bias, BatchNorm2d kernels with the bias folded in,
+    the identity pool skipped -- against the textbook composition in fp64: output and every parameter / input gradient."""
+    emb = eg.CNN(out_channels=[4], kernel_sizes=[3], pool_sizes=[1], cnn_dropout_p=0.0).to(DEV).train()
+    gen = torch.Generator(device=DEV).manual_seed(77)
+    with torch.no_grad():
+        for p in emb.parameters():
+            p.copy_(torch.randn(p.shape, device=DEV, generator=gen) * 0.5 + 0.1)
+    x = torch.randn(3, 1, 36, 40, device=DEV, generator=gen).requires_grad_()
+    dy = torch.randn(3, 4, 36, 40, device=DEV, generator=gen)
+    y = emb(x)
+    params = dict(emb.named_parameters())
+    got = torch.autograd.grad(y, [x] + list(params.values()), dy)
+    blk = "conv.0.0."
+    pd = {k: v.detach().double().requires_grad_() for k, v in params.items()}
+    xd = x.detach().double().requires_grad_()
+    z = TF.conv2d(xd, pd[blk + "conv.weight"], pd[blk + "conv.bias"], padding=1)
+    z = TF.batch_norm(z, None, None, pd[blk + "bn.weight"], pd[blk + "bn.bias"], True, 0.0, 1e-5)
+    res = TF.conv2d(xd, pd[blk + "one_by_one_cnn.weight"], pd[blk + "one_by_one_cnn.bias"])
+    yd = TF.relu(TF.max_pool2d(z + res, 1))
+    want = torch.autograd.grad(yd, [xd] + list(pd.values()), dy.double())
+    ok, worst = close(y.detach().cpu(), yd.detach().cpu(), 1e-4, 1e-5)
+    assert ok, f"y {worst}"
+    scale = max(float(b.abs().max()) for b in want)
+    for name, a, b in zip(["x"] + list(params), got, want):
+        if name.endswith(".conv.bias"):  # a bias in front of a train-mode BatchNorm: its gradient is identically zero
+            assert float(a.abs().max()) <= 1e-5 * scale and float(b.abs().max()) <= 1e-9 * scale, name
+            continue
+        ok, worst = close(a.cpu(), b.cpu(), 1e-3, 1e-4)
+        assert ok, f"d {name}: {worst}"
 
 
 # ---- dense transforms -----------------------------------------------------------------------------------------
