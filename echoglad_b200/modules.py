@@ -390,8 +390,11 @@ class _BatchNorm2d(nn.BatchNorm2d):
 
     def fused_ok(self, x: torch.Tensor) -> bool:
         """Whether `forward` on a map like `x` (device, dtype, channels, plane size) takes the two-launch kernels."""
+        plane = x.shape[2] * x.shape[3]
+        units = x.shape[0] * self.num_features * -(-plane // 4096)  # 16 KB work units: one double each of scratch
         return bool(self.training and x.is_cuda and self.track_running_stats and self.momentum is not None
-                    and self.num_features <= 64 and x.dtype == torch.float32 and (x.shape[2] * x.shape[3]) % 4 == 0)
+                    and self.num_features <= 64 and x.dtype == torch.float32 and plane % 4 == 0
+                    and units * 8 <= ops.WORKSPACE_BYTES // 2)
 
     def forward(self, x, relu_in: bool = False, pre_bias: Optional[torch.Tensor] = None):
         if self.fused_ok(x):
