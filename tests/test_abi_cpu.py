@@ -282,3 +282,24 @@ def test_evaluator_host_arithmetic_matches_reference_golden(eg, monkeypatch):
             want = float(z[f"{name}/compute/{k}"])
             assert abs(v - want) <= 1e-5 * max(abs(want), 1.0), (name, k)
         assert abs(ev.get_sum_of_width_MAE() - sum(float(z[f"{name}/compute/{k}"]) for k in ("ivs_w", "lvid_w", "lvpw_w"))) < 1e-3
+
+
+def test_pyramid_blocks_fall_back_to_plain_pytorch_off_the_device(eg):
+    """conv -> ReLU -> BatchNorm2d blocks of the pyramid and the embedder block: where the BatchNorm2d kernels do not
+    apply (CPU tensors here; eval mode, > 64 channels or odd plane sizes on the device) the modules run the textbook
+    PyTorch composition with the reference's parameters (src/core/models.py:71-260,841-876)."""
+    import torch.nn.functional as TF
+    from echoglad_b200.modules import _DownConv
+    torch.manual_seed(0)
+    blk = _DownConv(3, 5, 4).train()
+    x = torch.randn(2, 3, 9, 7)
+    want = TF.batch_norm(TF.relu(blk.conv1(x)), None, None, blk.BN1.weight, blk.BN1.bias, True, 0.1, 1e-5)
+    want = TF.batch_norm(TF.relu(blk.conv2(want)), None, None, blk.BN2.weight, blk.BN2.bias, True, 0.1, 1e-5)
+    want = TF.adaptive_max_pool2d(want, 4)
+    assert torch.allclose(blk(x), want, atol=1e-6)
+    assert int(blk.BN1.num_batches_tracked) == 1 and not blk.BN1.fused_ok(x)
+    emb = eg.CNN(out_channels=[4], kernel_sizes=[3], pool_sizes=[1], cnn_dropout_p=0.0).train()
+    b = emb.conv[0][0]
+    f = torch.randn(2, 1, 10, 6)
+    z = TF.batch_norm(b.conv(f), None, None, b.bn.weight, b.bn.bias, True, 0.1, 1e-5) + b.one_by_one_cnn(f)
+    assert torch.allclose(emb(f), TF.relu(z), atol=1e-6)
